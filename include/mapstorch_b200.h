@@ -1,0 +1,129 @@
+/*
+ * mapstorch_b200 -- C ABI of the B200-native per-pixel XRF map-fitting hot path.
+ *
+ * The reference (xyin-anl/MapsTorch) has no FFI: its boundary is plain Python
+ * (SURVEY.md section 8b).  These entry points are what a `mapstorch`-compatible
+ * Python package binds with ctypes; each one names the
+ * reference code it replaces.  Conventions:
+ *   - every pointer suffixed _dev is a DEVICE pointer owned by the caller (torch
+ *     tensors); pointers suffixed _host are host memory; the library allocates
+ *     nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and
+ *     asynchronous, the caller synchronises;
+ *   - return value: MT_OK or a negative MT_ERR_* code; mt_last_error() gives the
+ *     text of the last failure on the calling thread.  No exceptions cross the ABI;
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     MT_ERR_NO_DEVICE unless the current device is compute capability 10.x.
+ */
+#ifndef MAPSTORCH_B200_H
+#define MAPSTORCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_ABI_VERSION 1
+
+#define MT_OK 0
+#define MT_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
+#define MT_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define MT_ERR_UNSUPPORTED (-3) /* shape or dtype outside what the kernels cover */
+#define MT_ERR_NO_DEVICE (-4)   /* current device is not sm_100 */
+
+/* storage type of a spectral volume */
+#define MT_DTYPE_F32 0
+#define MT_DTYPE_F16 1
+
+/* ---- model terms (kernel K1) ------------------------------------------------
+ * One additive term of the MAPS forward model, evaluated per energy channel in
+ * the reference's fp32 operation order (map.py:57-69).  `delta = sign*(ev - e)`.
+ *   MT_TERM_GAUSS: amp * (p1 * exp(-0.5 * (delta/p0)^2))          p0=sigma p1=gain/(sigma*sqrt(2pi))
+ *   MT_TERM_STEP : amp * (p1 * erfc(delta/p0))                    p0=sqrt2*sigma p1=gain/2/E
+ *   MT_TERM_TAIL : amp * (p3 * (delta<0 ? exp(delta/p2)*v : v)),  v=erfc(delta/p0 + p1)
+ *                  p0=sqrt2*sigma p1=1/(gamma*sqrt2) p2=gamma*sigma p3=gain/2/gamma/sigma/exp(-0.5/gamma^2)
+ * Terms of one output column are stored contiguously and are accumulated in order.
+ */
+#define MT_TERM_GAUSS 0
+#define MT_TERM_STEP 1
+#define MT_TERM_TAIL 2
+
+typedef struct MtTerm {
+    int32_t kind;  /* MT_TERM_* */
+    float sign;    /* +1 or -1 (map.py:121 passes -delta_energy for the high-energy Compton tail) */
+    float e;       /* line energy, keV, already rounded to fp32 */
+    float p0, p1, p2, p3;
+    float amp;     /* faktor of the term (ratio * 10**logA / normalisation [* f_step | f_tail]) */
+} MtTerm;
+
+int mt_abi_version(void);
+const char *mt_last_error(void);
+
+/* MT_OK iff the current CUDA device is a compute-capability-10.x part. */
+int mt_device_check(void);
+
+/* K1 -- replaces the per-line torch op chains of model_elem_spec / elastic_peak /
+ * compton_peak (map.py:72-124,152-257).  out_dev[col*ld_out + c] = sum of the column's
+ * terms at channel c, fp32, accumulated in term order.  col_start_host has n_cols+1
+ * entries indexing terms_host.  ev_dev: [n_ch] fp32 energy axis (map.py:271-281, built on
+ * the host so that it is bit-identical to the reference's). */
+int mt_model_terms(const float *ev_dev, int32_t n_ch, const MtTerm *terms_host,
+                   const int32_t *col_start_host, int32_t n_cols, float *out_dev, int64_t ld_out,
+                   void *stream);
+
+/* Ordered column sum + optional escape-peak shift-add: replaces the agr_spec.add_ chain and
+ * escape_peak of model_spec (map.py:282-308, 127-150).  out = sum_col cols[col] (in order);
+ * if escape_bins > 0 and escape_factor > 0: out[c] += escape_factor * out_before[c + escape_bins]. */
+int mt_model_sum(const float *cols_dev, int64_t ld_cols, int32_t n_cols, int32_t n_ch,
+                 int32_t escape_bins, float escape_factor, float *out_dev, void *stream);
+
+/* K2 -- replaces snip_bkg/snip_op (bkg.py:53-114) for a batch of spectra.
+ * spec_dev: [n_px][ld_spec] of `dtype`, channels [ch0, ch0+n_ch) of every row are used.
+ * lohi_dev: [n_pass][n_ch] uint32, lo | (hi << 16): the gather indices of each clipping pass,
+ *           computed on the host with the reference's fp32 op sequence (bkg.py:57-62, 83-112).
+ * out_mode: MT_SNIP_BACKGROUND  out_dev = fp32 [n_px][ld_out] background in counts
+ *           MT_SNIP_RESIDUAL    out_dev = fp32 [n_px][ld_out] spectrum - background
+ *           MT_SNIP_RESIDUAL_HILO out_dev = fp32 [n_px][ld_out], ld_out >= 2*n_ch: residual split
+ *                               into a tf32-exact high part ([0,n_ch)) and remainder ([n_ch,2n_ch)) */
+#define MT_SNIP_BACKGROUND 0
+#define MT_SNIP_RESIDUAL 1
+#define MT_SNIP_RESIDUAL_HILO 2
+int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
+            int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar, float *out_dev,
+            int64_t ld_out, int32_t out_mode, void *stream);
+
+/* K3 -- the per-pixel amplitude solve: replaces the Adam loop of fit_spec (opt.py:249-317)
+ * for fixed global parameters, where the model is linear in the amplitudes.
+ * x[e][p] = colscale[e] * sum_k spec[p][k] * (w_hi[e][k] + lo_scale * w_lo[e][k]), i.e. the
+ * spectra contracted against the pseudo-inverse of the element basis on the tensor cores.
+ * spec_dev : [n_px][ld_spec] of `dtype` (row pitch must be a multiple of 16 bytes, base 16-B aligned)
+ * wpack_dev: [2*e_pad][ld_w] in the SAME dtype as spec (fp32 words hold tf32-exact values):
+ *            rows [0,e_pad) = high parts, rows [e_pad,2*e_pad) = low parts pre-multiplied by 1/lo_scale;
+ *            columns outside the fitted channel range hold zeros.  e_pad multiple of 8, <= 128.
+ * k_begin,k_end: channel window (elements) the kernel streams; rounded outwards to 128-byte blocks.
+ * x_dev    : fp32, element-major: x_dev[e*ld_x + p] for e < n_comp, p < n_px. */
+int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
+                    int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
+                    int64_t ld_w, int32_t e_pad, int32_t n_comp, const float *colscale_dev,
+                    float lo_scale, float *x_dev, int64_t ld_x, void *stream);
+
+/* Same contract on CUDA cores (no tensor cores, fp32 weights [n_comp][ld_w]); exists for
+ * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */
+int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
+                         int32_t k_begin, int32_t k_end, const float *w_dev, int64_t ld_w,
+                         int32_t n_comp, float *x_dev, int64_t ld_x, void *stream);
+
+/* Batched per-pixel non-negative fix-up of the least-squares amplitudes: minimise
+ * (x-xu)^T G (x-xu) s.t. x >= 0 with G = B^T B shared by all pixels (the converged answer of
+ * the reference's 10**a parametrisation, opt.py:154).  g_dev = G and hinv_dev = G^-1, both
+ * fp64 [n_comp][n_comp] row-major, n_comp <= 104.  Pixels whose unconstrained solution is
+ * already non-negative are untouched.  n_fixed_dev (optional, may be NULL): int32 counter,
+ * incremented once per pixel that needed the fix-up. */
+int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
+                  const double *hinv_dev, int32_t *n_fixed_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPSTORCH_B200_H */

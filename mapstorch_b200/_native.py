@@ -1,0 +1,114 @@
+"""ctypes binding of ``libmapstorch_b200.so`` (the C ABI in ``include/mapstorch_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point is
+called without an sm_100 device, a :class:`NativeError` is raised.
+"""
+import ctypes
+import os
+from pathlib import Path
+
+MT_OK = 0
+MT_DTYPE_F32, MT_DTYPE_F16 = 0, 1
+MT_TERM_GAUSS, MT_TERM_STEP, MT_TERM_TAIL = 0, 1, 2
+MT_SNIP_BACKGROUND, MT_SNIP_RESIDUAL, MT_SNIP_RESIDUAL_HILO = 0, 1, 2
+
+_LIB_NAME = "libmapstorch_b200.so"
+_lib = None
+
+
+class NativeError(RuntimeError):
+    """A C-ABI call returned a non-zero status (or the library could not be loaded)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"mapstorch_b200 native error {code}: {message}")
+        self.code = code
+
+
+class MtTerm(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("sign", ctypes.c_float), ("e", ctypes.c_float),
+                ("p0", ctypes.c_float), ("p1", ctypes.c_float), ("p2", ctypes.c_float),
+                ("p3", ctypes.c_float), ("amp", ctypes.c_float)]
+
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+# name -> argument types; every function returns int except mt_last_error
+SIGNATURES = {
+    "mt_abi_version": [],
+    "mt_device_check": [],
+    "mt_model_terms": [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
+    "mt_model_sum": [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp],
+    "mt_snip": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
+    "mt_fit_contract": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _f32, _vp,
+                        _i64, _vp],
+    "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp],
+    "mt_nnls_fixup": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp],
+    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+}
+
+
+def library_path():
+    override = os.environ.get("MAPSTORCH_B200_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / _LIB_NAME
+
+
+def load():
+    """Load (once) and return the ctypes handle of the native library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise NativeError(-100, f"{path} not found; build it with `make -C mapstorch_b200/csrc` "
+                                "(or python -c 'import __graft_entry__ as g; g.build()'). "
+                                "There is no CPU fallback.")
+    lib = ctypes.CDLL(str(path))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if name == "mt_refine":
+                continue
+            raise NativeError(-101, f"{path} does not export {name}")
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.mt_last_error.argtypes = []
+    lib.mt_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != MT_OK:
+        msg = load().mt_last_error()
+        raise NativeError(status, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def stream_ptr(stream=None):
+    """cudaStream_t of a torch stream (default: torch's current stream) as a void*."""
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def dtype_code(torch_dtype):
+    import torch
+
+    if torch_dtype == torch.float32:
+        return MT_DTYPE_F32
+    if torch_dtype == torch.float16:
+        return MT_DTYPE_F16
+    raise NativeError(-3, f"spectral volumes must be float32 or float16 on the device, got {torch_dtype}")
+
+
+def require_device():
+    """Raise unless the current CUDA device is an sm_100 part (no CPU fallback)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise NativeError(-4, "no CUDA device is visible; mapstorch_b200 has no CPU path")
+    call("mt_device_check")

@@ -1,0 +1,39 @@
+// Shared host-side plumbing for the C-ABI entry points (error text, device gate).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "mapstorch_b200.h"
+
+namespace mt {
+
+// thread-local text of the last failure, returned by mt_last_error()
+char *error_buffer();
+int fail(int code, const char *fmt, ...);
+
+// MT_OK iff the current device is compute capability 10.x (cached per device).
+int require_sm100();
+
+#define MT_CUDA_TRY(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::mt::fail(MT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define MT_REQUIRE(cond, ...)                                          \
+    do {                                                               \
+        if (!(cond)) return ::mt::fail(MT_ERR_INVALID, __VA_ARGS__);   \
+    } while (0)
+
+inline int num_sms() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+}  // namespace mt

@@ -1,0 +1,408 @@
+// K3 -- streaming per-pixel amplitude solve on the 5th-generation tensor cores.
+//
+// For fixed global parameters the MAPS model is linear in the element amplitudes and the Gram
+// matrix is pixel independent, so the reference's per-pixel Adam loop
+// (opt.py:249-317) collapses to X[P,E] = Y[P,C] . W[C,E] with W the pseudo-inverse of the
+// element basis.  Each spectrum byte is read from HBM exactly once:
+//
+//   warp 0   TMA producer : 2-D bulk-tensor loads of a [256 px x 128 B] slab of spectra
+//                           (evict-first) and the matching [N x 128 B] slab of W (evict-last,
+//                           L2 resident) into a ring of 128B-swizzled shared-memory stages
+//   warp 1   MMA issuer   : tcgen05.mma cta_group::1, M=128 (x2 pixel sub-tiles sharing the W
+//                           slab), N = 2*e_pad, kind::f16 for fp16 volumes / kind::tf32 for fp32;
+//                           accumulators live in TMEM, double buffered across pixel tiles
+//   warps 2-5 epilogue    : tcgen05.ld the finished tile, recombine the hi/lo split of W
+//                           (fp32-accurate result from 11-bit operands), scale, store
+//                           element-major amplitudes x[e][p] (coalesced over pixels)
+//
+// W is stored as two operand-precision parts (hi, lo/lo_scale) stacked along N; spectra are raw
+// counts, which fp16/tf32 hold exactly below 2048, so no A-side split is needed for them.
+// Bound: HBM (C*sizeof(in) + E*4 bytes per pixel); tensor-pipe use stays well below peak.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "mt_common.cuh"
+#include "mt_ptx.cuh"
+
+namespace {
+
+using namespace mt::ptx;
+
+constexpr int kFitThreads = 192;       // 6 warps: producer, MMA, 4 epilogue
+constexpr int kTileRows = 128;         // UMMA M
+constexpr int kRowBytes = 128;         // one swizzle-128B row = one k-block per row
+constexpr int kSubTileBytes = kTileRows * kRowBytes;  // 16 KiB
+constexpr int kSmemLimit = 227 * 1024;
+
+struct FitParams {
+    long long n_px;
+    long long ld_x;
+    float *x;
+    const float *colscale;
+    int n_tiles;
+    int kb_begin, kb_end;
+    int bke;  // elements per k-block (64 for fp16, 32 for fp32)
+    int n_mma, e_pad, n_comp;
+    int n_stages;
+    uint32_t stage_bytes;
+    uint32_t tmem_cols;
+    uint32_t idesc;
+    float lo_scale;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded spin: a protocol bug must surface as a launch failure, not hang the GPU
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spin & 0xFFFu) == 0xFFFu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 8000000000ll) {
+                printf("mt_fit_contract: barrier wait timed out (block %d thread %d)\n", blockIdx.x,
+                       threadIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
+template <int KIND, int M_TILES>
+__global__ void __launch_bounds__(kFitThreads, 1)
+fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_constant__ CUtensorMap tm_w,
+                    const FitParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t ring = (raw_addr + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
+    uint8_t *after_ring = smem_raw + (ring - raw_addr) + (size_t)p.n_stages * p.stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after_ring);
+    const uint32_t bar0 = smem_u32(bars);
+    // barrier slots: full[s], empty[s], tmem_full[2], tmem_empty[2]
+    auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.n_stages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.n_stages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.n_stages + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * p.n_stages + 4);
+    float *cs = reinterpret_cast<float *>(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int block_rows = kTileRows * M_TILES;
+    const uint32_t acc_cols = (uint32_t)(M_TILES * p.n_mma);
+
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&tm_spec);
+        prefetch_tensormap(&tm_w);
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+        tmem_relinquish();
+    }
+    for (int e = threadIdx.x; e < p.e_pad; e += kFitThreads) cs[e] = (e < p.n_comp) ? p.colscale[e] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int row0 = tile * block_rows;
+                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t dst = ring + (uint32_t)stage * p.stage_bytes;
+                    mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                    tma_load_2d(dst, &tm_spec, full_bar(stage), kb * p.bke, row0, kEvictFirst);
+                    tma_load_2d(dst + M_TILES * kSubTileBytes, &tm_w, full_bar(stage), kb * p.bke, 0, kEvictLast);
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
+                    mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a_addr = ring + (uint32_t)stage * p.stage_bytes;
+                    const uint64_t w_desc = umma_desc_sw128(a_addr + M_TILES * kSubTileBytes);
+#pragma unroll
+                    for (int mt = 0; mt < M_TILES; ++mt) {
+                        const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kSubTileBytes);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // 32 bytes (16 fp16 / 8 tf32) along K per instruction: +2 in 16-byte units
+                            tc_mma<KIND>(d_tmem, a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), p.idesc,
+                                         (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+                    if (++stage == p.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: TMEM -> registers -> x[e][p] =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int mt = 0; mt < M_TILES; ++mt) {
+                const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
+                const uint32_t taddr =
+                    tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+                for (int c0 = 0; c0 < p.e_pad; c0 += 8) {
+                    float hi[8], lo[8];
+                    tmem_ld8(taddr + (uint32_t)c0, hi);
+                    tmem_ld8(taddr + (uint32_t)(p.e_pad + c0), lo);
+                    tmem_ld_wait();
+                    if (px < p.n_px) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int e = c0 + j;
+                            if (e < p.n_comp) p.x[(long long)e * p.ld_x + px] = cs[e] * fmaf(lo[j], p.lo_scale, hi[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ---- CUDA-core version of the same contraction (cross-check / TMA-unfriendly layouts) ---------
+template <typename T>
+__device__ __forceinline__ float ld_val(const T *p);
+template <>
+__device__ __forceinline__ float ld_val<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_val<__half>(const __half *p) { return __half2float(__ldg(p)); }
+
+constexpr int kSimtPx = 4;    // pixels per warp
+constexpr int kSimtComp = 16; // components per pass
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fit_contract_simt_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int k_begin, int k_end,
+                         const float *__restrict__ w, long long ld_w, int n_comp, float *__restrict__ x,
+                         long long ld_x) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long px0 = warp_global * kSimtPx;
+    if (px0 >= n_px) return;
+    for (int e0 = 0; e0 < n_comp; e0 += kSimtComp) {
+        float acc[kSimtPx][kSimtComp];
+#pragma unroll
+        for (int i = 0; i < kSimtPx; ++i)
+#pragma unroll
+            for (int j = 0; j < kSimtComp; ++j) acc[i][j] = 0.f;
+        for (int k = k_begin + lane; k < k_end; k += 32) {
+            float y[kSimtPx];
+#pragma unroll
+            for (int i = 0; i < kSimtPx; ++i)
+                y[i] = (px0 + i < n_px) ? ld_val<T>(spec + (px0 + i) * ld_spec + k) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kSimtComp; ++j) {
+                const float wv = (e0 + j < n_comp) ? __ldg(w + (long long)(e0 + j) * ld_w + k) : 0.f;
+#pragma unroll
+                for (int i = 0; i < kSimtPx; ++i) acc[i][j] = fmaf(y[i], wv, acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSimtPx; ++i)
+#pragma unroll
+            for (int j = 0; j < kSimtComp; ++j) {
+                float v = acc[i][j];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                if (lane == 0 && px0 + i < n_px && e0 + j < n_comp) x[(long long)(e0 + j) * ld_x + px0 + i] = v;
+            }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D row-major tensor [rows][cols] with a row pitch, boxes of [box_rows][128 bytes], swizzle 128B
+int make_tile_map(CUtensorMap *map, const void *base, int dtype, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                  uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return mt::fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const uint32_t es = dtype == MT_DTYPE_F16 ? 2u : 4u;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {pitch_elems * es};
+    cuuint32_t box[2] = {kRowBytes / es, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dtype == MT_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                     2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return mt::fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return MT_OK;
+}
+
+template <int KIND, int M_TILES>
+int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_w, const FitParams &p, size_t smem, int grid,
+               cudaStream_t stream) {
+    auto kern = fit_contract_kernel<KIND, M_TILES>;
+    MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_w, p);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
+
+}  // namespace
+
+extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
+                               int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
+                               int64_t ld_w, int32_t e_pad, int32_t n_comp, const float *colscale_dev,
+                               float lo_scale, float *x_dev, int64_t ld_x, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
+    MT_REQUIRE(dtype == MT_DTYPE_F32 || dtype == MT_DTYPE_F16, "mt_fit_contract: dtype %d", dtype);
+    const int es = dtype == MT_DTYPE_F16 ? 2 : 4;
+    MT_REQUIRE(n_px >= 0 && n_px < (1ll << 31) - 512, "mt_fit_contract: n_px=%lld", (long long)n_px);
+    MT_REQUIRE(n_ch_total > 0 && ld_spec >= n_ch_total && ld_w >= n_ch_total,
+               "mt_fit_contract: n_ch_total=%d ld_spec=%lld ld_w=%lld", n_ch_total, (long long)ld_spec,
+               (long long)ld_w);
+    MT_REQUIRE(0 <= k_begin && k_begin < k_end && k_end <= n_ch_total, "mt_fit_contract: channel window [%d,%d)",
+               k_begin, k_end);
+    MT_REQUIRE(e_pad >= 8 && e_pad <= 128 && e_pad % 8 == 0 && n_comp >= 1 && n_comp <= e_pad,
+               "mt_fit_contract: e_pad=%d n_comp=%d", e_pad, n_comp);
+    MT_REQUIRE(ld_x >= n_px, "mt_fit_contract: ld_x=%lld < n_px", (long long)ld_x);
+    if ((ld_spec * es) % 16 || (ld_w * es) % 16 || ((uintptr_t)spec_dev & 15) || ((uintptr_t)wpack_dev & 15))
+        return mt::fail(MT_ERR_UNSUPPORTED,
+                        "mt_fit_contract: TMA needs 16-byte aligned base pointers and row pitches "
+                        "(ld_spec=%lld ld_w=%lld elements of %d bytes); use mt_fit_contract_simt",
+                        (long long)ld_spec, (long long)ld_w, es);
+    if (n_px == 0) return MT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    FitParams p{};
+    p.n_px = n_px;
+    p.ld_x = ld_x;
+    p.x = x_dev;
+    p.colscale = colscale_dev;
+    p.bke = kRowBytes / es;
+    p.kb_begin = k_begin / p.bke;
+    p.kb_end = (k_end + p.bke - 1) / p.bke;
+    p.n_mma = 2 * e_pad;
+    p.e_pad = e_pad;
+    p.n_comp = n_comp;
+    p.lo_scale = lo_scale;
+    const int m_tiles = (p.n_mma <= 128) ? 2 : 1;
+    const int block_rows = kTileRows * m_tiles;
+    p.n_tiles = (int)((n_px + block_rows - 1) / block_rows);
+    p.stage_bytes = (uint32_t)(m_tiles * kSubTileBytes + p.n_mma * kRowBytes);
+    const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64;
+    p.n_stages = (int)((kSmemLimit - fixed) / p.stage_bytes);
+    if (p.n_stages > 12) p.n_stages = 12;
+    MT_REQUIRE(p.n_stages >= 2, "mt_fit_contract: tile does not fit shared memory");
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * m_tiles * p.n_mma)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.idesc = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, kTileRows, p.n_mma);
+    const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
+
+    CUtensorMap tm_spec, tm_w;
+    if (int rc = make_tile_map(&tm_spec, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec,
+                               (uint32_t)block_rows))
+        return rc;
+    if (int rc = make_tile_map(&tm_w, wpack_dev, dtype, (uint64_t)n_ch_total, (uint64_t)p.n_mma, (uint64_t)ld_w,
+                               (uint32_t)p.n_mma))
+        return rc;
+    const int sms = mt::num_sms();
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    if (dtype == MT_DTYPE_F16)
+        return m_tiles == 2 ? launch_fit<0, 2>(tm_spec, tm_w, p, smem, grid, stream)
+                            : launch_fit<0, 1>(tm_spec, tm_w, p, smem, grid, stream);
+    return m_tiles == 2 ? launch_fit<1, 2>(tm_spec, tm_w, p, smem, grid, stream)
+                        : launch_fit<1, 1>(tm_spec, tm_w, p, smem, grid, stream);
+}
+
+extern "C" int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
+                                    int32_t k_begin, int32_t k_end, const float *w_dev, int64_t ld_w,
+                                    int32_t n_comp, float *x_dev, int64_t ld_x, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(spec_dev && w_dev && x_dev, "mt_fit_contract_simt: null pointer");
+    MT_REQUIRE(n_px >= 0 && 0 <= k_begin && k_begin < k_end && k_end <= ld_spec && k_end <= ld_w && n_comp >= 1 &&
+                   ld_x >= n_px,
+               "mt_fit_contract_simt: bad sizes");
+    if (n_px == 0) return MT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long warps = (n_px + kSimtPx - 1) / kSimtPx;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    if (dtype == MT_DTYPE_F32)
+        fit_contract_simt_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(spec_dev), n_px, ld_spec,
+                                                                  k_begin, k_end, w_dev, ld_w, n_comp, x_dev, ld_x);
+    else if (dtype == MT_DTYPE_F16)
+        fit_contract_simt_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half *>(spec_dev), n_px,
+                                                                   ld_spec, k_begin, k_end, w_dev, ld_w, n_comp,
+                                                                   x_dev, ld_x);
+    else
+        return mt::fail(MT_ERR_UNSUPPORTED, "mt_fit_contract_simt: dtype %d", dtype);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}

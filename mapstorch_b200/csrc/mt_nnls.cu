@@ -1,0 +1,211 @@
+// Batched per-pixel non-negative solve on the shared normal equations.
+//
+// The reference parametrises amplitudes as 10**a (opt.py:154, map.py:163), i.e. it solves a
+// non-negative least-squares problem; with fixed global parameters its converged answer is
+//     argmin_x (x - xu)^T G (x - xu)   s.t. x >= 0,      G = B^T B  (pixel independent),
+// where xu is the unconstrained solution produced by mt_fit_contract.  One thread owns one
+// pixel and runs block principal pivoting in fp64; each pivot step solves an SPD system on the
+// smaller of the two index sets:
+//     zero set  A small:  z = (H_AA)^-1 xu_A,  x_F = xu_F - H_FA z,  dual y_A = -z      (H = G^-1)
+//     free set  F small:  x_F = (G_FF)^-1 b_F,                       dual y_A = G_AF x_F - b_A
+// so the Cholesky factor never exceeds (E/2)(E/2+1)/2 entries of thread-local memory.  Pixels
+// whose xu is already non-negative (the common case on high-count maps) only pay the scan.
+#include "mt_common.cuh"
+
+namespace {
+
+constexpr int kNnlsThreads = 128;
+
+// Packed lower-triangular Cholesky of M[idx, idx] (M: shared, row-major ld), then solve into v.
+// Returns false if a pivot is not positive (numerically singular subset).
+template <int HALF>
+__device__ bool chol_solve(const double *M, int ld, const unsigned char *idx, int n, double *L, double *v) {
+    for (int j = 0; j < n; ++j) {
+        const double *mj = M + idx[j] * ld;
+        for (int i = 0; i <= j; ++i) {
+            double s = mj[idx[i]];
+            const double *lj = L + j * (j + 1) / 2, *li = L + i * (i + 1) / 2;
+            for (int k = 0; k < i; ++k) s -= lj[k] * li[k];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[j * (j + 1) / 2 + j] = sqrt(s);
+            } else {
+                L[j * (j + 1) / 2 + i] = s / li[i];
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) {  // forward
+        double s = v[i];
+        const double *li = L + i * (i + 1) / 2;
+        for (int k = 0; k < i; ++k) s -= li[k] * v[k];
+        v[i] = s / li[i];
+    }
+    for (int i = n - 1; i >= 0; --i) {  // backward
+        double s = v[i];
+        for (int k = i + 1; k < n; ++k) s -= L[k * (k + 1) / 2 + i] * v[k];
+        v[i] = s / L[i * (i + 1) / 2 + i];
+    }
+    return true;
+}
+
+template <int EMAX>
+__global__ void __launch_bounds__(kNnlsThreads)
+nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, const double *__restrict__ g_dev,
+                  const double *__restrict__ h_dev, int *__restrict__ n_fixed) {
+    constexpr int HALF = EMAX / 2;
+    extern __shared__ double mats[];  // G[E*E], H[E*E]
+    double *G = mats, *H = mats + E * E;
+    for (int i = threadIdx.x; i < E * E; i += kNnlsThreads) {
+        G[i] = g_dev[i];
+        H[i] = h_dev[i];
+    }
+    __syncthreads();
+    const long long px = (long long)blockIdx.x * kNnlsThreads + threadIdx.x;
+    if (px >= n_px) return;
+
+    double xu[EMAX];
+    bool any_neg = false;
+    double xmax = 0.0;
+    for (int e = 0; e < E; ++e) {
+        xu[e] = (double)x[(long long)e * ld_x + px];
+        any_neg |= (xu[e] < 0.0);
+        xmax = fmax(xmax, fabs(xu[e]));
+    }
+    if (!any_neg) return;
+    if (n_fixed) atomicAdd(n_fixed, 1);
+
+    double xs[EMAX];        // current primal (free set) / dual (zero set) values
+    double b[EMAX];         // G xu, filled lazily
+    bool have_b = false;
+    bool free_[EMAX];
+    unsigned char idx[EMAX];
+    double L[HALF * (HALF + 1) / 2];
+    double v[HALF];
+    int n_free = 0;
+    for (int e = 0; e < E; ++e) {
+        free_[e] = xu[e] > 0.0;
+        n_free += free_[e];
+    }
+    double gmax = 0.0;
+    for (int e = 0; e < E; ++e) gmax = fmax(gmax, G[e * E + e]);
+    const double tol_x = 1e-12 * xmax, tol_y = 1e-12 * xmax * gmax;
+
+    int ninf = E + 1, backup = 3;
+    const int max_iter = 8 * E + 16;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        const int n_zero = E - n_free;
+        bool ok = true;
+        if (n_zero <= n_free) {
+            // zero set is the smaller one: Schur complement on H = G^-1
+            int n = 0;
+            for (int e = 0; e < E; ++e)
+                if (!free_[e]) {
+                    idx[n] = (unsigned char)e;
+                    v[n] = xu[e];
+                    ++n;
+                }
+            ok = chol_solve<HALF>(H, E, idx, n, L, v);
+            if (ok) {
+                for (int e = 0; e < E; ++e) {
+                    if (free_[e]) {
+                        double s = xu[e];
+                        const double *he = H + e * E;
+                        for (int k = 0; k < n; ++k) s -= he[idx[k]] * v[k];
+                        xs[e] = s;
+                    }
+                }
+                for (int k = 0; k < n; ++k) xs[idx[k]] = -v[k];  // dual on the zero set; tol_y scale: G*x
+                // H-scaled dual has units x / H; compare on the same footing as G-form below
+            }
+        } else {
+            if (!have_b) {
+                for (int e = 0; e < E; ++e) {
+                    double s = 0.0;
+                    const double *ge = G + e * E;
+                    for (int k = 0; k < E; ++k) s += ge[k] * xu[k];
+                    b[e] = s;
+                }
+                have_b = true;
+            }
+            int n = 0;
+            for (int e = 0; e < E; ++e)
+                if (free_[e]) {
+                    idx[n] = (unsigned char)e;
+                    v[n] = b[e];
+                    ++n;
+                }
+            ok = chol_solve<HALF>(G, E, idx, n, L, v);
+            if (ok) {
+                for (int k = 0; k < n; ++k) xs[idx[k]] = v[k];
+                for (int e = 0; e < E; ++e) {
+                    if (!free_[e]) {
+                        double s = -b[e];
+                        const double *ge = G + e * E;
+                        for (int k = 0; k < n; ++k) s += ge[idx[k]] * v[k];
+                        xs[e] = s;
+                    }
+                }
+            }
+        }
+        if (!ok) break;
+        int n_bad = 0, last_bad = -1;
+        for (int e = 0; e < E; ++e) {
+            const bool bad = free_[e] ? (xs[e] < -tol_x) : (xs[e] < -tol_y);
+            if (bad) {
+                ++n_bad;
+                last_bad = e;
+            }
+        }
+        if (n_bad == 0) break;
+        bool flip_all;
+        if (n_bad < ninf) {
+            ninf = n_bad;
+            backup = 3;
+            flip_all = true;
+        } else if (backup > 0) {
+            --backup;
+            flip_all = true;
+        } else {
+            flip_all = false;
+        }
+        for (int e = 0; e < E; ++e) {
+            const bool bad = free_[e] ? (xs[e] < -tol_x) : (xs[e] < -tol_y);
+            if (bad && (flip_all || e == last_bad)) {
+                n_free += free_[e] ? -1 : 1;
+                free_[e] = !free_[e];
+            }
+        }
+    }
+    for (int e = 0; e < E; ++e) {
+        const double out = free_[e] ? fmax(xs[e], 0.0) : 0.0;
+        x[(long long)e * ld_x + px] = (float)out;
+    }
+}
+
+template <int EMAX>
+int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
+                cudaStream_t stream) {
+    auto kern = nnls_fixup_kernel<EMAX>;
+    const size_t smem = sizeof(double) * 2 * (size_t)E * E;
+    MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
+    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, n_px, E, g, h, n_fixed);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
+
+}  // namespace
+
+extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
+                             const double *hinv_dev, int32_t *n_fixed_dev, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(x_dev && g_dev && hinv_dev, "mt_nnls_fixup: null pointer");
+    MT_REQUIRE(n_px >= 0 && n_comp >= 1 && ld_x >= n_px, "mt_nnls_fixup: bad sizes");
+    if (n_px == 0) return MT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_comp <= 16) return launch_nnls<16>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
+    if (n_comp <= 32) return launch_nnls<32>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
+    if (n_comp <= 64) return launch_nnls<64>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
+    if (n_comp <= 104) return launch_nnls<104>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
+    return mt::fail(MT_ERR_UNSUPPORTED, "mt_nnls_fixup: n_comp=%d > 104", n_comp);
+}

@@ -1,0 +1,308 @@
+"""Fitting entry points -- the reference's ``mapstorch/opt.py`` surface plus the per-pixel ``fit_map``.
+
+``init_elem_amps`` (opt.py:63-97), ``create_tensors`` (opt.py:100-162) and ``fit_spec``
+(opt.py:165-327) keep their signatures.  ``fit_map`` is the entry point the reference lacks
+(SURVEY.md 0.2): it fits every pixel of a spectral volume.  For fixed global parameters the
+model is linear in the amplitudes 10**a and the Gram matrix is pixel independent, so the
+reference's per-spectrum Adam loop is replaced by
+
+    K1 basis B[E,C]  ->  host (fp64): G = B B^T, H = G^-1, W = H B, hi/lo operand split
+    [K2 SNIP residual]  ->  K3 tensor-core contraction X = Y W^T  ->  batched non-negative fix-up
+
+which is what the reference's fit converges to.  No CPU compute path exists.
+"""
+import numpy as np
+import torch
+
+from mapstorch_b200 import _native, bkg as _bkg, map as _map, tables
+from mapstorch_b200.default import (
+    default_fitting_elems,
+    default_fitting_params,
+    default_param_vals,
+    default_learning_rates,
+    default_energy_consts,
+    default_elem_info,
+)
+
+LO_SCALE = 2.0 ** -11  # the low operand part is stored pre-multiplied by 2**11
+SNIP_CHUNK_PX = 32768
+
+
+def init_elem_amps(elem, spec, e_sct, e_offset, e_slope, e_consts=default_energy_consts, verbose=False, *,
+                   compton_angle=None):
+    """log10 amplitude guess from the mean counts in a window around the element's first line
+    (opt.py:63-97).  Host-side NumPy like the reference; vectorises over leading dims of `spec`."""
+    try:
+        lo, hi = tables.amp_window(elem, spec.shape[-1], e_sct, e_offset, e_slope, e_consts, compton_angle)
+        size = (hi + 1) - lo
+        mean = np.sum(spec[..., lo: hi + 1], axis=-1) / size
+        return np.log10(np.maximum(mean * 8.0 + 0.01, 1.0))
+    except Exception:
+        if verbose:
+            print("Cannot initialize {} amplitude".format(elem))
+        return 0.0
+
+
+def create_tensors(elems_to_fit=default_fitting_elems, fitting_params=default_fitting_params,
+                   init_param_vals=default_param_vals, fixed_param_vals={}, map_shape=None, tune_params=True,
+                   init_amp=False, spec=None, device="cpu", verbose=False):
+    """Parameter / amplitude tensor dict and per-parameter optimiser groups (opt.py:100-162)."""
+    if init_amp:
+        assert spec is not None, "Initial amplitude initialization requires the spectrum to be provided."
+    tensors, opt_configs = {}, []
+    for name, default in default_param_vals.items():
+        start = init_param_vals.get(name, default)
+        tunable = name in fitting_params and tune_params and name not in fixed_param_vals
+        value = float(start) if tunable else fixed_param_vals.get(name, start)
+        tensors[name] = torch.tensor(value, requires_grad=tunable, device=device)
+        if tunable:
+            opt_configs.append({"params": tensors[name],
+                                "lr": default_learning_rates.get(name, default_learning_rates["default_lr"])})
+    for elem in elems_to_fit:
+        if init_amp:
+            angle = tensors["COMPTON_ANGLE"].item() if "COMPTON_ANGLE" in tensors else None
+            start = init_elem_amps(elem, spec, tensors["COHERENT_SCT_ENERGY"].item(), tensors["ENERGY_OFFSET"].item(),
+                                   tensors["ENERGY_SLOPE"].item(), verbose=verbose, compton_angle=angle)
+        else:
+            start = np.zeros(map_shape) if map_shape is not None else 0.0
+        tensors[elem] = torch.tensor(start, requires_grad=True, device=device)
+        opt_configs.append({"params": tensors[elem],
+                            "lr": default_learning_rates.get(elem, default_learning_rates["default_lr"])})
+    return tensors, opt_configs
+
+
+# ---- operand packing ---------------------------------------------------------------------------
+def _round_tf32(a):
+    """Round fp32 values to the nearest tf32 (10 explicit mantissa bits), returned as fp32."""
+    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def split_operand(w64, kind):
+    """W (float64 [E, C]) -> (colscale[E], hi, lo) with W ~= colscale * (hi + LO_SCALE * lo); hi and
+    lo are exactly representable in the tensor-core operand type (`kind`: 'f16' or 'tf32')."""
+    peak = np.max(np.abs(w64), axis=1)
+    peak = np.where(peak > 0, peak, 1.0)
+    scale = np.exp2(np.ceil(np.log2(peak)) - 14.0)  # rows scaled into [2**13, 2**14]: exact, fp16-safe
+    scaled = w64 / scale[:, None]
+    if kind == "f16":
+        hi = scaled.astype(np.float16)
+        lo = ((scaled - hi.astype(np.float64)) / LO_SCALE).astype(np.float16)
+    else:
+        hi = _round_tf32(scaled.astype(np.float32))
+        lo = _round_tf32(((scaled - hi.astype(np.float64)) / LO_SCALE).astype(np.float32))
+    return scale.astype(np.float32), hi, lo
+
+
+class MapFitPlan:
+    """Everything that depends only on the global parameters, prepared once per fit.
+
+    Attributes: names (component order = model_spec order), basis (CUDA fp32 [E, C]), gram/hinv
+    (fp64), er (inclusive channel pair)."""
+
+    def __init__(self, energy_range, elements_to_fit=default_fitting_elems, param_vals=default_param_vals,
+                 indices=None, use_snip=True, e_consts=default_energy_consts, elem_info=default_elem_info,
+                 detector_type="Si", escape_factor=0.0, boxcar_size=5):
+        _native.require_device()
+        self.er = (int(energy_range[0]), int(energy_range[1]))
+        self.n_ch = self.er[1] - self.er[0] + 1
+        self.params = dict(default_param_vals)
+        self.params.update({k: (v.item() if isinstance(v, torch.Tensor) else v) for k, v in param_vals.items()
+                            if k in default_param_vals})
+        self.use_snip = bool(use_snip)
+        self.boxcar_size = int(boxcar_size)
+        elements = list(dict.fromkeys(list(elements_to_fit)))
+        self.basis, self.names = _map.element_basis(self.params, self.er, elements, e_consts, elem_info,
+                                                    detector_type, escape_factor)
+        b64 = self.basis.double().cpu().numpy()
+        if indices is not None:
+            mask = np.zeros(self.n_ch, dtype=bool)
+            mask[np.asarray(indices)] = True
+            b64 = b64 * mask[None, :]
+        # components without any open line (or fully masked) cannot be fitted: amplitude 0
+        self.live = np.nonzero(np.sum(b64 * b64, axis=1) > 0)[0]
+        bl = b64[self.live]
+        gram = bl @ bl.T
+        hinv = np.linalg.inv(gram)
+        hinv = 0.5 * (hinv + hinv.T)
+        self.gram, self.hinv = gram, hinv
+        self.pinv = hinv @ bl  # [E_live, C]: x = pinv @ (y - bkg)
+        self.n_live = len(self.live)
+        self.e_pad = max(8, -(-self.n_live // 8) * 8)
+        if self.e_pad > 128:
+            raise _native.NativeError(-3, f"{self.n_live} fitted components exceed the 128 the contraction kernel holds")
+        self.gram_dev = torch.from_numpy(gram).cuda()
+        self.hinv_dev = torch.from_numpy(hinv).cuda()
+        self._packs = {}
+        self._snip = None
+        if self.use_snip:
+            p = self.params
+            self._snip = _bkg.snip_tables_device(
+                self.n_ch, self.er, *(torch.tensor(float(p[k])) for k in (
+                    "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")))
+
+    # -- operand packs, cached per (dtype, layout) ------------------------------------------------
+    def _pack(self, kind, n_cols, col0, repeat):
+        """wpack [2*e_pad, n_cols]: pinv placed at columns [col0, col0+n_ch) (`repeat` copies back to back)."""
+        key = (kind, n_cols, col0, repeat)
+        if key not in self._packs:
+            scale, hi, lo = split_operand(self.pinv, kind)
+            dt = np.float16 if kind == "f16" else np.float32
+            pack = np.zeros((2 * self.e_pad, n_cols), dtype=dt)
+            for r in range(repeat):
+                c = col0 + r * self.n_ch
+                pack[: self.n_live, c: c + self.n_ch] = hi
+                pack[self.e_pad: self.e_pad + self.n_live, c: c + self.n_ch] = lo
+            self._packs[key] = (torch.from_numpy(pack).cuda(), torch.from_numpy(scale).cuda())
+        return self._packs[key]
+
+    def _pinv_f32(self, n_cols, col0):
+        key = ("simt", n_cols, col0)
+        if key not in self._packs:
+            w = np.zeros((self.n_live, n_cols), dtype=np.float32)
+            w[:, col0: col0 + self.n_ch] = self.pinv.astype(np.float32)
+            self._packs[key] = torch.from_numpy(w).cuda()
+        return self._packs[key]
+
+    # -- the fit -----------------------------------------------------------------------------------
+    def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream):
+        """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
+        n_px, n_ch_total, ld = spec2d.shape[0], spec2d.shape[1], spec2d.stride(0)
+        es = spec2d.element_size()
+        tma_ok = (ld * es) % 16 == 0 and spec2d.data_ptr() % 16 == 0
+        if engine == "tensor" and not tma_ok:
+            engine = "simt"
+        if engine == "tensor":
+            kind = "f16" if spec2d.dtype == torch.float16 else "tf32"
+            pack, scale = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat)
+            _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
+                         n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
+                         self.n_live, scale.data_ptr(), float(LO_SCALE), x.data_ptr(), x.stride(0),
+                         _native.stream_ptr(stream))
+        elif engine == "simt":
+            if repeat != 1:
+                raise _native.NativeError(-3, "the CUDA-core contraction expects an unsplit residual")
+            w = self._pinv_f32(n_ch_total, col0)
+            _native.call("mt_fit_contract_simt", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
+                         int(k_begin), int(k_end), w.data_ptr(), w.stride(0), self.n_live, x.data_ptr(),
+                         x.stride(0), _native.stream_ptr(stream))
+        else:
+            raise ValueError(f"unknown engine {engine!r}")
+
+    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None):
+        """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
+        rows in `self.names` order (components without an open line stay 0)."""
+        if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
+            raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
+        if spec2d.shape[1] <= self.er[1]:
+            raise ValueError(f"spectra have {spec2d.shape[1]} channels, energy_range ends at {self.er[1]}")
+        n_px, n_all = spec2d.shape[0], len(self.names)
+        if out is None:
+            out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
+        dense = self.n_live == n_all
+        x = out if dense else torch.empty((self.n_live, n_px), dtype=torch.float32, device="cuda")
+        if not self.use_snip:
+            self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream)
+        else:
+            lohi, n_pass = self._snip
+            hilo = engine == "tensor"
+            width = 2 * self.n_ch if hilo else self.n_ch
+            chunk = min(SNIP_CHUNK_PX, n_px)
+            scratch = torch.empty((chunk, width), dtype=torch.float32, device="cuda")
+            mode = _native.MT_SNIP_RESIDUAL_HILO if hilo else _native.MT_SNIP_RESIDUAL
+            for p0 in range(0, n_px, chunk):
+                n = min(chunk, n_px - p0)
+                _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass, self.boxcar_size,
+                                 scratch[:n], mode, stream)
+                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream)
+        if nonneg and n_px:
+            _native.call("mt_nnls_fixup", x.data_ptr(), x.stride(0), n_px, self.n_live, self.gram_dev.data_ptr(),
+                         self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
+                         _native.stream_ptr(stream))
+        if not dense:
+            out[torch.as_tensor(self.live, device="cuda")] = x
+        return out
+
+
+def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_param_vals=default_param_vals,
+            fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
+            elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
+            device="cuda", engine="tensor", plan=None, return_plan=False):
+    """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
+
+    Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
+    init_param_vals=..., fixed_param_vals=..., tune_params=False, use_snip=..., indices=...)`` on each
+    pixel and running it to convergence.  Returns ``{name: amplitude map [...]}`` (linear counts, or
+    log10 like the reference's tensors if as_log10) on `device`; the two scatter components are
+    always fitted, as in fit_spec (opt.py:194-200)."""
+    _native.require_device()
+    if not isinstance(spec_vol, torch.Tensor):
+        arr = np.asarray(spec_vol)
+        if arr.dtype not in (np.float32, np.float16):
+            arr = arr.astype(np.float32)
+        spec_vol = torch.from_numpy(arr)
+    if spec_vol.dtype not in (torch.float32, torch.float16):
+        spec_vol = spec_vol.to(torch.float32)
+    vol = spec_vol.to("cuda", non_blocking=True)
+    lead = vol.shape[:-1]
+    flat = vol.reshape(-1, vol.shape[-1])
+    if flat.stride(1) != 1:
+        flat = flat.contiguous()
+    if plan is None:
+        params = dict(init_param_vals)
+        params.update(fixed_param_vals)
+        plan = MapFitPlan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
+                          detector_type, escape_factor)
+    x = plan.fit(flat, nonneg=nonneg, engine=engine)
+    if as_log10:
+        x = torch.log10(x)
+    x = x if torch.device(device).type == "cuda" else x.to(device)
+    maps = {name: x[i].reshape(lead) for i, name in enumerate(plan.names)}
+    return (maps, plan) if return_plan else maps
+
+
+def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitting_params=default_fitting_params,
+             init_param_vals=default_param_vals, fixed_param_vals={}, indices=None, tune_params=True, init_amp=True,
+             use_snip=True, loss="mse", optimizer="adam", n_iter=500, l1_lambda=0.0, progress_bar=True,
+             device="cuda", status_updator=None, verbose=False, use_finite_diff=False, finite_diff_epsilon=1e-8,
+             e_consts=default_energy_consts, elem_info=default_elem_info, detector_type="Si", escape_factor=0.0):
+    """Fit one spectrum (opt.py:165-327).  Returns (tensors, spec_fit, bkg, loss_trace) like the
+    reference; amplitudes are log10 in the tensor dict.
+
+    With ``tune_params=False`` and the MSE loss the problem is a non-negative linear least-squares
+    solve, done directly on the GPU (what the reference's Adam loop converges to); the iteration
+    controls (optimizer, n_iter, init_amp) are accepted for source compatibility and ignored."""
+    assert loss in ["mse", "l1"], "Loss function not supported"
+    assert optimizer in ["adam", "adamw"], "Optimizer not supported"
+    if tune_params:
+        from mapstorch_b200.refine import fit_spec_global
+
+        return fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals,
+                               fixed_param_vals, indices, use_snip, n_iter, e_consts, elem_info, detector_type,
+                               escape_factor, device, verbose)
+    if loss != "mse" or l1_lambda > 0:
+        raise NotImplementedError("only the MSE objective without L1 penalty has a direct solve (SURVEY.md 8f.4)")
+    _native.require_device()
+    spec = torch.as_tensor(np.asarray(int_spec, dtype=np.float32) if not isinstance(int_spec, torch.Tensor)
+                           else int_spec.detach().float().cpu().numpy())
+    elements = list(dict.fromkeys(list(elements_to_fit)))
+    maps, plan = fit_map(spec.reshape(1, -1), energy_range, elements, init_param_vals, fixed_param_vals, indices,
+                         use_snip, e_consts, elem_info, detector_type, escape_factor, return_plan=True)
+    tensors, _ = create_tensors(plan.names, [], init_param_vals, fixed_param_vals, tune_params=False, device=device)
+    amps = torch.stack([maps[n].reshape(()) for n in plan.names])
+    for n, a in zip(plan.names, amps):
+        tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
+    spec_fit = (amps[None, :] @ plan.basis).reshape(-1)
+    cropped = spec[plan.er[0]: plan.er[1] + 1].cuda()
+    if use_snip:
+        p = plan.params
+        bkg = _bkg.snip_bkg(cropped, plan.er, *(torch.tensor(float(p[k])) for k in (
+            "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")),
+            device="cuda")
+    else:
+        bkg = torch.zeros_like(cropped)
+    resid = spec_fit + bkg - cropped
+    if indices is not None:
+        resid = resid[torch.as_tensor(np.asarray(indices), device="cuda")]
+    loss_trace = [float(torch.sum(resid * resid).item())]
+    return tensors, spec_fit.cpu().numpy(), bkg.cpu().numpy(), loss_trace

@@ -1,0 +1,398 @@
+"""CPU oracle of the per-pixel XRF map-fitting hot path.  TEST INFRASTRUCTURE ONLY.
+
+A NumPy restatement of the reference algorithm (xyin-anl/MapsTorch), written from the
+reference sources; every function cites the file:line it follows.  It exists so that the
+CUDA path can be checked on the GPU box, where /root/reference does not exist.  Only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import it; the product package ``mapstorch_b200`` never does.
+
+Parity pinning: the reference ships no tests or golden vectors, so the oracle
+is pinned against outputs of the reference itself, generated in the build container by
+``tests/golden/make_golden.py`` and committed under ``tests/golden/*.npz``
+(``tests/test_oracle_golden.py`` checks oracle == golden on every CPU run).
+
+The element dictionaries come from ``mapstorch_b200.default`` (host-side data, themselves
+verified field-by-field against the reference dump in ``tests/test_dictionaries.py``).
+"""
+import math
+
+import numpy as np
+from scipy.special import erfc as _erfc
+
+f32 = np.float32
+M_PI = math.pi
+M_SQRT2 = math.sqrt(2)
+SQRT_2XPI = math.sqrt(2 * math.pi)
+SCATTER = ("COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE")
+
+
+def _defaults():
+    from mapstorch_b200 import default
+
+    return default
+
+
+def p32(params, key):
+    v = params[key]
+    return f32(v.item() if hasattr(v, "item") else v)
+
+
+# ---- forward model ---------------------------------------------------------------------------
+def energy_axis(params, energy_range):
+    """map.py:271-281: ev = off + slope*c + quad*c**2, all fp32, evaluated left to right."""
+    c = np.arange(energy_range[0], energy_range[1] + 1, dtype=np.float32)
+    return (p32(params, "ENERGY_OFFSET") + p32(params, "ENERGY_SLOPE") * c) + p32(params, "ENERGY_QUADRATIC") * (c * c)
+
+
+def erfc32(x):
+    return _erfc(x.astype(np.float64)).astype(np.float32)
+
+
+def peak(gain, sigma, delta):
+    """map.py:57-58."""
+    q = delta / sigma
+    return (gain / (sigma * f32(SQRT_2XPI))) * np.exp(f32(-0.5) * (q * q))
+
+
+def step(gain, sigma, delta, peak_e):
+    """map.py:61-62."""
+    return (gain / f32(2.0) / f32(peak_e)) * erfc32(delta / (f32(M_SQRT2) * sigma))
+
+
+def tail(gain, sigma, delta, gamma):
+    """map.py:65-69."""
+    v1 = erfc32(delta / (f32(M_SQRT2) * sigma) + (f32(1.0) / (gamma * f32(M_SQRT2))))
+    with np.errstate(over="ignore", invalid="ignore"):
+        v2 = np.exp(delta / (gamma * sigma)) * v1
+    d_e = np.where(delta < 0, v2, v1)
+    norm = np.exp((f32(1.0) / (gamma * gamma)) * f32(-0.5))
+    return (gain / f32(2.0) / gamma / sigma / norm) * d_e
+
+
+def _sigma(params, e_times_296):
+    a = p32(params, "FWHM_OFFSET") / f32(2.3548)
+    return np.sqrt(a * a + e_times_296 * p32(params, "FWHM_FANOPRIME"))
+
+
+def compton_energy(params):
+    """map.py:83-87."""
+    e0 = p32(params, "COHERENT_SCT_ENERGY")
+    ang = p32(params, "COMPTON_ANGLE") * f32(2) * f32(M_PI) / f32(360.0)
+    return e0 / (f32(1) + (e0 / f32(511)) * (f32(1) - np.cos(ang)))
+
+
+def elastic_peak(params, ev, gain):
+    """map.py:72-79."""
+    e0 = p32(params, "COHERENT_SCT_ENERGY")
+    sigma = _sigma(params, e0 * f32(2.96))
+    amp = np.power(f32(10), p32(params, "COHERENT_SCT_AMPLITUDE"))
+    return amp * peak(f32(gain), sigma, ev - e0)
+
+
+def compton_peak(params, ev, gain, use_step=True, use_tail=False):
+    """map.py:82-124."""
+    gain = f32(gain)
+    ce = compton_energy(params)
+    sigma = _sigma(params, ce * f32(2.96))
+    delta = ev - ce
+    f_step, f_tail, hi_tail = (p32(params, k) for k in ("COMPTON_F_STEP", "COMPTON_F_TAIL", "COMPTON_HI_F_TAIL"))
+    norm = f32(1.0)
+    if use_step and f_step > 0:
+        norm = norm + f_step
+    if use_tail:
+        if f_tail > 0:
+            norm = norm + f_tail
+        if hi_tail > 0:
+            norm = norm + hi_tail
+    faktor = np.power(f32(10), p32(params, "COMPTON_AMPLITUDE")) / norm
+    counts = faktor * peak(gain, sigma * p32(params, "COMPTON_FWHM_CORR"), delta)
+    if use_step and f_step > 0:
+        counts = counts + (faktor * f_step) * step(gain, sigma, delta, ce)
+    if use_tail:
+        if f_tail > 0:
+            counts = counts + (faktor * f_tail) * tail(gain, sigma, delta, p32(params, "COMPTON_GAMMA"))
+        if hi_tail > 0:
+            counts = counts + (faktor * hi_tail) * tail(gain, sigma, -delta, p32(params, "COMPTON_HI_GAMMA"))
+    return counts.astype(np.float32)
+
+
+_TAIL_LINES = ("Ka1", "Ka2", "La1", "La2", "Lb1", "Lb2", "Lb3", "Lb4", "Lg1", "Lg2", "Lg3", "Lg4", "Ll", "Ln")
+
+
+def model_elem_spec(params, element, ev, use_step=True, use_tail=True, e_consts=None, elem_info=None):
+    """map.py:152-257, fp32, same accumulation order."""
+    d = _defaults()
+    e_consts = d.default_energy_consts if e_consts is None else e_consts
+    elem_info = d.default_elem_info if elem_info is None else elem_info
+    gain = p32(params, "ENERGY_SLOPE")
+    e0 = p32(params, "COHERENT_SCT_ENERGY")
+    spec = np.zeros_like(ev, dtype=np.float32)
+    pre = np.power(f32(10), p32(params, element))
+    for s in e_consts[element]:
+        sigma = _sigma(params, f32(s.energy * 2.96))
+        mu, en = f32(s.mu_fraction), f32(s.energy)
+        f_step = np.abs(mu * (p32(params, "F_STEP_OFFSET") + p32(params, "F_STEP_LINEAR") * en))
+        f_tail = np.abs(p32(params, "F_TAIL_OFFSET") + p32(params, "F_TAIL_LINEAR") * mu)
+        kb_f_tail = np.abs(p32(params, "KB_F_TAIL_OFFSET") + p32(params, "KB_F_TAIL_LINEAR") * mu)
+        if s.ratio == 0 or s.energy <= 0:
+            continue
+        delta = ev - en
+        faktor = f32(s.ratio) * pre
+        if s.check_binding_energy(elem_info, e0):
+            if s.ptype.startswith("Ka") or s.ptype.startswith("L"):
+                faktor = faktor / ((f32(1.0) + f_step + f_tail) if use_tail else (f32(1.0) + f_step))
+            elif s.ptype.startswith("Kb"):
+                faktor = faktor / ((f32(1.0) + f_step + kb_f_tail) if use_tail else (f32(1.0) + f_step))
+        else:
+            faktor = f32(0)
+        spec = spec + faktor * peak(gain, sigma, delta)
+        if f_step > 0 and use_step:
+            spec = spec + (faktor * f_step) * step(gain, sigma, delta, s.energy)
+        if use_tail and (s.ptype in ("Kb1", "Kb2") or s.ptype in _TAIL_LINES):
+            gamma = np.abs(p32(params, "GAMMA_OFFSET") + p32(params, "GAMMA_LINEAR") * en) * f32(s.width_multi)
+            frac = kb_f_tail if s.ptype in ("Kb1", "Kb2") else f_tail
+            spec = spec + (faktor * frac) * tail(gain, sigma, delta, gamma)
+    return spec.astype(np.float32)
+
+
+def escape_peak(spectrum, ev, escape_factor, detector_type="Si"):
+    """map.py:127-150."""
+    esc_e = 9.886 if detector_type == "Ge" else 1.73998
+    out = np.zeros_like(spectrum)
+    if ev.size < 2:
+        return out
+    delta_e = float(np.mean((ev[1:] - ev[:-1]).astype(np.float32), dtype=np.float32))
+    if delta_e <= 0:
+        return out
+    bins = int(round(esc_e / delta_e))
+    if bins < ev.size:
+        out[: ev.size - bins] = spectrum[bins:] * f32(escape_factor)
+    return out
+
+
+def model_spec(params, energy_range, elements_to_fit, e_consts=None, elem_info=None, detector_type="Si",
+               escape_factor=0.0):
+    """map.py:260-309 (elements with use_step=True, use_tail=False)."""
+    d = _defaults()
+    e_consts = d.default_energy_consts if e_consts is None else e_consts
+    ev = energy_axis(params, energy_range)
+    agr = np.zeros_like(ev)
+    for e in elements_to_fit:
+        if e in e_consts and e not in SCATTER:
+            agr = agr + model_elem_spec(params, e, ev, True, False, e_consts, elem_info)
+    gain = p32(params, "ENERGY_SLOPE")
+    agr = agr + elastic_peak(params, ev, gain)
+    agr = agr + compton_peak(params, ev, gain, True, False)
+    if escape_factor > 0.0:
+        agr = agr + escape_peak(agr, ev, escape_factor, detector_type)
+    return agr.astype(np.float32)
+
+
+def component_names(elements_to_fit, e_consts=None):
+    d = _defaults()
+    e_consts = d.default_energy_consts if e_consts is None else e_consts
+    return [e for e in elements_to_fit if e in e_consts and e not in SCATTER] + [
+        "COHERENT_SCT_AMPLITUDE", "COMPTON_AMPLITUDE"]
+
+
+def basis(params, energy_range, elements_to_fit, e_consts=None, elem_info=None, detector_type="Si",
+          escape_factor=0.0):
+    """Unit-amplitude columns [C, E] of model_spec (the model is linear in 10**a)."""
+    names = component_names(elements_to_fit, e_consts)
+    ev = energy_axis(params, energy_range)
+    unit = dict(params)
+    cols = []
+    for n in names:
+        unit[n] = 0.0
+        if n == "COHERENT_SCT_AMPLITUDE":
+            col = elastic_peak(unit, ev, p32(params, "ENERGY_SLOPE"))
+        elif n == "COMPTON_AMPLITUDE":
+            col = compton_peak(unit, ev, p32(params, "ENERGY_SLOPE"), True, False)
+        else:
+            col = model_elem_spec(unit, n, ev, True, False, e_consts, elem_info)
+        if escape_factor > 0.0:
+            col = col + escape_peak(col, ev, escape_factor, detector_type)
+        cols.append(col.astype(np.float32))
+    return np.stack(cols, axis=1), names
+
+
+# ---- evaluation of compiled term tables (mirror of csrc/mt_model.cu arithmetic) --------------
+def eval_terms(terms, col_start, ev):
+    ev = np.asarray(ev, dtype=np.float32)
+    out = np.zeros((len(col_start) - 1, ev.size), dtype=np.float32)
+    for col in range(len(col_start) - 1):
+        acc = np.zeros_like(ev)
+        for t in terms[col_start[col]: col_start[col + 1]]:
+            d = ev - t["e"]
+            if t["sign"] < 0:
+                d = -d
+            if t["kind"] == 0:
+                q = d / t["p0"]
+                v = t["amp"] * (t["p1"] * np.exp(f32(-0.5) * (q * q)))
+            elif t["kind"] == 1:
+                v = t["amp"] * (t["p1"] * erfc32(d / t["p0"]))
+            else:
+                v1 = erfc32(d / t["p0"] + t["p1"])
+                with np.errstate(over="ignore", invalid="ignore"):
+                    v2 = np.exp(d / t["p2"]) * v1
+                v = t["amp"] * (t["p3"] * np.where(d < 0, v2, v1))
+            acc = acc + v.astype(np.float32)
+        out[col] = acc
+    return out
+
+
+# ---- SNIP background -------------------------------------------------------------------------
+def snip_widths(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+    """bkg.py:83-91 in fp32."""
+    idx = np.arange(n_ch, dtype=np.float32) + f32(ch0)
+    energy = (f32(e_offset) + f32(e_slope) * idx) + f32(e_quad) * (idx * idx)
+    a = f32(fwhm_offset) / f32(2.3548)
+    sigma_sq = np.maximum(a * a + (energy * f32(2.96)) * f32(fwhm_fanoprime), f32(0))
+    return (f32(snip_width) * f32(2.35)) * np.sqrt(sigma_sq) / f32(e_slope)
+
+
+def snip_indices(n_ch, width):
+    """bkg.py:57-62: clamp in fp32, then truncate."""
+    i = np.arange(n_ch, dtype=np.float32)
+    lo = np.clip(i - width, f32(0), f32(n_ch - 1)).astype(np.int64)
+    hi = np.clip(i + width, f32(0), f32(n_ch - 1)).astype(np.int64)
+    return lo, hi
+
+
+def snip_pass_tables(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+    """Pass schedule of bkg.py:104-112 -> list of (lo, hi)."""
+    w = snip_widths(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
+    passes = [snip_indices(n_ch, w), snip_indices(n_ch, w)]
+    while float(np.max(w)) >= 0.5:
+        passes.append(snip_indices(n_ch, w))
+        w = (w / f32(M_SQRT2)).astype(np.float32)
+    return passes
+
+
+def snip_bkg(spec, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime, boxcar_size=5):
+    """bkg.py:69-114 for spec[..., C]."""
+    spec = np.asarray(spec, dtype=np.float32)
+    n_ch = spec.shape[-1]
+    flat = spec.reshape(-1, n_ch)
+    half = boxcar_size // 2
+    padded = np.pad(flat, ((0, 0), (half, half)))
+    bg = np.zeros_like(flat)
+    w = f32(1.0) / f32(boxcar_size)
+    for j in range(boxcar_size):
+        bg = bg + padded[:, j: j + n_ch] * w
+    with np.errstate(all="ignore"):
+        bg = np.log1p(bg)
+    bg = np.nan_to_num(bg, nan=0.0, posinf=0.0, neginf=0.0)
+    for lo, hi in snip_pass_tables(n_ch, er[0], e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+        bg = np.minimum((bg[:, lo] + bg[:, hi]) / f32(2), bg)
+    with np.errstate(all="ignore"):
+        bg = np.expm1(bg)
+    return np.nan_to_num(bg, nan=0.0, posinf=0.0, neginf=0.0).reshape(spec.shape).astype(np.float32)
+
+
+# ---- initial amplitudes, peak windows --------------------------------------------------------
+def init_elem_amps(elem, spec, e_sct, e_offset, e_slope, e_consts=None, compton_angle=None):
+    """opt.py:63-97."""
+    e_consts = _defaults().default_energy_consts if e_consts is None else e_consts
+    try:
+        if elem in SCATTER:
+            if elem == "COMPTON_AMPLITUDE" and compton_angle is not None:
+                th = np.deg2rad(compton_angle)
+                e_energy = e_sct / (1.0 + (e_sct / 511.0) * (1.0 - np.cos(th)))
+            else:
+                e_energy = e_sct
+            min_e, max_e = e_energy - 0.4, e_energy + 0.4
+        else:
+            e_energy = e_consts[elem][0].energy
+            min_e, max_e = e_energy - 0.1, e_energy + 0.1
+        er_min = max(0, round((min_e - e_offset) / e_slope))
+        er_max = min(spec.shape[-1] - 1, round((max_e - e_offset) / e_slope))
+        er_size = (er_max + 1) - er_min
+        e_sum = np.sum(spec[..., er_min: er_max + 1], axis=-1) / er_size
+        return np.log10(np.maximum(e_sum * 8.0 + 0.01, 1.0))
+    except Exception:
+        return 0.0
+
+
+def get_peak_ranges(elements, coherent_sct_energy, compton_angle, energy_offset, energy_slope, energy_quadratic,
+                    energy_range, e_consts=None):
+    """util.py:60-108 (float64 energy axis, first channel with ev >= bound)."""
+    d = _defaults()
+    e_consts = d.default_energy_consts if e_consts is None else e_consts
+    ch = np.arange(energy_range[0], energy_range[1] + 1, dtype=float)
+    ev = energy_offset + energy_slope * ch + energy_quadratic * (ch ** 2)
+    centers = {}
+    for e in elements:
+        if e == "COMPTON_AMPLITUDE":
+            centers[e] = coherent_sct_energy / (
+                1 + (coherent_sct_energy / 511) * (1 - math.cos(compton_angle * 2 * M_PI / 360.0)))
+        elif e == "COHERENT_SCT_AMPLITUDE":
+            centers[e] = coherent_sct_energy
+        elif e in d.default_fitting_elems:
+            for i, er in enumerate(e_consts[e]):
+                if er.energy > 0:
+                    centers[e + "_" + str(i)] = er.energy
+
+    def chan(energy):
+        hits = np.nonzero(ev >= energy)[0]
+        return int(hits[0]) if hits.size else len(ev) - 1
+
+    out = {}
+    for name, c in centers.items():
+        width = math.sqrt(150.0 ** 2 + (c * 12.0) ** 2) / 2000
+        out[name] = (chan(c - width), chan(c + width))
+    return out
+
+
+# ---- the fit ---------------------------------------------------------------------------------
+def fit_lstsq(spectra, B, bkg=None):
+    """float64 unconstrained least squares of (spectra - bkg) on the basis columns B [C,E]."""
+    y = np.asarray(spectra, dtype=np.float64).reshape(-1, B.shape[0])
+    if bkg is not None:
+        y = y - np.asarray(bkg, dtype=np.float64).reshape(y.shape)
+    sol, *_ = np.linalg.lstsq(B.astype(np.float64), y.T, rcond=None)
+    return sol.T
+
+
+def fit_nnls(spectra, B, bkg=None):
+    """float64 NNLS per spectrum: what the reference's 10**a parametrisation converges to
+    (SURVEY.md 0.4)."""
+    from scipy.optimize import nnls
+
+    y = np.asarray(spectra, dtype=np.float64).reshape(-1, B.shape[0])
+    if bkg is not None:
+        y = y - np.asarray(bkg, dtype=np.float64).reshape(y.shape)
+    B64 = B.astype(np.float64)
+    return np.stack([nnls(B64, row, maxiter=50 * B.shape[1])[0] for row in y])
+
+
+def fit_spec_adam(spectrum, B, bkg=None, init_log_amps=None, n_iter=500, lr=1e-2, loss="mse", betas=(0.9, 0.999),
+                  eps=1e-8):
+    """The reference's per-spectrum fit (opt.py:165-327) with tune_params=False: Adam on the
+    log10 amplitudes, objective sum((B @ 10**a + bkg - y)**2) (opt.py:371-375), torch.optim.Adam
+    update rule, fp32 state.  Gradients are analytic (the model is linear in 10**a)."""
+    y = np.asarray(spectrum, dtype=np.float32)
+    bk = np.zeros_like(y) if bkg is None else np.asarray(bkg, dtype=np.float32)
+    a = np.zeros(B.shape[1], dtype=np.float32) if init_log_amps is None else np.asarray(init_log_amps, np.float32).copy()
+    m = np.zeros_like(a)
+    v = np.zeros_like(a)
+    ln10 = f32(math.log(10.0))
+    trace = []
+    for t in range(1, n_iter + 1):
+        amp = np.power(f32(10), a)
+        r = (B @ amp + bk) - y
+        if loss == "mse":
+            trace.append(float(np.sum(r * r)))
+            g_amp = f32(2) * (B.T @ r)
+        else:
+            trace.append(float(np.sum(np.abs(r))))
+            g_amp = B.T @ np.sign(r)
+        g = (g_amp * amp * ln10).astype(np.float32)
+        m = f32(betas[0]) * m + f32(1 - betas[0]) * g
+        v = f32(betas[1]) * v + f32(1 - betas[1]) * (g * g)
+        bc1 = 1 - betas[0] ** t
+        bc2 = 1 - betas[1] ** t
+        step_size = lr / bc1
+        denom = np.sqrt(v) / f32(math.sqrt(bc2)) + f32(eps)
+        a = (a - f32(step_size) * (m / denom)).astype(np.float32)
+    return a, trace

@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+Only runs in the build container, where the unmodified reference is mounted read-only at
+/root/reference (it cannot travel to the GPU box; the fixtures do):
+
+    PYTHONHASHSEED=0 python tests/golden/make_golden.py [--skip-fit]
+
+Outputs (np.savez_compressed):
+  model_golden.npz  model_elem_spec / compton_peak / elastic_peak / model_spec outputs
+  snip_golden.npz   snip_bkg inputs+outputs and the per-pass gather indices
+  fit_golden.npz    per-spectrum fit_spec(tune_params=False) runs (converged Adam) + loss traces
+  host_golden.npz   init_elem_amps, get_peak_ranges, escape bins
+The reference ships no tests or fixtures of its own, so these are the pins.
+"""
+import argparse
+import os
+import sys
+import types
+import warnings
+from pathlib import Path
+
+warnings.filterwarnings("ignore")
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+if os.environ.get("PYTHONHASHSEED") != "0":
+    print("re-exec with PYTHONHASHSEED=0 (fit_spec iterates a set() of element names, opt.py:194-200)")
+    os.environ["PYTHONHASHSEED"] = "0"
+    os.execv(sys.executable, [sys.executable] + sys.argv)
+
+sys.path.insert(0, "/root/reference")
+# mapstorch.util imports two UI packages that are not installed; stub them (only the pure helpers are used)
+for _name in ("anywidget", "traitlets"):
+    _m = types.ModuleType(_name)
+    sys.modules[_name] = _m
+sys.modules["anywidget"].AnyWidget = type("AnyWidget", (), {})
+
+
+class _Trait:
+    def __init__(self, *a, **k):
+        pass
+
+    def tag(self, **k):
+        return self
+
+
+for _t in ("Dict", "List", "Int", "Unicode", "Bool", "Float"):
+    setattr(sys.modules["traitlets"], _t, _Trait)
+
+from mapstorch import bkg as rbkg, map as rmap, opt as ropt, util as rutil  # noqa: E402
+from mapstorch.default import default_param_vals, default_fitting_elems, default_energy_consts  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+ELEMS10 = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+ELEMS20 = "Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As".split()
+ELEMS30 = ELEMS20[:19] + "Ba_L Ce_L Gd_L W_L Pt_L Au_L Au_M Pt_M Hg_M W_M Si_Si".split()
+MODEL_ELEMS = ["Fe", "Ca", "Zn", "Si", "Pb_L", "Au_L", "Ba_L", "Au_M", "Pt_M", "Si_Si", "Si_Cl", "Hf_L"]
+
+
+def params_a():
+    p = dict(default_param_vals)
+    p["COHERENT_SCT_ENERGY"] = 12.0
+    return p
+
+
+def params_b():
+    p = dict(default_param_vals)
+    p.update({"COHERENT_SCT_ENERGY": 17.5, "F_STEP_OFFSET": 0.002, "F_STEP_LINEAR": 0.0004,
+              "COMPTON_F_STEP": 0.01, "GAMMA_LINEAR": 0.05, "F_TAIL_LINEAR": 1e-4, "KB_F_TAIL_LINEAR": 2e-4,
+              "ENERGY_OFFSET": 0.0113, "FWHM_OFFSET": 0.0912})
+    return p
+
+
+def params_4096():
+    p = params_a()
+    p.update({"ENERGY_SLOPE": 0.00599, "ENERGY_QUADRATIC": 0.0})
+    return p
+
+
+def tens(p, extra=None):
+    t = {k: torch.tensor(float(v)) for k, v in p.items()}
+    for k, v in (extra or {}).items():
+        t[k] = torch.tensor(float(v))
+    return t
+
+
+def ev_of(t, er):
+    ch = torch.arange(er[0], er[1] + 1, dtype=torch.float32)
+    return t["ENERGY_OFFSET"] + t["ENERGY_SLOPE"] * ch + t["ENERGY_QUADRATIC"] * (ch ** 2)
+
+
+def gen_model(out):
+    for tag, p, er in (("a", params_a(), (0, 2047)), ("b", params_b(), (50, 1450)), ("c", params_4096(), (0, 4095))):
+        out[f"{tag}_er"] = np.array(er)
+        out[f"{tag}_param_names"] = np.array(list(p.keys()))
+        out[f"{tag}_param_vals"] = np.array([p[k] for k in p], dtype=np.float64)
+        for logamp in (0.0, 2.3):
+            t = tens(p, {e: logamp for e in default_fitting_elems})
+            ev = ev_of(t, er)
+            if logamp == 0.0:
+                out[f"{tag}_ev"] = ev.numpy()
+            for us in (False, True):
+                for ut in (False, True):
+                    if tag == "c" and (logamp != 0.0):
+                        continue
+                    key = f"{tag}_amp{logamp}_s{int(us)}_t{int(ut)}"
+                    cols = [rmap.model_elem_spec(t, e, ev, us, ut).numpy() for e in MODEL_ELEMS]
+                    out[key + "_elems"] = np.stack(cols)
+                    out[key + "_compton"] = rmap.compton_peak(t, ev, t["ENERGY_SLOPE"], us, ut).numpy()
+            out[f"{tag}_amp{logamp}_elastic"] = rmap.elastic_peak(t, ev, t["ENERGY_SLOPE"]).numpy()
+        # every default component at unit amplitude, default flags of model_spec: compact statistics
+        t = tens(p, {e: 0.0 for e in default_fitting_elems})
+        ev = ev_of(t, er)
+        names = [e for e in default_fitting_elems if e in default_energy_consts]
+        stats = []
+        for e in names:
+            c = rmap.model_elem_spec(t, e, ev, True, False).numpy().astype(np.float64)
+            stats.append([c.sum(), c.max(), float(c.argmax()), (c * c).sum()])
+        out[f"{tag}_all_names"] = np.array(names)
+        out[f"{tag}_all_stats"] = np.array(stats)
+        # model_spec with amplitudes, with and without escape peaks
+        rng = np.random.default_rng(7)
+        for set_name, elems in (("e10", ELEMS10), ("e30", ELEMS30)):
+            amps = {e: float(rng.uniform(1.5, 3.0)) for e in elems + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]}
+            t = tens(p, amps)
+            out[f"{tag}_{set_name}_logamps"] = np.array([amps[e] for e in elems + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]])
+            out[f"{tag}_{set_name}_spec"] = rmap.model_spec(t, er, elems).numpy()
+            out[f"{tag}_{set_name}_spec_si"] = rmap.model_spec(t, er, elems, detector_type="Si", escape_factor=0.05).numpy()
+            out[f"{tag}_{set_name}_spec_ge"] = rmap.model_spec(t, er, elems, detector_type="Ge", escape_factor=0.02).numpy()
+    out["model_elems"] = np.array(MODEL_ELEMS)
+    out["elems10"], out["elems30"] = np.array(ELEMS10), np.array(ELEMS30)
+
+
+def synth_spectrum(p, er_full, elems, rng, lo=1.5, hi=3.0, flat=2.0):
+    amps = {e: float(rng.uniform(lo, hi)) for e in elems + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]}
+    t = tens(p, amps)
+    lam = rmap.model_spec(t, er_full, elems).numpy().astype(np.float64) + flat
+    return rng.poisson(lam).astype(np.float32), amps
+
+
+def gen_snip(out):
+    rng = np.random.default_rng(11)
+    cases = (("c2048", params_a(), (0, 2047), ELEMS10), ("c1401", params_a(), (50, 1450), ELEMS10),
+             ("c4096", params_4096(), (0, 4095), ELEMS30))
+    for tag, p, er, elems in cases:
+        n_full = 2048 if tag != "c4096" else 4096
+        specs = np.stack([synth_spectrum(p, (0, n_full - 1), elems, rng, flat=f)[0] for f in (0.0, 2.0, 40.0)])
+        # a few awkward rows: all zero, single spike, negative values
+        odd = np.zeros((3, n_full), dtype=np.float32)
+        odd[1, n_full // 3] = 1000.0
+        odd[2] = rng.normal(0, 3, n_full).astype(np.float32)
+        specs = np.concatenate([specs, odd])
+        crop = specs[:, er[0]: er[1] + 1]
+        t = tens(p)
+        args = (t["ENERGY_OFFSET"], t["ENERGY_SLOPE"], t["ENERGY_QUADRATIC"], t["SNIP_WIDTH"], t["FWHM_OFFSET"],
+                t["FWHM_FANOPRIME"])
+        batch = rbkg.snip_bkg(torch.tensor(crop), er, *args).numpy()
+        single = rbkg.snip_bkg(torch.tensor(crop[1]), er, *args).numpy()
+        assert np.array_equal(batch[1], single)
+        out[f"{tag}_er"] = np.array(er)
+        out[f"{tag}_spec"] = crop
+        out[f"{tag}_bkg"] = batch
+        out[f"{tag}_params"] = np.array([float(a) for a in args], dtype=np.float64)
+        # per-pass gather indices, replaying bkg.py:83-112 / 57-62 with the reference's own ops
+        n_ch = crop.shape[-1]
+        local = torch.arange(n_ch, dtype=torch.float32)
+        gidx = local + er[0]
+        energy = args[0] + (args[1] * gidx) + (args[2] * (gidx ** 2))
+        sig = torch.clamp((args[4] / 2.3548) ** 2 + energy * 2.96 * args[5], min=0.0)
+        w = args[3] * 2.35 * torch.sqrt(sig) / args[1]
+        tabs = []
+
+        def idx(w):
+            lo = torch.clamp(local - w, 0, n_ch - 1).to(torch.int64)
+            hi = torch.clamp(local + w, 0, n_ch - 1).to(torch.int64)
+            return torch.stack([lo, hi]).numpy().astype(np.int32)
+
+        tabs += [idx(w), idx(w)]
+        from mapstorch.constant import M_SQRT2
+        while torch.max(w).item() >= 0.5:
+            tabs.append(idx(w))
+            w = w / M_SQRT2
+        out[f"{tag}_lohi"] = np.stack(tabs)
+
+
+def gen_host(out):
+    rng = np.random.default_rng(5)
+    p = params_a()
+    spec, _ = synth_spectrum(p, (0, 2047), ELEMS10, rng)
+    vol = rng.poisson(5.0, size=(3, 4, 2048)).astype(np.float32) + spec
+    out["init_spec"], out["init_vol"] = spec, vol
+    names = list(default_fitting_elems)
+    out["init_names"] = np.array(names)
+    out["init_amps_spec"] = np.array([float(ropt.init_elem_amps(e, spec, 12.0, p["ENERGY_OFFSET"], p["ENERGY_SLOPE"],
+                                                               compton_angle=p["COMPTON_ANGLE"])) for e in names])
+    out["init_amps_vol"] = np.stack([np.asarray(ropt.init_elem_amps(e, vol, 12.0, p["ENERGY_OFFSET"], p["ENERGY_SLOPE"],
+                                                                    compton_angle=p["COMPTON_ANGLE"]), dtype=np.float64)
+                                     * np.ones((3, 4)) for e in names])
+    for tag, pp, er in (("a", params_a(), (0, 2047)), ("b", params_b(), (50, 1450)), ("c", params_4096(), (0, 4095))):
+        rr = rutil.get_peak_ranges(names, pp["COHERENT_SCT_ENERGY"], pp["COMPTON_ANGLE"], pp["ENERGY_OFFSET"],
+                                   pp["ENERGY_SLOPE"], pp["ENERGY_QUADRATIC"], er)
+        out[f"ranges_{tag}_keys"] = np.array(list(rr.keys()))
+        out[f"ranges_{tag}_vals"] = np.array(list(rr.values()), dtype=np.int64)
+        t = tens(pp)
+        ev = ev_of(t, er)
+        bins = []
+        for det, esc in (("Si", 1.73998), ("Ge", 9.886)):
+            delta_e = torch.mean(ev[1:] - ev[:-1]).item()
+            bins.append(int(round(esc / delta_e)))
+        out[f"escape_bins_{tag}"] = np.array(bins)
+
+
+def gen_fit(out, quick):
+    torch.set_num_threads(8)
+    rng = np.random.default_rng(3)
+    runs = []
+    p = params_a()
+    for i, (lo, hi) in enumerate(((1.5, 3.0), (1.5, 3.0), (0.0, 2.0))):
+        spec, amps = synth_spectrum(p, (0, 2047), ELEMS10, rng, lo, hi, flat=0.0)
+        runs.append((f"e10_px{i}", p, (0, 2047), ELEMS10, spec, False, 500 if quick else 4000))
+    spec, amps = synth_spectrum(p, (0, 2047), ELEMS10, rng, 1.5, 3.0, flat=3.0)
+    runs.append(("e10_snip", p, (50, 1450), ELEMS10, spec, True, 500 if quick else 4000))
+    if not quick:
+        p4 = params_4096()
+        spec, amps = synth_spectrum(p4, (0, 4095), ELEMS30, rng, 1.5, 3.0, flat=0.0)
+        runs.append(("e30_px0", p4, (0, 4095), ELEMS30, spec, False, 4000))
+    out["fit_runs"] = np.array([r[0] for r in runs])
+    for tag, pp, er, elems, spec, use_snip, n_iter in runs:
+        tensors, spec_fit, bkg, trace = ropt.fit_spec(
+            spec, er, elements_to_fit=list(elems), init_param_vals=pp, tune_params=False, init_amp=True,
+            use_snip=use_snip, loss="mse", optimizer="adam", n_iter=n_iter, progress_bar=False)
+        names = list(elems) + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+        out[f"{tag}_spec"] = spec
+        out[f"{tag}_er"] = np.array(er)
+        out[f"{tag}_names"] = np.array(names)
+        out[f"{tag}_param_names"] = np.array(list(pp.keys()))
+        out[f"{tag}_param_vals"] = np.array([pp[k] for k in pp], dtype=np.float64)
+        out[f"{tag}_logamps"] = np.array([tensors[n].item() for n in names], dtype=np.float64)
+        out[f"{tag}_spec_fit"] = spec_fit
+        out[f"{tag}_bkg"] = bkg
+        out[f"{tag}_trace"] = np.array(trace, dtype=np.float64)
+        out[f"{tag}_use_snip"] = np.array(use_snip)
+        out[f"{tag}_n_iter"] = np.array(n_iter)
+        print(tag, "final loss", trace[-1], flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-fit", action="store_true")
+    ap.add_argument("--quick-fit", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    jobs = {"model": gen_model, "snip": gen_snip, "host": gen_host}
+    for name, fn in jobs.items():
+        if args.only and args.only != name:
+            continue
+        out = {}
+        fn(out)
+        np.savez_compressed(HERE / f"{name}_golden.npz", **out)
+        print("wrote", name, (HERE / f"{name}_golden.npz").stat().st_size, flush=True)
+    if not args.skip_fit and args.only in ("", "fit"):
+        out = {}
+        gen_fit(out, args.quick_fit)
+        np.savez_compressed(HERE / "fit_golden.npz", **out)
+        print("wrote fit", (HERE / "fit_golden.npz").stat().st_size, flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+"""K3 (tensor-core contraction) + the batched non-negative solve + fit_map, on the GPU.
+
+Oracle: float64 least squares / NNLS on the oracle's basis (what the reference's per-spectrum
+Adam fit converges to) and the converged reference fits in tests/golden/fit_golden.npz.
+Tolerance (north_star): amplitudes within 1e-4 relative on interior components."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_params
+
+pytestmark = pytest.mark.gpu
+
+ELEMS10 = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+ELEMS30 = ("Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge "
+           "Ba_L Ce_L Gd_L W_L Pt_L Au_L Au_M Pt_M Hg_M W_M Si_Si").split()
+
+
+def params12(n_ch=2048):
+    from mapstorch_b200.default import default_param_vals
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    if n_ch == 4096:
+        p.update(ENERGY_SLOPE=0.00599, ENERGY_QUADRATIC=0.0)
+    return p
+
+
+def synth(p, er, elems, n_px, seed, lo=1.5, hi=3.0, flat=0.0, n_full=None):
+    from oracle import maps_oracle as mo
+
+    rng = np.random.default_rng(seed)
+    n_full = n_full or (er[1] + 1)
+    B, names = mo.basis(p, (0, n_full - 1), elems)
+    amps = 10.0 ** rng.uniform(lo, hi, size=(n_px, B.shape[1]))
+    lam = amps @ B.astype(np.float64).T + flat
+    return rng.poisson(lam).astype(np.float32), names
+
+
+def check_against(x, ref, tol=1e-4):
+    """interior components (> 1e-3 of the pixel maximum) within tol relative; the rest within tol * max."""
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    interior = ref > 1e-3 * scale
+    rel = np.abs(x - ref) / np.where(interior, np.abs(ref), scale)
+    assert rel.max() <= tol, rel.max()
+
+
+@pytest.mark.parametrize("dtype,n_ch,elems,n_px", [
+    (torch.float16, 2048, ELEMS10, 300), (torch.float32, 2048, ELEMS10, 257),
+    (torch.float16, 4096, ELEMS30, 513), (torch.float32, 4096, ELEMS30, 128),
+    (torch.float32, 2048, ELEMS10, 1), (torch.float16, 2048, ELEMS10, 127),
+])
+def test_unconstrained_solution_matches_float64_lstsq(dtype, n_ch, elems, n_px):
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12(n_ch)
+    er = (0, n_ch - 1)
+    y, names = synth(p, er, elems, n_px, seed=n_px)
+    assert y.max() < 2048
+    plan = opt.MapFitPlan(er, elems, p, use_snip=False)
+    assert plan.names == names
+    B, _ = mo.basis(p, er, elems)
+    ref = mo.fit_lstsq(y, B)
+    dev = torch.from_numpy(y).to("cuda", dtype)
+    x = plan.fit(dev, nonneg=False).cpu().numpy().T
+    check_against(x, ref, 2e-5)
+    xs = plan.fit(dev, nonneg=False, engine="simt").cpu().numpy().T
+    check_against(xs, ref, 2e-5)
+
+
+def test_energy_range_crop_and_unaligned_rows():
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12()
+    er = (50, 1450)
+    y, names = synth(p, er, ELEMS10, 200, seed=5, n_full=2048)
+    B, _ = mo.basis(p, er, ELEMS10)
+    ref = mo.fit_lstsq(y[:, 50:1451], B)
+    plan = opt.MapFitPlan(er, ELEMS10, p, use_snip=False)
+    x = plan.fit(torch.from_numpy(y).cuda(), nonneg=False).cpu().numpy().T
+    check_against(x, ref, 2e-5)
+    # rows whose pitch is not a multiple of 16 bytes cannot go through TMA: CUDA-core path
+    odd = torch.from_numpy(np.ascontiguousarray(y[:, :2046])).cuda()
+    x2 = plan.fit(odd, nonneg=False).cpu().numpy().T
+    check_against(x2, ref, 2e-5)
+
+
+def test_nonnegative_solve_matches_scipy_nnls():
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12(4096)
+    er = (0, 4095)
+    y, names = synth(p, er, ELEMS30, 96, seed=21, lo=-0.5, hi=1.5)  # low counts: many clamped components
+    B, _ = mo.basis(p, er, ELEMS30)
+    ref = mo.fit_nnls(y, B)
+    assert (ref == 0).mean() > 0.05
+    plan = opt.MapFitPlan(er, ELEMS30, p, use_snip=False)
+    n_fixed = torch.zeros(1, dtype=torch.int32, device="cuda")
+    x = plan.fit(torch.from_numpy(y).half().cuda(), nonneg=True, n_fixed=n_fixed).cpu().numpy().T
+    assert (x >= 0).all() and int(n_fixed) > 0
+    scale = ref.max(axis=1, keepdims=True)
+    assert (np.abs(x - ref) / scale).max() <= 1e-4
+    interior = ref > 1e-3 * scale
+    assert (np.abs(x - ref)[interior] / ref[interior]).max() <= 2e-3
+    # objective value: never worse than scipy's
+    r_mine = ((y - x @ B.T.astype(np.float64)) ** 2).sum(axis=1)
+    r_ref = ((y - ref @ B.T.astype(np.float64)) ** 2).sum(axis=1)
+    assert np.all(r_mine <= r_ref * (1 + 1e-6))
+
+
+def test_fit_map_matches_converged_reference_fits(fit_golden):
+    """fit_golden holds fit_spec(tune_params=False, optimizer='adam', n_iter=4000) of the reference."""
+    from mapstorch_b200 import opt
+
+    g = fit_golden
+    for tag in [str(t) for t in g["fit_runs"]]:
+        p = golden_params(g, tag)
+        er = tuple(int(v) for v in g[f"{tag}_er"])
+        names = [str(n) for n in g[f"{tag}_names"]]
+        use_snip = bool(g[f"{tag}_use_snip"])
+        spec = g[f"{tag}_spec"]
+        maps = opt.fit_map(spec.reshape(1, 1, -1), er, names[:-2], init_param_vals=p, use_snip=use_snip, device="cpu")
+        ref = np.array([10.0 ** v for v in g[f"{tag}_logamps"]])
+        mine = np.array([float(maps[n]) for n in names])
+        interior = ref > 1e-3 * ref.max()
+        assert (np.abs(mine - ref)[interior] / ref[interior]).max() <= 1e-4, tag
+        assert np.all(mine[~interior] <= ref[~interior] + 1e-4 * ref.max()), tag
+        tensors, spec_fit, bkg, trace = opt.fit_spec(spec, er, names[:-2], init_param_vals=p, tune_params=False,
+                                                     use_snip=use_snip)
+        assert np.abs(spec_fit - g[f"{tag}_spec_fit"]).max() <= 2e-4 * g[f"{tag}_spec_fit"].max()
+        assert np.abs(bkg - g[f"{tag}_bkg"]).max() <= 1e-5 * max(g[f"{tag}_bkg"].max(), 1e-30)
+        assert trace[-1] <= g[f"{tag}_trace"][-1] * (1 + 1e-5)
+        assert abs(float(tensors["Fe"]) - dict(zip(names, g[f"{tag}_logamps"]))["Fe"]) < 1e-4
+
+
+def test_fit_map_with_snip_background_and_shards():
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12()
+    er = (0, 2047)
+    y, names = synth(p, er, ELEMS10, 8 * 12, seed=9, flat=3.0)
+    vol = y.reshape(8, 12, -1)
+    pr = [p[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")]
+    bkg = mo.snip_bkg(y, er, *pr)
+    B, _ = mo.basis(p, er, ELEMS10)
+    ref = mo.fit_nnls(y, B, bkg)
+    maps, plan = opt.fit_map(torch.from_numpy(vol), er, ELEMS10, init_param_vals=p, use_snip=True, return_plan=True)
+    x = torch.stack([maps[n] for n in names], dim=-1).reshape(-1, len(names)).cpu().numpy()
+    check_against(x, ref, 1e-4)
+    assert maps["Fe"].shape == (8, 12) and maps["Fe"].is_cuda
+    # row shards give bit-identical maps (pixels are independent): the multi-GPU partitioning
+    parts = [opt.fit_map(torch.from_numpy(vol[r0:r1]), er, ELEMS10, plan=plan) for r0, r1 in ((0, 3), (3, 8))]
+    for n in names:
+        assert torch.equal(torch.cat([q[n] for q in parts], dim=0), maps[n]), n
+    # restricting the objective to peak windows (`indices`) == least squares on the masked channels
+    from mapstorch_b200 import util
+
+    rr = util.get_peak_ranges(names, 12.0, p["COMPTON_ANGLE"], p["ENERGY_OFFSET"], p["ENERGY_SLOPE"], p["ENERGY_QUADRATIC"], er)
+    idx = util.peak_range_indices(rr, 2048)
+    m2 = opt.fit_map(torch.from_numpy(vol), er, ELEMS10, init_param_vals=p, use_snip=True, indices=idx)
+    ref2 = mo.fit_nnls(y[:, idx], B[idx], bkg[:, idx])
+    x2 = torch.stack([m2[n] for n in names], dim=-1).reshape(-1, len(names)).cpu().numpy()
+    check_against(x2, ref2, 1e-4)
+
+
+def test_gated_off_component_and_escape_factor():
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12()
+    er = (0, 2047)
+    elems = ELEMS10 + ["Pb_L"]  # every Pb L edge lies above 12 keV: column is identically zero
+    y, _ = synth(p, er, ELEMS10, 40, seed=2)
+    maps = opt.fit_map(torch.from_numpy(y), er, elems, init_param_vals=p, use_snip=False, escape_factor=0.05)
+    assert float(maps["Pb_L"].abs().max()) == 0.0
+    B, names = mo.basis(p, er, ELEMS10, escape_factor=0.05)
+    ref = mo.fit_nnls(y, B)
+    x = torch.stack([maps[n] for n in names], dim=-1).cpu().numpy()
+    check_against(x, ref, 1e-4)
+
+
+def test_full_size_linearity_property():
+    """BASELINE config 2 size (256x256x2048, 10 elements): fit(Y1 + Y2) == fit(Y1) + fit(Y2) for the
+    unconstrained solve, and duplicated pixels give identical answers wherever they sit."""
+    from mapstorch_b200 import opt
+
+    p = params12()
+    er = (0, 2047)
+    plan = opt.MapFitPlan(er, ELEMS10, p, use_snip=False)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    lam = plan.basis.T @ (10 ** (1.0 + 1.5 * torch.rand(len(plan.names), 256, device="cuda", generator=gen)))
+    y1 = torch.poisson(lam.T.repeat(256, 1), generator=gen)
+    y2 = torch.poisson(lam.T.repeat(256, 1).flip(0), generator=gen)
+    assert y1.shape == (65536, 2048) and float((y1 + y2).max()) < 2048
+    a, b, c = (plan.fit(t, nonneg=False) for t in (y1, y2, y1 + y2))
+    scale = c.abs().max(dim=0).values
+    assert float(((a + b - c).abs() / scale).max()) <= 2e-5
+    y1[40000] = y1[3]
+    d = plan.fit(y1.half(), nonneg=False)
+    assert torch.equal(d[:, 40000], d[:, 3])
+    assert float(((d - a)[:, :40000].abs() / scale[:40000]).max()) <= 2e-5

@@ -1,0 +1,131 @@
+"""Host-side table compiler (mapstorch_b200.tables / util / opt helpers) against the reference
+goldens: index tables are bit-exact, compiled term tables reproduce the reference columns."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_params
+from mapstorch_b200 import default as d, opt, tables, util
+from oracle import maps_oracle as mo
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_energy_axis_bit_exact(model_golden, tag):
+    p = golden_params(model_golden, tag)
+    ev = tables.energy_axis(p, tuple(model_golden[f"{tag}_er"]))
+    assert ev.dtype == torch.float32 and np.array_equal(ev.numpy(), model_golden[f"{tag}_ev"])
+    tens = {k: torch.tensor(float(v)) for k, v in p.items()}
+    assert np.array_equal(tables.energy_axis(tens, tuple(model_golden[f"{tag}_er"])).numpy(), model_golden[f"{tag}_ev"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_compiled_terms_reproduce_reference_columns(model_golden, tag):
+    g = model_golden
+    p = golden_params(g, tag)
+    elems = [str(e) for e in g["model_elems"]]
+    ev = g[f"{tag}_ev"]
+    comps = elems + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+    for amp in (0.0, 2.3):
+        pp = dict(p, **{c: amp for c in comps})
+        for us in (0, 1):
+            for ut in (0, 1):
+                key = f"{tag}_amp{amp}_s{us}_t{ut}"
+                if key + "_elems" not in g:
+                    continue
+                cols = tables.compile_terms(pp, comps, d.default_energy_consts, d.default_elem_info, bool(us), bool(ut),
+                                            log_amps=pp)
+                terms, starts = tables.pack_columns(cols)
+                out = mo.eval_terms(terms, starts, ev)
+                refs = list(g[key + "_elems"]) + [g[key + "_compton"], g[f"{tag}_amp{amp}_elastic"]]
+                for name, o, r in zip(comps, out, refs):
+                    scale = np.abs(r).max()
+                    if scale == 0:
+                        assert not o.any(), (key, name)
+                    else:
+                        assert np.abs(o - r).max() <= 1e-6 * scale, (key, name)
+
+
+def test_term_counts_for_benchmark_set(model_golden):
+    # the 30-element benchmark set: 136 lines with a non-zero ratio, of which the 12 keV gate opens 115
+    p = golden_params(model_golden, "c")
+    elems = [str(e) for e in model_golden["elems30"]]
+    names = tables.fitted_components(elems, d.default_energy_consts)
+    assert names[-2:] == ["COHERENT_SCT_AMPLITUDE", "COMPTON_AMPLITUDE"] and len(names) == 32
+    cols = tables.compile_terms(p, names, d.default_energy_consts, d.default_elem_info)
+    n_lines = sum(1 for n in names[:-2] for s in d.default_energy_consts[n] if s.ratio != 0 and s.energy > 0)
+    assert n_lines == 136
+    n_open = sum(len(c) for c in cols[:-2])  # lines whose absorption edge lies below 12 keV
+    assert n_open == 115
+    terms, starts = tables.pack_columns(cols)
+    assert terms.dtype.itemsize == 32 and starts[-1] == n_open + 2
+
+
+@pytest.mark.parametrize("tag", ["c2048", "c1401", "c4096"])
+def test_snip_tables_bit_exact(snip_golden, tag):
+    g = snip_golden
+    er, pr, lohi = tuple(g[f"{tag}_er"]), g[f"{tag}_params"], g[f"{tag}_lohi"]
+    n_ch = g[f"{tag}_spec"].shape[-1]
+    for args in ([torch.tensor(float(v)) for v in pr], [float(np.float32(v)) for v in pr]):
+        tab = tables.snip_tables(n_ch, er[0], *args)
+        assert tab.dtype == np.uint32 and tab.shape == (lohi.shape[0], n_ch)
+        assert np.array_equal(tab & 0xFFFF, lohi[:, 0]) and np.array_equal(tab >> 16, lohi[:, 1])
+    # last pass is the asymmetric lo = i-1 / hi = i window the truncation produces
+    last = tab[-1]
+    i = np.arange(n_ch)
+    assert np.all((i - (last & 0xFFFF)) <= 1) and np.all((last >> 16) == i)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_escape_bins_and_peak_ranges(host_golden, model_golden, tag):
+    p = golden_params(model_golden, tag)
+    er = tuple(int(v) for v in model_golden[f"{tag}_er"])
+    ev = tables.energy_axis(p, er)
+    want = host_golden[f"escape_bins_{tag}"]
+    for det, b in zip(("Si", "Ge"), want):
+        assert tables.escape_bins(ev, det) == (int(b) if b < ev.numel() else 0)
+    rr = util.get_peak_ranges(list(d.default_fitting_elems), p["COHERENT_SCT_ENERGY"], p["COMPTON_ANGLE"],
+                              p["ENERGY_OFFSET"], p["ENERGY_SLOPE"], p["ENERGY_QUADRATIC"], er)
+    keys = [str(k) for k in host_golden[f"ranges_{tag}_keys"]]
+    assert list(rr.keys()) == keys
+    assert np.array_equal(np.array(list(rr.values())), host_golden[f"ranges_{tag}_vals"])
+    idx = util.peak_range_indices(rr, er[1] - er[0] + 1)
+    assert idx.size and idx.max() <= er[1] - er[0]
+
+
+def test_init_elem_amps_matches_reference(host_golden):
+    g = host_golden
+    dp = d.default_param_vals
+    names = [str(n) for n in g["init_names"]]
+    got = np.array([float(opt.init_elem_amps(e, g["init_spec"], 12.0, dp["ENERGY_OFFSET"], dp["ENERGY_SLOPE"],
+                                             compton_angle=dp["COMPTON_ANGLE"])) for e in names])
+    assert np.array_equal(got, g["init_amps_spec"])
+    vol = np.stack([np.asarray(opt.init_elem_amps(e, g["init_vol"], 12.0, dp["ENERGY_OFFSET"], dp["ENERGY_SLOPE"],
+                                                  compton_angle=dp["COMPTON_ANGLE"])) * np.ones((3, 4)) for e in names])
+    assert np.array_equal(vol, g["init_amps_vol"])
+    assert opt.init_elem_amps("NotAnElement", g["init_spec"], 12.0, 0.0, 0.012) == 0.0
+
+
+def test_create_tensors_mirrors_reference_layout():
+    tensors, groups = opt.create_tensors(["Fe", "Cu"], fixed_param_vals={"ENERGY_SLOPE": 0.0123})
+    assert set(tensors) == set(d.default_param_vals) | {"Fe", "Cu"}
+    assert not tensors["ENERGY_SLOPE"].requires_grad and tensors["ENERGY_OFFSET"].requires_grad
+    assert tensors["Fe"].requires_grad and float(tensors["Fe"]) == 0.0
+    assert len(groups) == 11 + 2 and groups[-1]["lr"] == 1e-2
+    t2, g2 = opt.create_tensors(["Fe"], tune_params=False)
+    assert [k for k, v in t2.items() if v.requires_grad] == ["Fe"] and len(g2) == 1
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+def test_operand_split_is_fp32_accurate(kind):
+    rng = np.random.default_rng(0)
+    w = rng.normal(size=(12, 512)) * np.exp(rng.uniform(-12, 3, size=(12, 512)))
+    w[3] = 0.0
+    scale, hi, lo = opt.split_operand(w, kind)
+    rebuilt = scale[:, None].astype(np.float64) * (hi.astype(np.float64) + opt.LO_SCALE * lo.astype(np.float64))
+    peak = np.abs(w).max(axis=1, keepdims=True)
+    peak[peak == 0] = 1
+    assert np.abs(rebuilt - w).max() / 1 <= 2.0 ** -21 * np.abs(w).max()
+    assert (np.abs(rebuilt - w) / peak).max() <= 2.0 ** -21
+    assert np.all(np.isfinite(hi.astype(np.float64))) and np.abs(hi.astype(np.float64)).max() <= 2.0 ** 14
+    if kind == "tf32":
+        assert not np.any(hi.view(np.uint32) & 0x1FFF) and not np.any(lo.view(np.uint32) & 0x1FFF)
