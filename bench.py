@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the per-pixel XRF map fit (BASELINE.json metric: pixels/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A step is one fit of
+the rank's resident row shard (plus, for N > 1, the all-gather of the element maps).  Rank 0
+prints ONE JSON line.  `--impl reference` times the CPU baseline (the oracle's composition of the
+reference functions) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# per-GPU workloads (weak scaling: every rank gets one of these; see DESIGN.md "Measurement")
+WORKLOADS = {
+    # BASELINE config 5 = 2048x2048x4096 fp16 on 8 GPUs -> each GPU owns 256 rows
+    "c5": dict(rows=256, width=2048, n_ch=4096, dtype="f16", elems="ELEMS30", snip=False, flat=0.0,
+               desc="BASELINE config 5 row shard: 256x2048x4096 fp16 per GPU (8 GPUs = the 2048x2048x4096 map), "
+                    "30 elements + 2 scatter peaks"),
+    # BASELINE config 2 (the whole map on every GPU)
+    "c2": dict(rows=256, width=256, n_ch=2048, dtype="f32", elems="ELEMS10", snip=False, flat=0.0,
+               desc="BASELINE config 2: 256x256x2048 fp32, 10 elements + 2 scatter peaks"),
+    # BASELINE config 3 = 1024x1024x4096 fp32 + SNIP on 8 GPUs -> each GPU owns 128 rows
+    "c3": dict(rows=128, width=1024, n_ch=4096, dtype="f32", elems="ELEMS30", snip=True, flat=3.0,
+               desc="BASELINE config 3 row shard: 128x1024x4096 fp32 per GPU (8 GPUs = the 1024x1024x4096 map), "
+                    "30 elements + 2 scatter peaks, SNIP background"),
+}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc, self.path = None, None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in Path(self.path).read_text().strip().splitlines() if r.strip()]
+            sm = [float(r[0]) for r in rows]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.strip().lower() == "active"})
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                   "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def build_workload(name, rank, world, device):
+    from mapstorch_b200 import opt, synth
+
+    w = WORKLOADS[name]
+    elems = getattr(synth, w["elems"])
+    params = synth.benchmark_params(w["n_ch"])
+    er = (0, w["n_ch"] - 1)
+    plan = opt.MapFitPlan(er, elems, params, use_snip=w["snip"])
+    truth = synth.truth_maps(len(plan.names), w["rows"], w["width"], seed=1234, row0=rank * w["rows"],
+                             total_rows=world * w["rows"], device=device)
+    dtype = torch.float16 if w["dtype"] == "f16" else torch.float32
+    vol = synth.poisson_volume(plan.basis, truth, dtype=dtype, flat=w["flat"], seed=99 + rank)
+    return w, elems, params, er, plan, truth, vol
+
+
+def cpu_baseline(w, params, er, elems, budget_s=12.0, threads=None):
+    """Oracle composition of the reference functions on the host cores, on a bounded sample."""
+    from oracle import maps_oracle as mo
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    B, names = mo.basis(params, er, elems)
+    snip_args = [params[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET",
+                                     "FWHM_FANOPRIME")] if w["snip"] else None
+
+    def sample(n):
+        amps = 10.0 ** rng.uniform(1.5, 3.0, size=(n, B.shape[1]))
+        return rng.poisson(amps @ B.astype(np.float64).T + w["flat"]).astype(np.float32)
+
+    n = 512
+    y = sample(n)
+    t0 = time.perf_counter()
+    mo.fit_map_composed(y, B, snip_args, er)
+    dt = time.perf_counter() - t0
+    n_big = int(min(max(n, n * budget_s / max(dt, 1e-6)), 1 << 18))
+    y = sample(n_big)
+    t0 = time.perf_counter()
+    mo.fit_map_composed(y, B, snip_args, er)
+    dt = time.perf_counter() - t0
+    # the reference's own per-spectrum fit: Adam, 500 iterations (restated with analytic gradients)
+    t1 = time.perf_counter()
+    for i in range(4):
+        mo.fit_spec_adam(y[i] if not w["snip"] else y[i], B, None, np.full(B.shape[1], 2.0, np.float32), n_iter=500)
+    adam = 4 / (time.perf_counter() - t1)
+    return {"value": n_big / dt, "unit": "px/s", "cores": cores, "kind": "port",
+            "sample": f"{n_big} synthetic pixels of the same workload: oracle composition of the reference functions "
+                      f"({'snip_bkg + ' if w['snip'] else ''}fp32 BLAS contraction with pinv(B) + scipy NNLS on negative "
+                      f"pixels), {dt:.1f} s",
+            "reference_adam_500it_px_s": adam}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from mapstorch_b200 import synth
+
+    w = WORKLOADS[args.workload]
+    elems = getattr(synth, w["elems"])
+    params = synth.benchmark_params(w["n_ch"])
+    er = (0, w["n_ch"] - 1)
+    vals = []
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(w, params, er, elems, budget_s=per_step_budget)
+        if i >= args.warmup:
+            vals.append(cb)
+    value = float(np.mean([c["value"] for c in vals]))
+    cb = dict(vals[-1], value=value)
+    line = {"impl": "reference", "metric": "pixels/sec", "value": value, "unit": "px/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "name": args.workload},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from mapstorch_b200 import _native, opt
+    from mapstorch_b200.dist import gather_maps
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    w, elems, params, er, plan, truth, vol = build_workload(args.workload, rank, world, device)
+    flat = vol.reshape(-1, vol.shape[-1])
+    n_px = flat.shape[0]
+    n_comp = len(plan.names)
+    out = torch.zeros((n_comp, n_px), dtype=torch.float32, device=device)
+    total_rows = world * w["rows"]
+
+    def step(gather=True):
+        plan.fit(flat, out=out)
+        if world > 1 and gather:
+            return gather_maps(out, total_rows, w["width"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step()
+    # accuracy of what is being timed: amplitudes against the ground truth (Poisson-limited) and
+    # against a float64 solve of a pixel sample
+    got = step(gather=False)
+    sample = torch.arange(0, n_px, max(1, n_px // 512), device=device)[:512]
+    y64 = flat[sample].double()
+    if w["snip"]:
+        from mapstorch_b200 import bkg as _bkg
+        pr = [torch.tensor(float(params[k])) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH",
+                                                       "FWHM_OFFSET", "FWHM_FANOPRIME")]
+        y64 = y64 - _bkg.snip_bkg(flat[sample].float(), er, *pr, device="cuda").double()
+    ref = torch.linalg.lstsq(plan.basis.double().T, y64.T).solution.T  # [n, E]
+    mine = got[:, sample].T.double()
+    interior = (ref > 1e-3 * ref.max(dim=1, keepdim=True).values) & (mine > 0)
+    check = float(((mine - ref).abs() / ref.abs())[interior].max())
+
+    # ---- device-resident timing (value) ---------------------------------------------------------
+    plan.timers = []
+    launches0 = _native.launch_count
+    sampler = ClockSampler(device)
+    ms_total = timed(step, args.steps)
+    clocks = sampler.stop()
+    launches = _native.launch_count - launches0
+    timers, plan.timers = plan.timers, None
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in timers]))
+    kernel_px = float(np.mean([n for _, _, n in timers]))
+    ms_fit_only = timed(lambda: step(gather=False), args.steps) if world > 1 else ms_total
+    ms_per_step = ms_total / args.steps
+    value = world * n_px / (ms_per_step * 1e-3)
+
+    es = flat.element_size()
+    in_row_bytes = w["n_ch"] * es * (1 if not w["snip"] else 1)
+    bytes_per_px = w["n_ch"] * (es if not w["snip"] else 4 * 2) + n_comp * 4  # what the contraction kernel streams
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_px * kernel_px / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "fit_contract_kernel (tcgen05 + TMA)", "bytes_per_px": bytes_per_px,
+                "px_per_launch": kernel_px, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "job_frac": (w["n_ch"] * es + n_comp * 4) * n_px / (ms_fit_only / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the public API, host buffers ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        host.copy_(flat)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            maps = opt.fit_map(host.reshape(vol.shape), er, elems, init_param_vals=params, use_snip=w["snip"],
+                               device="cpu")
+            return maps
+
+        e2e_step()
+        ms = timed(e2e_step, args.e2e_steps) / args.e2e_steps
+        e2e = {"value": world * n_px / (ms * 1e-3), "unit": "px/s", "h2d_bytes_per_step": world * flat.numel() * es,
+               "d2h_bytes_per_step": world * n_comp * n_px * 4, "ms_per_step": ms, "steps": args.e2e_steps,
+               "api": "mapstorch_b200.opt.fit_map(pinned host volume) -> host maps; plan build, chunked H2D "
+                      "overlapped with the fit, D2H of the maps all inside the timed region"}
+        del host
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(w, params, er, elems)
+
+    if rank == 0:
+        line = {"metric": "pixels/sec", "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05)" if w["dtype"] == "f16" else "tf32 x tf32 -> f32 (tcgen05)",
+                "data": "synthetic",
+                "config": {"workload": w["desc"], "name": args.workload, "pixels_per_gpu": n_px, "channels": w["n_ch"],
+                           "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
+                           "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
+                           "step": "fit of the resident shard (contraction + non-negative fix-up)" +
+                                   (" + all-gather of the element maps" if world > 1 else "")},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
+                "fit_only_px_s": world * n_px / (ms_fit_only / args.steps * 1e-3),
+                "max_rel_err_vs_float64_lstsq": check}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,8 +83,16 @@ def check(status):
         raise NativeError(status, msg.decode("utf-8", "replace") if msg else "unknown error")
 
 
+# kernels launched per successful call of each entry point (bench.py reports the total)
+KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
+                    "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_refine": 1}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
     check(getattr(load(), name)(*args))
+    launch_count += KERNELS_PER_CALL.get(name, 0)
 
 
 def stream_ptr(stream=None):

@@ -135,6 +135,8 @@ class MapFitPlan:
         self.hinv_dev = torch.from_numpy(hinv).cuda()
         self._packs = {}
         self._snip = None
+        self._host_out = {}
+        self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
         if self.use_snip:
             p = self.params
             self._snip = _bkg.snip_tables_device(
@@ -167,6 +169,17 @@ class MapFitPlan:
     # -- the fit -----------------------------------------------------------------------------------
     def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream):
         """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
+        if self.timers is not None:
+            s = stream if stream is not None else torch.cuda.current_stream()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(s)
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream)
+            t1.record(s)
+            self.timers.append((t0, t1, spec2d.shape[0]))
+        else:
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream)
+
+    def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream):
         n_px, n_ch_total, ld = spec2d.shape[0], spec2d.shape[1], spec2d.stride(0)
         es = spec2d.element_size()
         tma_ok = (ld * es) % 16 == 0 and spec2d.data_ptr() % 16 == 0
@@ -224,10 +237,52 @@ class MapFitPlan:
         return out
 
 
+def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
+    """Stream a HOST volume [P, C] through the device in row slabs: slab k+1 is copied
+    host->device on a second stream while slab k is being fitted (pinned host memory makes the
+    copies asynchronous).  Returns x [E, P] on the device."""
+    n_px, n_ch = host2d.shape
+    out = torch.zeros((len(self.names), n_px), dtype=torch.float32, device="cuda")
+    chunk = max(1, min(int(chunk_px), n_px))
+    compute = torch.cuda.current_stream()
+    copier = torch.cuda.Stream()
+    bufs = [torch.empty((chunk, n_ch), dtype=host2d.dtype, device="cuda") for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for i, p0 in enumerate(range(0, n_px, chunk)):
+        b, n = i & 1, min(chunk, n_px - p0)
+        with torch.cuda.stream(copier):
+            if i >= 2:
+                copier.wait_event(consumed[b])
+            bufs[b][:n].copy_(host2d[p0: p0 + n], non_blocking=True)
+            copied[b].record(copier)
+        compute.wait_event(copied[b])
+        self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine)
+        consumed[b].record(compute)
+    for buf in bufs:
+        buf.record_stream(compute)
+    return out
+
+
+def _to_host(self, x):
+    """Device -> pinned host copy of a result (the pinned buffer is cached per shape)."""
+    key = (tuple(x.shape), x.dtype)
+    if key not in self._host_out:
+        self._host_out[key] = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    host = self._host_out[key]
+    host.copy_(x, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host
+
+
+MapFitPlan.fit_host = _fit_host
+MapFitPlan.to_host = _to_host
+
+
 def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_param_vals=default_param_vals,
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
-            device="cuda", engine="tensor", plan=None, return_plan=False):
+            device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384):
     """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
 
     Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
@@ -243,9 +298,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         spec_vol = torch.from_numpy(arr)
     if spec_vol.dtype not in (torch.float32, torch.float16):
         spec_vol = spec_vol.to(torch.float32)
-    vol = spec_vol.to("cuda", non_blocking=True)
-    lead = vol.shape[:-1]
-    flat = vol.reshape(-1, vol.shape[-1])
+    lead = spec_vol.shape[:-1]
+    flat = spec_vol.reshape(-1, spec_vol.shape[-1])
     if flat.stride(1) != 1:
         flat = flat.contiguous()
     if plan is None:
@@ -253,10 +307,14 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         params.update(fixed_param_vals)
         plan = MapFitPlan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
                           detector_type, escape_factor)
-    x = plan.fit(flat, nonneg=nonneg, engine=engine)
+    if flat.device.type == "cuda":
+        x = plan.fit(flat, nonneg=nonneg, engine=engine)
+    else:
+        x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px)
     if as_log10:
         x = torch.log10(x)
-    x = x if torch.device(device).type == "cuda" else x.to(device)
+    if torch.device(device).type != "cuda":
+        x = plan.to_host(x)
     maps = {name: x[i].reshape(lead) for i, name in enumerate(plan.names)}
     return (maps, plan) if return_plan else maps
 
