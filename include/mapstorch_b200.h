@@ -95,18 +95,22 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
 
 /* K3 -- the per-pixel amplitude solve: replaces the Adam loop of fit_spec (opt.py:249-317)
  * for fixed global parameters, where the model is linear in the amplitudes.
- * x[e][p] = colscale[e] * sum_k spec[p][k] * (w_hi[e][k] + lo_scale * w_lo[e][k]), i.e. the
- * spectra contracted against the pseudo-inverse of the element basis on the tensor cores.
+ *   x[e][p] = colscale[e] * sum_d plane_ratio^d * ( sum_k spec[p][k] * wpack[d*e_pad + e][k] )
+ * i.e. the spectra contracted on the tensor cores against the pseudo-inverse of the element
+ * basis, which is stored as n_planes operand-precision "digit" planes stacked along N.  With
+ * small-integer digits (10 bits per plane) and integer counts every partial sum is an integer
+ * below 2^24, so the fp32 tensor-core accumulation is exact.
  * spec_dev : [n_px][ld_spec] of `dtype` (row pitch must be a multiple of 16 bytes, base 16-B aligned)
- * wpack_dev: [2*e_pad][ld_w] in the SAME dtype as spec (fp32 words hold tf32-exact values):
- *            rows [0,e_pad) = high parts, rows [e_pad,2*e_pad) = low parts pre-multiplied by 1/lo_scale;
- *            columns outside the fitted channel range hold zeros.  e_pad multiple of 8, <= 128.
+ * wpack_dev: [n_planes*e_pad][ld_w] in the SAME dtype as spec (fp32 words must hold tf32-exact
+ *            values); columns outside the fitted channel range hold zeros.  e_pad multiple of 8,
+ *            n_planes*e_pad a multiple of 16 and <= 256.
  * k_begin,k_end: channel window (elements) the kernel streams; rounded outwards to 128-byte blocks.
  * x_dev    : fp32, element-major: x_dev[e*ld_x + p] for e < n_comp, p < n_px. */
 int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                     int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
-                    int64_t ld_w, int32_t e_pad, int32_t n_comp, const float *colscale_dev,
-                    float lo_scale, float *x_dev, int64_t ld_x, void *stream);
+                    int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
+                    const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
+                    void *stream);
 
 /* Same contract on CUDA cores (no tensor cores, fp32 weights [n_comp][ld_w]); exists for
  * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */

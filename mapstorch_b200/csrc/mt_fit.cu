@@ -9,14 +9,18 @@
 //                           (evict-first) and the matching [N x 128 B] slab of W (evict-last,
 //                           L2 resident) into a ring of 128B-swizzled shared-memory stages
 //   warp 1   MMA issuer   : tcgen05.mma cta_group::1, M=128 (x2 pixel sub-tiles sharing the W
-//                           slab), N = 2*e_pad, kind::f16 for fp16 volumes / kind::tf32 for fp32;
-//                           accumulators live in TMEM, double buffered across pixel tiles
-//   warps 2-5 epilogue    : tcgen05.ld the finished tile, recombine the hi/lo split of W
-//                           (fp32-accurate result from 11-bit operands), scale, store
-//                           element-major amplitudes x[e][p] (coalesced over pixels)
+//                           slab), N = n_planes*e_pad, kind::f16 for fp16 volumes / kind::tf32 for
+//                           fp32; accumulators live in TMEM, double buffered across pixel tiles
+//   warps 2-5 epilogue    : tcgen05.ld the finished tile, recombine the digit planes of W
+//                           (Horner, fp32), scale, store element-major amplitudes x[e][p]
+//                           (coalesced over pixels)
 //
-// W is stored as two operand-precision parts (hi, lo/lo_scale) stacked along N; spectra are raw
-// counts, which fp16/tf32 hold exactly below 2048, so no A-side split is needed for them.
+// W is stored as n_planes small-integer "digit" planes stacked along N (10 bits each, exact in
+// fp16/tf32).  Spectra are raw counts (exact below 2048), so every product and every partial sum
+// is an integer: as long as sum_k y_k*|digit_k| < 2^24 the fp32 accumulation in the tensor core
+// is EXACT, and the only rounding left is the fp32 Horner recombination (~1e-7 relative).  With
+// full-mantissa operands the tensor-core accumulator (which truncates) costs ~4e-6 of the pixel
+// maximum instead -- measured, see DESIGN.md.
 // Bound: HBM (C*sizeof(in) + E*4 bytes per pixel); tensor-pipe use stays well below peak.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,12 +46,12 @@ struct FitParams {
     int n_tiles;
     int kb_begin, kb_end;
     int bke;  // elements per k-block (64 for fp16, 32 for fp32)
-    int n_mma, e_pad, n_comp;
+    int n_mma, e_pad, n_comp, n_planes;
     int n_stages;
     uint32_t stage_bytes;
     uint32_t tmem_cols;
     uint32_t idesc;
-    float lo_scale;
+    float plane_ratio;
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -186,15 +190,22 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                 const uint32_t taddr =
                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
                 for (int c0 = 0; c0 < p.e_pad; c0 += 8) {
-                    float hi[8], lo[8];
-                    tmem_ld8(taddr + (uint32_t)c0, hi);
-                    tmem_ld8(taddr + (uint32_t)(p.e_pad + c0), lo);
+                    // planes are stacked along N; Horner from the least significant plane:
+                    // x = cs * (S0 + r * (S1 + r * S2))
+                    float acc[8], part[8];
+                    tmem_ld8(taddr + (uint32_t)((p.n_planes - 1) * p.e_pad + c0), acc);
                     tmem_ld_wait();
+                    for (int d = p.n_planes - 2; d >= 0; --d) {
+                        tmem_ld8(taddr + (uint32_t)(d * p.e_pad + c0), part);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], p.plane_ratio, part[j]);
+                    }
                     if (px < p.n_px) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int e = c0 + j;
-                            if (e < p.n_comp) p.x[(long long)e * p.ld_x + px] = cs[e] * fmaf(lo[j], p.lo_scale, hi[j]);
+                            if (e < p.n_comp) p.x[(long long)e * p.ld_x + px] = cs[e] * acc[j];
                         }
                     }
                 }
@@ -307,7 +318,13 @@ template <int KIND, int M_TILES>
 int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_w, const FitParams &p, size_t smem, int grid,
                cudaStream_t stream) {
     auto kern = fit_contract_kernel<KIND, M_TILES>;
-    MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set[16] = {0};  // per device: opt in to the large dynamic smem carve-out once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 16 || smem_set[dev] < (int)smem) {
+        MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        if (dev < 16) smem_set[dev] = kSmemLimit;
+    }
     kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_w, p);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
@@ -317,8 +334,9 @@ int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_w, const FitPar
 
 extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                                int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
-                               int64_t ld_w, int32_t e_pad, int32_t n_comp, const float *colscale_dev,
-                               float lo_scale, float *x_dev, int64_t ld_x, void *stream_) {
+                               int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
+                               const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
+                               void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
     MT_REQUIRE(dtype == MT_DTYPE_F32 || dtype == MT_DTYPE_F16, "mt_fit_contract: dtype %d", dtype);
@@ -329,8 +347,11 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                (long long)ld_w);
     MT_REQUIRE(0 <= k_begin && k_begin < k_end && k_end <= n_ch_total, "mt_fit_contract: channel window [%d,%d)",
                k_begin, k_end);
-    MT_REQUIRE(e_pad >= 8 && e_pad <= 128 && e_pad % 8 == 0 && n_comp >= 1 && n_comp <= e_pad,
-               "mt_fit_contract: e_pad=%d n_comp=%d", e_pad, n_comp);
+    MT_REQUIRE(n_planes >= 1 && n_planes <= 4, "mt_fit_contract: n_planes=%d", n_planes);
+    MT_REQUIRE(e_pad >= 8 && e_pad % 8 == 0 && n_comp >= 1 && n_comp <= e_pad && (n_planes * e_pad) % 16 == 0 &&
+                   n_planes * e_pad <= 256,
+               "mt_fit_contract: e_pad=%d n_comp=%d n_planes=%d (need n_planes*e_pad a multiple of 16, <= 256)",
+               e_pad, n_comp, n_planes);
     MT_REQUIRE(ld_x >= n_px, "mt_fit_contract: ld_x=%lld < n_px", (long long)ld_x);
     if ((ld_spec * es) % 16 || (ld_w * es) % 16 || ((uintptr_t)spec_dev & 15) || ((uintptr_t)wpack_dev & 15))
         return mt::fail(MT_ERR_UNSUPPORTED,
@@ -348,10 +369,11 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.bke = kRowBytes / es;
     p.kb_begin = k_begin / p.bke;
     p.kb_end = (k_end + p.bke - 1) / p.bke;
-    p.n_mma = 2 * e_pad;
+    p.n_mma = n_planes * e_pad;
     p.e_pad = e_pad;
     p.n_comp = n_comp;
-    p.lo_scale = lo_scale;
+    p.n_planes = n_planes;
+    p.plane_ratio = plane_ratio;
     const int m_tiles = (p.n_mma <= 128) ? 2 : 1;
     const int block_rows = kTileRows * m_tiles;
     p.n_tiles = (int)((n_px + block_rows - 1) / block_rows);

@@ -187,7 +187,13 @@ int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, co
                 cudaStream_t stream) {
     auto kern = nnls_fixup_kernel<EMAX>;
     const size_t smem = sizeof(double) * 2 * (size_t)E * E;
-    MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 16 || smem_set[dev] < (int)smem) {
+        MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 16) smem_set[dev] = (int)smem;
+    }
     const unsigned grid = (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
     kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, n_px, E, g, h, n_fixed);
     MT_CUDA_TRY(cudaGetLastError());

@@ -24,7 +24,9 @@ from mapstorch_b200.default import (
     default_elem_info,
 )
 
-LO_SCALE = 2.0 ** -11  # the low operand part is stored pre-multiplied by 2**11
+DIGIT_BITS = 10    # bits per operand plane of the pseudo-inverse (|digit| <= 512: exact in fp16 / tf32)
+N_PLANES = 3       # 30 bits in total
+PLANE_RATIO = 2.0 ** -DIGIT_BITS
 SNIP_CHUNK_PX = 32768
 
 
@@ -72,26 +74,23 @@ def create_tensors(elems_to_fit=default_fitting_elems, fitting_params=default_fi
 
 
 # ---- operand packing ---------------------------------------------------------------------------
-def _round_tf32(a):
-    """Round fp32 values to the nearest tf32 (10 explicit mantissa bits), returned as fp32."""
-    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
-    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+def digit_planes(w64, n_planes=N_PLANES, bits=DIGIT_BITS):
+    """W (float64 [E, C]) -> (colscale[E] fp32, digits int [n_planes, E, C]) with
+    W ~= colscale * sum_d 2**(-bits*d) * digits[d]  and  |digits| <= 2**(bits-1).
 
-
-def split_operand(w64, kind):
-    """W (float64 [E, C]) -> (colscale[E], hi, lo) with W ~= colscale * (hi + LO_SCALE * lo); hi and
-    lo are exactly representable in the tensor-core operand type (`kind`: 'f16' or 'tf32')."""
+    Balanced base-2**bits digits of W scaled row-wise by a power of two: each plane is exactly
+    representable in fp16 and tf32, products with integer counts are integers, and the truncation
+    error is <= 2**(-bits*n_planes) of the row maximum."""
     peak = np.max(np.abs(w64), axis=1)
     peak = np.where(peak > 0, peak, 1.0)
-    scale = np.exp2(np.ceil(np.log2(peak)) - 14.0)  # rows scaled into [2**13, 2**14]: exact, fp16-safe
-    scaled = w64 / scale[:, None]
-    if kind == "f16":
-        hi = scaled.astype(np.float16)
-        lo = ((scaled - hi.astype(np.float64)) / LO_SCALE).astype(np.float16)
-    else:
-        hi = _round_tf32(scaled.astype(np.float32))
-        lo = _round_tf32(((scaled - hi.astype(np.float64)) / LO_SCALE).astype(np.float32))
-    return scale.astype(np.float32), hi, lo
+    scale = np.exp2(np.ceil(np.log2(peak)) - (bits - 1))
+    rest = w64 / scale[:, None]
+    planes = []
+    for _ in range(n_planes):
+        digit = np.rint(rest)
+        planes.append(digit)
+        rest = (rest - digit) * (2.0 ** bits)
+    return scale.astype(np.float32), np.stack(planes)
 
 
 class MapFitPlan:
@@ -128,9 +127,10 @@ class MapFitPlan:
         self.gram, self.hinv = gram, hinv
         self.pinv = hinv @ bl  # [E_live, C]: x = pinv @ (y - bkg)
         self.n_live = len(self.live)
-        self.e_pad = max(8, -(-self.n_live // 8) * 8)
-        if self.e_pad > 128:
-            raise _native.NativeError(-3, f"{self.n_live} fitted components exceed the 128 the contraction kernel holds")
+        self.e_pad = max(16, -(-self.n_live // 16) * 16)  # N = N_PLANES * e_pad must be a multiple of 16
+        if N_PLANES * self.e_pad > 256:
+            raise _native.NativeError(-3, f"{self.n_live} fitted components exceed the {256 // N_PLANES} one "
+                                          "tensor-core tile holds (split the element list)")
         self.gram_dev = torch.from_numpy(gram).cuda()
         self.hinv_dev = torch.from_numpy(hinv).cuda()
         self._packs = {}
@@ -145,16 +145,17 @@ class MapFitPlan:
 
     # -- operand packs, cached per (dtype, layout) ------------------------------------------------
     def _pack(self, kind, n_cols, col0, repeat):
-        """wpack [2*e_pad, n_cols]: pinv placed at columns [col0, col0+n_ch) (`repeat` copies back to back)."""
+        """wpack [N_PLANES*e_pad, n_cols]: digit planes of pinv at columns [col0, col0+n_ch)
+        (`repeat` copies back to back), in the operand dtype of the volume."""
         key = (kind, n_cols, col0, repeat)
         if key not in self._packs:
-            scale, hi, lo = split_operand(self.pinv, kind)
+            scale, planes = digit_planes(self.pinv)
             dt = np.float16 if kind == "f16" else np.float32
-            pack = np.zeros((2 * self.e_pad, n_cols), dtype=dt)
+            pack = np.zeros((N_PLANES * self.e_pad, n_cols), dtype=dt)
             for r in range(repeat):
                 c = col0 + r * self.n_ch
-                pack[: self.n_live, c: c + self.n_ch] = hi
-                pack[self.e_pad: self.e_pad + self.n_live, c: c + self.n_ch] = lo
+                for d in range(N_PLANES):
+                    pack[d * self.e_pad: d * self.e_pad + self.n_live, c: c + self.n_ch] = planes[d]
             self._packs[key] = (torch.from_numpy(pack).cuda(), torch.from_numpy(scale).cuda())
         return self._packs[key]
 
@@ -190,7 +191,7 @@ class MapFitPlan:
             pack, scale = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat)
             _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
                          n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
-                         self.n_live, scale.data_ptr(), float(LO_SCALE), x.data_ptr(), x.stride(0),
+                         self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), x.data_ptr(), x.stride(0),
                          _native.stream_ptr(stream))
         elif engine == "simt":
             if repeat != 1:
@@ -264,6 +265,20 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
     return out
 
 
+def _make_graph(self, spec2d, out, nonneg=True, engine="tensor"):
+    """Capture one fit of a resident volume into a CUDA graph (the launch-bound inner loop of a
+    repeated fit: two kernel launches per step replayed without host work).  Returns the
+    torch.cuda.CUDAGraph; call .replay()."""
+    saved, self.timers = self.timers, None
+    self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)  # warm caches (operand packs, attributes)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)
+    self.timers = saved
+    return graph
+
+
 def _to_host(self, x):
     """Device -> pinned host copy of a result (the pinned buffer is cached per shape)."""
     key = (tuple(x.shape), x.dtype)
@@ -276,6 +291,7 @@ def _to_host(self, x):
 
 
 MapFitPlan.fit_host = _fit_host
+MapFitPlan.make_graph = _make_graph
 MapFitPlan.to_host = _to_host
 
 

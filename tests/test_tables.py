@@ -115,17 +115,15 @@ def test_create_tensors_mirrors_reference_layout():
     assert [k for k, v in t2.items() if v.requires_grad] == ["Fe"] and len(g2) == 1
 
 
-@pytest.mark.parametrize("kind", ["f16", "tf32"])
-def test_operand_split_is_fp32_accurate(kind):
+def test_digit_planes_hold_30_bits_in_fp16_exact_integers():
     rng = np.random.default_rng(0)
     w = rng.normal(size=(12, 512)) * np.exp(rng.uniform(-12, 3, size=(12, 512)))
     w[3] = 0.0
-    scale, hi, lo = opt.split_operand(w, kind)
-    rebuilt = scale[:, None].astype(np.float64) * (hi.astype(np.float64) + opt.LO_SCALE * lo.astype(np.float64))
+    scale, planes = opt.digit_planes(w)
+    assert planes.shape == (3, 12, 512) and np.abs(planes).max() <= 512
+    assert np.array_equal(planes, np.rint(planes)) and np.array_equal(planes.astype(np.float16).astype(np.float64), planes)
+    rebuilt = scale[:, None].astype(np.float64) * sum(opt.PLANE_RATIO ** d * planes[d] for d in range(3))
     peak = np.abs(w).max(axis=1, keepdims=True)
     peak[peak == 0] = 1
-    assert np.abs(rebuilt - w).max() / 1 <= 2.0 ** -21 * np.abs(w).max()
-    assert (np.abs(rebuilt - w) / peak).max() <= 2.0 ** -21
-    assert np.all(np.isfinite(hi.astype(np.float64))) and np.abs(hi.astype(np.float64)).max() <= 2.0 ** 14
-    if kind == "tf32":
-        assert not np.any(hi.view(np.uint32) & 0x1FFF) and not np.any(lo.view(np.uint32) & 0x1FFF)
+    assert (np.abs(rebuilt - w) / peak).max() <= 2.0 ** -29
+    assert np.all(np.log2(scale) == np.rint(np.log2(scale)))  # power-of-two row scales: exact
