@@ -222,7 +222,8 @@ class MapFitPlan:
             hilo = engine == "tensor"
             width = 2 * self.n_ch if hilo else self.n_ch
             chunk = min(SNIP_CHUNK_PX, n_px)
-            scratch = torch.empty((chunk, width), dtype=torch.float32, device="cuda")
+            pitch = -(-width // 4) * 4  # 16-byte row pitch so that TMA can address the scratch rows
+            scratch = torch.empty((chunk, pitch), dtype=torch.float32, device="cuda")[:, :width]
             mode = _native.MT_SNIP_RESIDUAL_HILO if hilo else _native.MT_SNIP_RESIDUAL
             for p0 in range(0, n_px, chunk):
                 n = min(chunk, n_px - p0)
