@@ -105,12 +105,15 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
  *            values); columns outside the fitted channel range hold zeros.  e_pad multiple of 8,
  *            n_planes*e_pad a multiple of 16 and <= 256.
  * k_begin,k_end: channel window (elements) the kernel streams; rounded outwards to 128-byte blocks.
- * x_dev    : fp32, element-major: x_dev[e*ld_x + p] for e < n_comp, p < n_px. */
+ * x_dev    : fp32, element-major: x_dev[e*ld_x + p] for e < n_comp, p < n_px.
+ * neg_list_dev / neg_count_dev (optional, both or neither): the epilogue appends px_offset + p of
+ *            every pixel whose solution has a negative component to neg_list_dev (capacity >= n_px)
+ *            and bumps *neg_count_dev (caller zeroes it); consumed by mt_nnls_list. */
 int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                     int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                     int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                     const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
-                    void *stream);
+                    int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev, void *stream);
 
 /* Same contract on CUDA cores (no tensor cores, fp32 weights [n_comp][ld_w]); exists for
  * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */
@@ -126,6 +129,11 @@ int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int6
  * incremented once per pixel that needed the fix-up. */
 int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
                   const double *hinv_dev, int32_t *n_fixed_dev, void *stream);
+
+/* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
+ * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]). */
+int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
+                 int32_t n_comp, const double *g_dev, const double *hinv_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,9 @@ constexpr int kSmemLimit = 227 * 1024;
 struct FitParams {
     long long n_px;
     long long ld_x;
+    long long px_offset;  // added to local pixel numbers written to neg_list
+    int *neg_list;        // optional: pixels whose solution has a negative component
+    int *neg_count;
     float *x;
     const float *colscale;
     int n_tiles;
@@ -189,6 +192,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                 const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
                 const uint32_t taddr =
                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+                bool negative = false;
                 for (int c0 = 0; c0 < p.e_pad; c0 += 8) {
                     // planes are stacked along N; Horner from the least significant plane:
                     // x = cs * (S0 + r * (S1 + r * S2))
@@ -205,8 +209,22 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int e = c0 + j;
-                            if (e < p.n_comp) p.x[(long long)e * p.ld_x + px] = cs[e] * acc[j];
+                            if (e < p.n_comp) {
+                                const float v = cs[e] * acc[j];
+                                negative |= (v < 0.f);
+                                p.x[(long long)e * p.ld_x + px] = v;
+                            }
                         }
+                    }
+                }
+                if (p.neg_list != nullptr) {
+                    // compact the pixels that need the non-negative fix-up: one atomic per warp
+                    const unsigned ballot = __ballot_sync(0xffffffffu, negative);
+                    if (ballot != 0u) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(p.neg_count, __popc(ballot));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (negative) p.neg_list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)(p.px_offset + px);
                     }
                 }
             }
@@ -336,7 +354,7 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                                int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                                int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                                const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
-                               void *stream_) {
+                               int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
     MT_REQUIRE(dtype == MT_DTYPE_F32 || dtype == MT_DTYPE_F16, "mt_fit_contract: dtype %d", dtype);
@@ -362,8 +380,14 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
     FitParams p{};
+    MT_REQUIRE((neg_list_dev == nullptr) == (neg_count_dev == nullptr),
+               "mt_fit_contract: neg_list and neg_count must be given together");
+    MT_REQUIRE(px_offset >= 0 && px_offset + n_px < (1ll << 31), "mt_fit_contract: px_offset=%lld", (long long)px_offset);
     p.n_px = n_px;
     p.ld_x = ld_x;
+    p.px_offset = px_offset;
+    p.neg_list = neg_list_dev;
+    p.neg_count = neg_count_dev;
     p.x = x_dev;
     p.colscale = colscale_dev;
     p.bke = kRowBytes / es;

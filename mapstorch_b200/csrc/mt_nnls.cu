@@ -49,10 +49,14 @@ __device__ bool chol_solve(const double *M, int ld, const unsigned char *idx, in
 }
 
 template <int EMAX>
+__device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, int E, const double *G,
+                          const double *H, int *__restrict__ n_fixed);
+
+template <int EMAX>
 __global__ void __launch_bounds__(kNnlsThreads)
 nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, const double *__restrict__ g_dev,
-                  const double *__restrict__ h_dev, int *__restrict__ n_fixed) {
-    constexpr int HALF = EMAX / 2;
+                  const double *__restrict__ h_dev, int *__restrict__ n_fixed, const int *__restrict__ list,
+                  const int *__restrict__ list_count) {
     extern __shared__ double mats[];  // G[E*E], H[E*E]
     double *G = mats, *H = mats + E * E;
     for (int i = threadIdx.x; i < E * E; i += kNnlsThreads) {
@@ -60,9 +64,17 @@ nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, 
         H[i] = h_dev[i];
     }
     __syncthreads();
-    const long long px = (long long)blockIdx.x * kNnlsThreads + threadIdx.x;
-    if (px >= n_px) return;
+    // scan mode: one thread per pixel of [0, n_px); list mode: grid-stride over the compacted list
+    const long long n_items = list ? (long long)*list_count : n_px;
+    for (long long item = (long long)blockIdx.x * kNnlsThreads + threadIdx.x; item < n_items;
+         item += (long long)gridDim.x * kNnlsThreads)
+        fix_pixel<EMAX>(x, ld_x, list ? (long long)list[item] : item, E, G, H, n_fixed);
+}
 
+template <int EMAX>
+__device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, int E, const double *G,
+                          const double *H, int *__restrict__ n_fixed) {
+    constexpr int HALF = EMAX / 2;
     double xu[EMAX];
     bool any_neg = false;
     double xmax = 0.0;
@@ -184,7 +196,7 @@ nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, 
 
 template <int EMAX>
 int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
-                cudaStream_t stream) {
+                const int *list, const int *list_count, cudaStream_t stream) {
     auto kern = nnls_fixup_kernel<EMAX>;
     const size_t smem = sizeof(double) * 2 * (size_t)E * E;
     static int smem_set[16] = {0};
@@ -194,10 +206,19 @@ int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, co
         MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev < 16) smem_set[dev] = (int)smem;
     }
-    const unsigned grid = (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
-    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, n_px, E, g, h, n_fixed);
+    const unsigned grid = list ? (unsigned)(mt::num_sms() * 8) : (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
+    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
+}
+
+int dispatch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
+                  const int *list, const int *list_count, cudaStream_t stream) {
+    if (E <= 16) return launch_nnls<16>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, stream);
+    if (E <= 32) return launch_nnls<32>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, stream);
+    if (E <= 64) return launch_nnls<64>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, stream);
+    if (E <= 104) return launch_nnls<104>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, stream);
+    return mt::fail(MT_ERR_UNSUPPORTED, "non-negative solve: n_comp=%d > 104", E);
 }
 
 }  // namespace
@@ -209,9 +230,15 @@ extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n
     MT_REQUIRE(n_px >= 0 && n_comp >= 1 && ld_x >= n_px, "mt_nnls_fixup: bad sizes");
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (n_comp <= 16) return launch_nnls<16>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
-    if (n_comp <= 32) return launch_nnls<32>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
-    if (n_comp <= 64) return launch_nnls<64>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
-    if (n_comp <= 104) return launch_nnls<104>(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, stream);
-    return mt::fail(MT_ERR_UNSUPPORTED, "mt_nnls_fixup: n_comp=%d > 104", n_comp);
+    return dispatch_nnls(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, nullptr, nullptr, stream);
 }
+
+extern "C" int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
+                            int32_t n_comp, const double *g_dev, const double *hinv_dev, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(x_dev && list_dev && count_dev && g_dev && hinv_dev, "mt_nnls_list: null pointer");
+    MT_REQUIRE(n_comp >= 1, "mt_nnls_list: n_comp=%d", n_comp);
+    return dispatch_nnls(x_dev, ld_x, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev,
+                         static_cast<cudaStream_t>(stream_));
+}
+

@@ -136,6 +136,8 @@ class MapFitPlan:
         self._packs = {}
         self._snip = None
         self._host_out = {}
+        self._neg = None
+        self._last_engine = None
         self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
         if self.use_snip:
             p = self.params
@@ -167,32 +169,41 @@ class MapFitPlan:
             self._packs[key] = torch.from_numpy(w).cuda()
         return self._packs[key]
 
+    def _neg_buffers(self, n_px):
+        """(pixel list, counter) the K3 epilogue fills; grown on demand, reused across calls."""
+        if self._neg is None or self._neg[0].numel() < n_px:
+            self._neg = (torch.empty(n_px, dtype=torch.int32, device="cuda"),
+                         torch.zeros(1, dtype=torch.int32, device="cuda"))
+        return self._neg
+
     # -- the fit -----------------------------------------------------------------------------------
-    def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream):
+    def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0):
         """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
         if self.timers is not None:
             s = stream if stream is not None else torch.cuda.current_stream()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record(s)
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream)
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset)
             t1.record(s)
             self.timers.append((t0, t1, spec2d.shape[0]))
         else:
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream)
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset)
 
-    def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream):
+    def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0):
         n_px, n_ch_total, ld = spec2d.shape[0], spec2d.shape[1], spec2d.stride(0)
         es = spec2d.element_size()
         tma_ok = (ld * es) % 16 == 0 and spec2d.data_ptr() % 16 == 0
         if engine == "tensor" and not tma_ok:
             engine = "simt"
+        self._last_engine = engine
         if engine == "tensor":
             kind = "f16" if spec2d.dtype == torch.float16 else "tf32"
             pack, scale = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat)
             _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
                          n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
                          self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), x.data_ptr(), x.stride(0),
-                         _native.stream_ptr(stream))
+                         int(px_offset), neg[0].data_ptr() if neg is not None else None,
+                         neg[1].data_ptr() if neg is not None else None, _native.stream_ptr(stream))
         elif engine == "simt":
             if repeat != 1:
                 raise _native.NativeError(-3, "the CUDA-core contraction expects an unsplit residual")
@@ -215,8 +226,13 @@ class MapFitPlan:
             out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
         dense = self.n_live == n_all
         x = out if dense else torch.empty((self.n_live, n_px), dtype=torch.float32, device="cuda")
+        # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
+        neg = None
+        if nonneg and engine == "tensor" and n_px:
+            neg = self._neg_buffers(n_px)
+            neg[1].zero_()
         if not self.use_snip:
-            self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream)
+            self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg)
         else:
             lohi, n_pass = self._snip
             hilo = engine == "tensor"
@@ -229,11 +245,18 @@ class MapFitPlan:
                 n = min(chunk, n_px - p0)
                 _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass, self.boxcar_size,
                                  scratch[:n], mode, stream)
-                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream)
+                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0)
         if nonneg and n_px:
-            _native.call("mt_nnls_fixup", x.data_ptr(), x.stride(0), n_px, self.n_live, self.gram_dev.data_ptr(),
-                         self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
-                         _native.stream_ptr(stream))
+            if self._last_engine == "tensor" and neg is not None:
+                _native.call("mt_nnls_list", x.data_ptr(), x.stride(0), neg[0].data_ptr(), neg[1].data_ptr(),
+                             self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
+                             _native.stream_ptr(stream))
+                if n_fixed is not None:
+                    n_fixed.copy_(neg[1])
+            else:
+                _native.call("mt_nnls_fixup", x.data_ptr(), x.stride(0), n_px, self.n_live, self.gram_dev.data_ptr(),
+                             self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
+                             _native.stream_ptr(stream))
         if not dense:
             out[torch.as_tensor(self.live, device="cuda")] = x
         return out
