@@ -3,14 +3,15 @@
 // Replaces snip_bkg/snip_op (bkg.py:53-114): boxcar smooth -> log1p -> n_pass clipping passes
 // bg[i] <- min((bg[lo_i] + bg[hi_i]) / 2, bg[i]) -> expm1, for a batch of spectra.  The
 // reference runs ~10 ATen ops plus a host sync per pass over HBM-resident [P,C] tensors; here
-// a CTA keeps PIX spectra on chip for all passes:
-//   * every thread owns channels {tid + T*k} of each of the CTA's PIX pixels and keeps their
-//     current values in registers (the centre value never touches shared memory);
-//   * neighbours bg[lo], bg[hi] come from ONE shared-memory copy of each spectrum
-//     (read phase -> barrier -> write phase -> barrier per pass);
+// a CTA keeps FOUR spectra on chip for all passes:
+//   * shared memory holds the log-background channel-major as float4 = the 4 pixels of the CTA,
+//     so one LDS.128 fetches a neighbour for all four pixels with a single address;
+//   * every thread owns channels {tid + T*k} and keeps their current values in registers (the
+//     centre value never touches shared memory): 2 LDS.128 + 1 STS.128 per channel and pass;
 //   * the gather indices depend only on global parameters, so they are precomputed on the
-//     host bit-exactly and shared by the PIX pixels of the CTA.
-// Bound: shared-memory bandwidth (2 LDS + 1 STS per channel, pass and pixel), not HBM.
+//     host bit-exactly; the words of the next pass are prefetched into registers
+//     while the current pass computes (they come from L2).
+// Bound: shared-memory bandwidth (12 bytes per channel, pass and pixel), not HBM.
 #include <cuda_fp16.h>
 
 #include "mt_common.cuh"
@@ -18,6 +19,7 @@
 namespace {
 
 constexpr int kSnipThreads = 512;
+constexpr int kSnipPix = 4;
 
 __device__ __forceinline__ float load_count(const float *p) { return __ldg(p); }
 __device__ __forceinline__ float load_count(const __half *p) { return __half2float(__ldg(p)); }
@@ -27,104 +29,129 @@ __device__ __forceinline__ float finite_or_zero(float v) {
     return (fabsf(v) <= 3.402823466e+38f) ? v : 0.f;
 }
 
-// PIX pixels per CTA, KCH channels per thread (n_ch <= kSnipThreads * KCH).
-template <typename T, int PIX, int KCH>
-__global__ void __launch_bounds__(kSnipThreads)
+__device__ __forceinline__ float clip(float a, float b, float c) {
+    return fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), c);
+}
+
+// KCH channels per thread (n_ch <= kSnipThreads * KCH); 4 pixels per CTA.
+template <typename T, int KCH>
+__global__ void __launch_bounds__(kSnipThreads, (KCH <= 4 ? 3 : (KCH <= 8 ? 2 : 1)))
 snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int ch0, int n_ch,
             const uint32_t *__restrict__ lohi, int n_pass, int boxcar, float *__restrict__ out,
             long long ld_out, int out_mode) {
-    extern __shared__ float sbuf[];  // [PIX][n_ch]
+    extern __shared__ float4 sb[];  // [n_ch] x (4 pixels)
     const int tid = threadIdx.x;
-    const long long px0 = (long long)blockIdx.x * PIX;
+    const long long px0 = (long long)blockIdx.x * kSnipPix;
     const int half = boxcar / 2;
     const float wgt = 1.0f / (float)boxcar;
+    const T *rows[kSnipPix];
+#pragma unroll
+    for (int p = 0; p < kSnipPix; ++p) rows[p] = spec + (px0 + p < n_px ? px0 + p : px0) * ld_spec + ch0;
 
-    float cur[PIX][KCH];
+    float4 cur[KCH];
 
     // ---- stage raw counts in shared memory -------------------------------------------------
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) {
-        const long long px = px0 + p;
-        const T *row = spec + (px < n_px ? px : 0) * ld_spec + ch0;
-#pragma unroll
-        for (int k = 0; k < KCH; ++k) {
-            const int i = tid + k * kSnipThreads;
-            if (i < n_ch) sbuf[p * n_ch + i] = (px < n_px) ? load_count(row + i) : 0.f;
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        if (i < n_ch) {
+            float4 r;
+            r.x = load_count(rows[0] + i);
+            r.y = (px0 + 1 < n_px) ? load_count(rows[1] + i) : 0.f;
+            r.z = (px0 + 2 < n_px) ? load_count(rows[2] + i) : 0.f;
+            r.w = (px0 + 3 < n_px) ? load_count(rows[3] + i) : 0.f;
+            sb[i] = r;
         }
     }
     __syncthreads();
 
     // ---- boxcar mean (zero padded, bkg.py:93-97) and log1p (bkg.py:100-101) -----------------
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) {
-#pragma unroll
-        for (int k = 0; k < KCH; ++k) {
-            const int i = tid + k * kSnipThreads;
-            float acc = 0.f;
-            if (i < n_ch) {
-                for (int j = -half; j <= half; ++j) {
-                    const int q = i + j;
-                    const float v = (q >= 0 && q < n_ch) ? sbuf[p * n_ch + q] : 0.f;
-                    acc = __fadd_rn(acc, __fmul_rn(v, wgt));
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n_ch) {
+            for (int j = -half; j <= half; ++j) {
+                const int q = i + j;
+                if (q >= 0 && q < n_ch) {
+                    const float4 v = sb[q];
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, wgt));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, wgt));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, wgt));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, wgt));
+                } else {  // the zero padding still takes part in the sum (adds +0)
+                    acc.x = __fadd_rn(acc.x, 0.f);
+                    acc.y = __fadd_rn(acc.y, 0.f);
+                    acc.z = __fadd_rn(acc.z, 0.f);
+                    acc.w = __fadd_rn(acc.w, 0.f);
                 }
-                acc = finite_or_zero(log1pf(acc));
             }
-            cur[p][k] = acc;
+            acc.x = finite_or_zero(log1pf(acc.x));
+            acc.y = finite_or_zero(log1pf(acc.y));
+            acc.z = finite_or_zero(log1pf(acc.z));
+            acc.w = finite_or_zero(log1pf(acc.w));
         }
+        cur[k] = acc;
     }
     __syncthreads();
 #pragma unroll
-    for (int p = 0; p < PIX; ++p)
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        if (i < n_ch) sb[i] = cur[k];
+    }
+
+    // ---- clipping passes (bkg.py:53-66, 104-112), Jacobi style ------------------------------
+    uint32_t tab[KCH], tab_next[KCH];
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        tab[k] = (n_pass > 0 && i < n_ch) ? __ldg(lohi + i) : 0u;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const uint32_t *next = lohi + (long long)(pass + 1) * n_ch;
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
             const int i = tid + k * kSnipThreads;
-            if (i < n_ch) sbuf[p * n_ch + i] = cur[p][k];
+            tab_next[k] = (pass + 1 < n_pass && i < n_ch) ? __ldg(next + i) : 0u;
         }
-    __syncthreads();
-
-    // ---- clipping passes (bkg.py:53-66, 104-112), Jacobi style ------------------------------
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const uint32_t *tab = lohi + (long long)pass * n_ch;
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
             const int i = tid + k * kSnipThreads;
             if (i < n_ch) {
-                const uint32_t w = __ldg(tab + i);
-                const int lo = w & 0xffffu, hi = w >> 16;
-#pragma unroll
-                for (int p = 0; p < PIX; ++p) {
-                    const float a = sbuf[p * n_ch + lo], b = sbuf[p * n_ch + hi];
-                    cur[p][k] = fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), cur[p][k]);
-                }
+                const float4 a = sb[tab[k] & 0xffffu], b = sb[tab[k] >> 16];
+                cur[k].x = clip(a.x, b.x, cur[k].x);
+                cur[k].y = clip(a.y, b.y, cur[k].y);
+                cur[k].z = clip(a.z, b.z, cur[k].z);
+                cur[k].w = clip(a.w, b.w, cur[k].w);
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int p = 0; p < PIX; ++p)
-#pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-                const int i = tid + k * kSnipThreads;
-                if (i < n_ch) sbuf[p * n_ch + i] = cur[p][k];
-            }
+        for (int k = 0; k < KCH; ++k) {
+            const int i = tid + k * kSnipThreads;
+            if (i < n_ch) sb[i] = cur[k];
+            tab[k] = tab_next[k];
+        }
         __syncthreads();
     }
 
     // ---- back to counts (bkg.py:113-114) and output -----------------------------------------
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) {
-        const long long px = px0 + p;
-        if (px >= n_px) continue;
-        const T *row = spec + px * ld_spec + ch0;
-        float *orow = out + px * ld_out;
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        if (i >= n_ch) continue;
+        const float vals[kSnipPix] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
 #pragma unroll
-        for (int k = 0; k < KCH; ++k) {
-            const int i = tid + k * kSnipThreads;
-            if (i >= n_ch) continue;
-            const float bkg = finite_or_zero(expm1f(cur[p][k]));
+        for (int p = 0; p < kSnipPix; ++p) {
+            const long long px = px0 + p;
+            if (px >= n_px) continue;
+            float *orow = out + px * ld_out;
+            const float bkg = finite_or_zero(expm1f(vals[p]));
             if (out_mode == MT_SNIP_BACKGROUND) {
                 orow[i] = bkg;
             } else {
-                const float r = __fsub_rn(load_count(row + i), bkg);
+                const float r = __fsub_rn(load_count(rows[p] + i), bkg);
                 if (out_mode == MT_SNIP_RESIDUAL) {
                     orow[i] = r;
                 } else {
@@ -137,15 +164,21 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
     }
 }
 
-template <typename T, int PIX, int KCH>
+template <typename T, int KCH>
 int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi,
                 int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
-    auto kern = snip_kernel<T, PIX, KCH>;
-    const size_t smem = sizeof(float) * (size_t)PIX * n_ch;
-    MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long n_cta = (n_px + PIX - 1) / PIX;
-    kern<<<(unsigned)n_cta, kSnipThreads, smem, stream>>>(static_cast<const T *>(spec), n_px, ld_spec, ch0,
-                                                          n_ch, lohi, n_pass, boxcar, out, ld_out, out_mode);
+    auto kern = snip_kernel<T, KCH>;
+    const size_t smem = sizeof(float4) * (size_t)n_ch;
+    static int smem_set[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 16 || smem_set[dev] < (int)smem) {
+        MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 16) smem_set[dev] = (int)smem;
+    }
+    const long long n_cta = (n_px + kSnipPix - 1) / kSnipPix;
+    kern<<<(unsigned)n_cta, kSnipThreads, smem, stream>>>(static_cast<const T *>(spec), n_px, ld_spec, ch0, n_ch, lohi,
+                                                          n_pass, boxcar, out, ld_out, out_mode);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
@@ -153,18 +186,14 @@ int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_
 template <typename T>
 int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi,
                   int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
-    if (n_ch <= kSnipThreads * 2)
-        return launch_snip<T, 4, 2>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out,
-                                    out_mode, stream);
-    if (n_ch <= kSnipThreads * 4)
-        return launch_snip<T, 4, 4>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out,
-                                    out_mode, stream);
-    if (n_ch <= kSnipThreads * 8)
-        return launch_snip<T, 4, 8>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out,
-                                    out_mode, stream);
-    if (n_ch <= kSnipThreads * 16)
-        return launch_snip<T, 2, 16>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out,
-                                     out_mode, stream);
+#define MT_SNIP_CASE(K)                                                                                    \
+    if (n_ch <= kSnipThreads * K)                                                                          \
+        return launch_snip<T, K>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out, out_mode, stream);
+    MT_SNIP_CASE(2)
+    MT_SNIP_CASE(4)
+    MT_SNIP_CASE(8)
+    MT_SNIP_CASE(16)
+#undef MT_SNIP_CASE
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: n_ch=%d exceeds the on-chip limit of %d channels", n_ch,
                     kSnipThreads * 16);
 }

@@ -214,9 +214,15 @@ class MapFitPlan:
         else:
             raise ValueError(f"unknown engine {engine!r}")
 
-    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None):
+    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None):
         """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
-        rows in `self.names` order (components without an open line stay 0)."""
+        rows in `self.names` order (components without an open line stay 0).
+
+        exact_counts: the tensor-core operands (fp16 / tf32) hold 11 significant bits, i.e. integer
+        counts below 2048 exactly.  fp16 volumes satisfy that by construction and the SNIP path
+        splits its residual exactly; for fp32 volumes without SNIP, None (default) checks the
+        maximum on the device (one extra read of the volume and a host sync) and routes volumes
+        with larger values through an exact hi/lo split; True skips the check."""
         if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
             raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
         if spec2d.shape[1] <= self.er[1]:
@@ -231,7 +237,23 @@ class MapFitPlan:
         if nonneg and engine == "tensor" and n_px:
             neg = self._neg_buffers(n_px)
             neg[1].zero_()
-        if not self.use_snip:
+        wide = False
+        if not self.use_snip and engine == "tensor" and spec2d.dtype == torch.float32 and not exact_counts:
+            wide = bool(spec2d[:, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0)
+        if wide:
+            # exact for any magnitude: stream the volume as a tf32-exact high part plus remainder
+            width = 2 * self.n_ch
+            pitch = -(-width // 4) * 4
+            chunk = min(SNIP_CHUNK_PX, n_px)
+            scratch = torch.empty((chunk, pitch), dtype=torch.float32, device="cuda")[:, :width]
+            for p0 in range(0, n_px, chunk):
+                n = min(chunk, n_px - p0)
+                y = spec2d[p0: p0 + n, self.er[0]: self.er[1] + 1]
+                hi = (y.view(torch.int32) & -8192).view(torch.float32)
+                scratch[:n, : self.n_ch] = hi
+                scratch[:n, self.n_ch:] = y - hi
+                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2, 0, width, engine, stream, neg, p0)
+        elif not self.use_snip:
             self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg)
         else:
             lohi, n_pass = self._snip

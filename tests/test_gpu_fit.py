@@ -206,3 +206,24 @@ def test_full_size_linearity_property():
     d = plan.fit(y1.half(), nonneg=False)
     assert torch.equal(d[:, 40000], d[:, 3])
     assert float(((d - a)[:, :40000].abs() / scale[:40000]).max()) <= 2e-5
+
+
+def test_fp32_counts_above_2048_take_the_exact_split_path():
+    """tf32 operands hold integers below 2048 exactly; brighter fp32 volumes must not lose bits."""
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12()
+    er = (0, 2047)
+    y, names = synth(p, er, ELEMS10, 300, seed=31, lo=3.6, hi=4.4)
+    assert y.max() > 20000
+    B, _ = mo.basis(p, er, ELEMS10)
+    ref = mo.fit_lstsq(y, B)
+    plan = opt.MapFitPlan(er, ELEMS10, p, use_snip=False)
+    dev = torch.from_numpy(y).cuda()
+    x = plan.fit(dev, nonneg=False).cpu().numpy().T
+    check_against(x, ref, 1e-4)
+    assert (np.abs(x - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() <= 2e-6
+    # the unchecked direct path truncates operands: visibly worse, which is why the check exists
+    bad = plan.fit(dev, nonneg=False, exact_counts=True).cpu().numpy().T
+    assert (np.abs(bad - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() > 1e-5
