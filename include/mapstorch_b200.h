@@ -135,6 +135,47 @@ int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, cons
 int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
                  int32_t n_comp, const double *g_dev, const double *hinv_dev, void *stream);
 
+/* ---- K4: batched per-pixel nonlinear refinement (BASELINE config 4) ----------------------------
+ * Replaces fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:165-327) applied per pixel:
+ * every pixel refines up to four peak-shape parameters together with all amplitudes by a damped
+ * Gauss-Newton iteration with analytic Jacobians on sum_c (model_c + bkg_c - y_c)^2.
+ * Model terms: Gaussian lines  x[comp] * factor * slope / (sigma sqrt(2 pi)) * exp(-(ev_c - energy)^2 / (2 sigma^2)),
+ * sigma = sigma_scale * sqrt((FWHM_OFFSET / 2.3548)^2 + e296 * FWHM_FANOPRIME)  (map.py:57-58, 165-168, 208). */
+#define MT_THETA_ENERGY_OFFSET 0
+#define MT_THETA_ENERGY_SLOPE 1
+#define MT_THETA_FWHM_OFFSET 2
+#define MT_THETA_FWHM_FANOPRIME 3
+#define MT_MAX_THETA 4
+
+typedef struct MtRefineLine {
+    float energy;      /* keV */
+    float factor;      /* branching ratio / normalisation of the line (amplitude excluded) */
+    int32_t comp;      /* component (row of x) the line belongs to */
+    float sigma_scale; /* 1, or COMPTON_FWHM_CORR for the Compton Gaussian (map.py:105) */
+    float e296;        /* energy * 2.96 as the reference rounds it (map.py:167) */
+} MtRefineLine;
+
+typedef struct MtRefineConfig {
+    int32_t n_ch, ch0;  /* fitted channels [ch0, ch0 + n_ch) of each spectrum row */
+    int32_t n_comp, n_lines, n_theta, max_iter;
+    int32_t theta_id[MT_MAX_THETA]; /* MT_THETA_* of each free parameter */
+    float theta0[MT_MAX_THETA], theta_lo[MT_MAX_THETA], theta_hi[MT_MAX_THETA];
+    float energy_offset, energy_slope, energy_quad, fwhm_offset, fwhm_fanoprime; /* global values */
+    float tol;          /* stop when steps fall below tol (relative) */
+} MtRefineConfig;
+
+/* lines_host sorted by energy; chan_lines_host[c] = lo | hi << 16 is the range of line indices that can
+ * contribute at channel c; comp_start_host/comp_lines_host list each component's lines;
+ * line_window_host[l] = first | (last + 1) << 16 local channel of line l's window; g0inv_dev = inverse
+ * Gram matrix of the unit-amplitude basis at the global parameters, fp32 [n_comp][n_comp].
+ * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
+ * theta_dev [n_theta][ld_x], loss_dev [n_px], iters_dev [n_px] are optional outputs. */
+int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
+              int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+              const uint32_t *chan_lines_host, const int32_t *comp_start_host, const int32_t *comp_lines_host,
+              const uint32_t *line_window_host, const float *g0inv_dev, float *x_dev, int64_t ld_x,
+              float *theta_dev, float *loss_dev, int32_t *iters_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,22 @@ class MtTerm(ctypes.Structure):
                 ("p3", ctypes.c_float), ("amp", ctypes.c_float)]
 
 
+class MtRefineLine(ctypes.Structure):
+    _fields_ = [("energy", ctypes.c_float), ("factor", ctypes.c_float), ("comp", ctypes.c_int32),
+                ("sigma_scale", ctypes.c_float), ("e296", ctypes.c_float)]
+
+
+class MtRefineConfig(ctypes.Structure):
+    _fields_ = [("n_ch", ctypes.c_int32), ("ch0", ctypes.c_int32), ("n_comp", ctypes.c_int32),
+                ("n_lines", ctypes.c_int32), ("n_theta", ctypes.c_int32), ("max_iter", ctypes.c_int32),
+                ("theta_id", ctypes.c_int32 * 4), ("theta0", ctypes.c_float * 4), ("theta_lo", ctypes.c_float * 4),
+                ("theta_hi", ctypes.c_float * 4), ("energy_offset", ctypes.c_float), ("energy_slope", ctypes.c_float),
+                ("energy_quad", ctypes.c_float), ("fwhm_offset", ctypes.c_float), ("fwhm_fanoprime", ctypes.c_float),
+                ("tol", ctypes.c_float)]
+
+
+THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3}
+
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 # name -> argument types; every function returns int except mt_last_error
@@ -44,7 +60,7 @@ SIGNATURES = {
     "mt_nnls_list": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp],
     "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp],
     "mt_nnls_fixup": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp],
-    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
 }
 
 
@@ -67,8 +83,6 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name, None)
         if fn is None:
-            if name == "mt_refine":
-                continue
             raise NativeError(-101, f"{path} does not export {name}")
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int

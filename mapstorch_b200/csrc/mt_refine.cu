@@ -1,0 +1,425 @@
+// K4 -- batched per-pixel nonlinear refinement (BASELINE config 4).
+//
+// The reference can free calibration parameters per spectrum with
+// fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:201,119,249-317): Adam over autograd
+// on the objective sum_c (model_c(theta, a) + bkg_c - y_c)^2.  Here every pixel refines up to four
+// peak-shape parameters theta (energy offset / slope, FWHM offset / Fano term) together with all
+// amplitudes by a damped Gauss-Newton iteration with ANALYTIC Jacobians:
+//
+//   one CTA (128 threads) per pixel, per iteration
+//   B1  channel-major : every thread evaluates its channels: model m_c, the theta-derivatives
+//                       d_k(c) = dm_c/dtheta_k and the residual r_c (kept in shared memory), with
+//                       thread-local partial sums of the loss, D^T r and D^T D
+//   B2  component-major: every warp owns whole components and reduces B^T r and D^T B over the
+//                       line windows (deterministic: no atomics, fixed reduction trees)
+//   C   solve         : the amplitude block of the Gauss-Newton matrix is the pixel-independent
+//                       Gram matrix G0 (its inverse is an input), the theta block and the coupling
+//                       are exact, so the step is a Schur complement on an n_theta x n_theta system
+//
+// The gradient is exact, only the amplitude curvature is frozen at the global parameters, so the
+// fixed point is the true minimiser.  Model terms are the Gaussian lines of model_spec's default
+// path (map.py:152-208 with f_step = 0, elastic, Compton Gaussian); exp dominates (MUFU bound).
+#include <cuda_fp16.h>
+
+#include "mt_common.cuh"
+
+namespace {
+
+constexpr int kRefThreads = 128;
+constexpr int kRefWarps = kRefThreads / 32;
+constexpr int kMaxLines = 512;
+constexpr int kMaxComp = 64;
+constexpr int kMaxTheta = MT_MAX_THETA;
+
+struct RefParams {
+    MtRefineConfig cfg;
+    const MtRefineLine *lines;      // [n_lines], sorted by energy
+    const uint32_t *chan_lines;     // [n_ch]: lo | hi << 16, line index range covering the channel
+    const int32_t *comp_start;      // [n_comp + 1] into comp_lines
+    const int32_t *comp_lines;      // line indices grouped by component
+    const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
+    const float *g0inv;             // [n_comp][n_comp]
+    const float *bkg;
+    long long ld_bkg;
+    const void *spec;
+    long long ld_spec;
+    float *x;
+    long long ld_x;
+    float *theta_out;
+    float *loss_out;
+    int *iters_out;
+    long long n_px;
+};
+
+template <typename T>
+__device__ __forceinline__ float ld_spec(const T *p);
+template <>
+__device__ __forceinline__ float ld_spec<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_spec<__half>(const __half *p) { return __half2float(__ldg(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRefThreads)
+refine_kernel(const RefParams p) {
+    extern __shared__ float dyn[];  // r[n_ch], d[n_theta][n_ch]
+    const MtRefineConfig &cfg = p.cfg;
+    const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines, NT = cfg.n_theta;
+    float *r_s = dyn;
+    float *d_s = dyn + n_ch;
+
+    __shared__ float l_inv_sigma[kMaxLines], l_unit[kMaxLines], l_coef[kMaxLines], l_dfo[kMaxLines],
+        l_dfa[kMaxLines];
+    __shared__ float xs[kMaxComp], x_prev[kMaxComp], dx[kMaxComp], gx[kMaxComp], w_s[kMaxComp];
+    __shared__ float hthx[kMaxTheta][kMaxComp], t1[kMaxComp][kMaxTheta];
+    __shared__ float part[kRefWarps][1 + kMaxTheta + kMaxTheta * kMaxTheta];
+    __shared__ float theta[kMaxTheta], theta_prev[kMaxTheta], dtheta[kMaxTheta];
+    __shared__ float ctl[4];  // loss, loss_prev, alpha, flag
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long px = blockIdx.x;
+    const T *row = static_cast<const T *>(p.spec) + px * p.ld_spec + cfg.ch0;
+    const float *brow = p.bkg ? p.bkg + px * p.ld_bkg : nullptr;
+
+    for (int e = tid; e < E; e += kRefThreads) {
+        xs[e] = fmaxf(p.x[(long long)e * p.ld_x + px], 0.f);
+        x_prev[e] = xs[e];
+        dx[e] = 0.f;
+    }
+    if (tid < kMaxTheta) {
+        theta[tid] = tid < NT ? cfg.theta0[tid] : 0.f;
+        theta_prev[tid] = theta[tid];
+        dtheta[tid] = 0.f;
+    }
+    if (tid == 0) {
+        ctl[1] = 3.0e38f;  // loss_prev
+        ctl[2] = 1.f;      // alpha
+    }
+    __syncthreads();
+
+    int iter = 0;
+    for (;; ++iter) {
+        // ---- current calibration ------------------------------------------------------------
+        float off = cfg.energy_offset, slope = cfg.energy_slope, fo = cfg.fwhm_offset, fa = cfg.fwhm_fanoprime;
+        int k_off = -1, k_slope = -1, k_fo = -1, k_fa = -1;
+        for (int k = 0; k < NT; ++k) {
+            const int id = cfg.theta_id[k];
+            if (id == MT_THETA_ENERGY_OFFSET) { off = theta[k]; k_off = k; }
+            if (id == MT_THETA_ENERGY_SLOPE) { slope = theta[k]; k_slope = k; }
+            if (id == MT_THETA_FWHM_OFFSET) { fo = theta[k]; k_fo = k; }
+            if (id == MT_THETA_FWHM_FANOPRIME) { fa = theta[k]; k_fa = k; }
+        }
+        const float s0 = fo / 2.3548f;
+        // ---- A: per-line shape constants ---------------------------------------------------
+        for (int l = tid; l < L; l += kRefThreads) {
+            const MtRefineLine ln = p.lines[l];
+            const float base = sqrtf(fmaxf(s0 * s0 + ln.e296 * fa, 1e-12f));
+            const float sigma = base * ln.sigma_scale;
+            const float unit = ln.factor * slope / (sigma * 2.5066282746310002f);
+            l_inv_sigma[l] = 1.f / sigma;
+            l_unit[l] = unit;
+            l_coef[l] = unit * xs[ln.comp];
+            l_dfo[l] = ln.sigma_scale * s0 / (2.3548f * base);  // d sigma / d FWHM_OFFSET
+            l_dfa[l] = ln.sigma_scale * ln.e296 / (2.f * base); // d sigma / d FWHM_FANOPRIME
+        }
+        __syncthreads();
+
+        // ---- B1: channels -> model, theta derivatives, residual ---------------------------
+        float acc[1 + kMaxTheta + kMaxTheta * kMaxTheta];
+#pragma unroll
+        for (int i = 0; i < 1 + kMaxTheta + kMaxTheta * kMaxTheta; ++i) acc[i] = 0.f;
+        for (int c = tid; c < n_ch; c += kRefThreads) {
+            const float cg = (float)(cfg.ch0 + c);
+            const float ev = off + slope * cg + cfg.energy_quad * (cg * cg);
+            const uint32_t range = __ldg(p.chan_lines + c);
+            float m = 0.f, d_ev = 0.f, d_fo = 0.f, d_fa = 0.f;
+            for (int l = (int)(range & 0xffffu); l < (int)(range >> 16); ++l) {
+                const float is = l_inv_sigma[l];
+                const float u = (ev - __ldg(&p.lines[l].energy)) * is;
+                const float v = l_coef[l] * expf(-0.5f * u * u);
+                m += v;
+                d_ev -= v * u * is;
+                const float dsg = v * (u * u - 1.f) * is;
+                d_fo += dsg * l_dfo[l];
+                d_fa += dsg * l_dfa[l];
+            }
+            float d[kMaxTheta] = {0.f, 0.f, 0.f, 0.f};
+            if (k_off >= 0) d[k_off] = d_ev;
+            if (k_slope >= 0) d[k_slope] = d_ev * cg + m / slope;
+            if (k_fo >= 0) d[k_fo] = d_fo;
+            if (k_fa >= 0) d[k_fa] = d_fa;
+            const float res = m + (brow ? __ldg(brow + c) : 0.f) - ld_spec<T>(row + c);
+            r_s[c] = res;
+            acc[0] += res * res;
+#pragma unroll
+            for (int k = 0; k < kMaxTheta; ++k) {
+                if (k < NT) {
+                    d_s[k * n_ch + c] = d[k];
+                    acc[1 + k] += d[k] * res;
+#pragma unroll
+                    for (int k2 = 0; k2 < kMaxTheta; ++k2) acc[1 + kMaxTheta + k * kMaxTheta + k2] += d[k] * d[k2];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 1 + kMaxTheta + kMaxTheta * kMaxTheta; ++i) {
+            const float v = warp_sum(acc[i]);
+            if (lane == 0) part[warp][i] = v;
+        }
+        __syncthreads();
+
+        // ---- B2: components -> B^T r and D^T B over the line windows ------------------------
+        for (int e = warp; e < E; e += kRefWarps) {
+            float g = 0.f, h[kMaxTheta] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = p.comp_start[e]; j < p.comp_start[e + 1]; ++j) {
+                const int l = p.comp_lines[j];
+                const uint32_t win = __ldg(p.line_window + l);
+                const float is = l_inv_sigma[l], unit = l_unit[l], el = __ldg(&p.lines[l].energy);
+                for (int c = (int)(win & 0xffffu) + lane; c < (int)(win >> 16); c += 32) {
+                    const float cg = (float)(cfg.ch0 + c);
+                    const float ev = off + slope * cg + cfg.energy_quad * (cg * cg);
+                    const float u = (ev - el) * is;
+                    const float b = unit * expf(-0.5f * u * u);
+                    g += b * r_s[c];
+#pragma unroll
+                    for (int k = 0; k < kMaxTheta; ++k)
+                        if (k < NT) h[k] += b * d_s[k * n_ch + c];
+                }
+            }
+            g = warp_sum(g);
+#pragma unroll
+            for (int k = 0; k < kMaxTheta; ++k) h[k] = warp_sum(h[k]);
+            if (lane == 0) {
+                gx[e] = g;
+#pragma unroll
+                for (int k = 0; k < kMaxTheta; ++k) hthx[k][e] = h[k];
+            }
+        }
+        __syncthreads();
+
+        // ---- accept / reject the previous step -----------------------------------------------
+        if (tid == 0) {
+            float loss = 0.f;
+            for (int w = 0; w < kRefWarps; ++w) loss += part[w][0];
+            ctl[0] = loss;
+            const bool worse = loss > ctl[1] * (1.f + 1e-6f) && iter > 0;
+            ctl[3] = worse ? 1.f : 0.f;
+        }
+        __syncthreads();
+        const bool rejected = ctl[3] != 0.f;
+        if (rejected) {
+            // go back and retry with half the step (costs one evaluation)
+            const float alpha = ctl[2] * 0.5f;
+            for (int e = tid; e < E; e += kRefThreads) xs[e] = fmaxf(x_prev[e] + alpha * dx[e], 0.f);
+            if (tid < NT) theta[tid] = fminf(fmaxf(theta_prev[tid] + alpha * dtheta[tid], cfg.theta_lo[tid]), cfg.theta_hi[tid]);
+            __syncthreads();
+            if (tid == 0) ctl[2] = alpha;
+            __syncthreads();
+            if (alpha < 1e-3f || iter >= cfg.max_iter + 8) {
+                // give up on this direction: restore the last accepted state and stop
+                for (int e = tid; e < E; e += kRefThreads) xs[e] = x_prev[e];
+                if (tid < NT) theta[tid] = theta_prev[tid];
+                if (tid == 0) ctl[0] = ctl[1];
+                __syncthreads();
+                break;
+            }
+            continue;
+        }
+
+        // ---- C: damped Gauss-Newton step through the Schur complement on theta ----------------
+        for (int i = tid; i < E * (NT + 1); i += kRefThreads) {
+            const int e = i / (NT + 1), k = i % (NT + 1);
+            const float *gi = p.g0inv + (long long)e * E;
+            float s = 0.f;
+            if (k == NT) {
+                for (int j = 0; j < E; ++j) s += __ldg(gi + j) * gx[j];
+                w_s[e] = s;
+            } else {
+                for (int j = 0; j < E; ++j) s += __ldg(gi + j) * hthx[k][j];
+                t1[e][k] = s;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float S[kMaxTheta][kMaxTheta], rhs[kMaxTheta], sol[kMaxTheta];
+            for (int k = 0; k < NT; ++k) {
+                float g = 0.f;
+                for (int w = 0; w < kRefWarps; ++w) g += part[w][1 + k];
+                for (int j = 0; j < E; ++j) g -= hthx[k][j] * w_s[j];
+                rhs[k] = -g;
+                for (int k2 = 0; k2 < NT; ++k2) {
+                    float h = 0.f;
+                    for (int w = 0; w < kRefWarps; ++w) h += part[w][1 + kMaxTheta + k * kMaxTheta + k2];
+                    for (int j = 0; j < E; ++j) h -= hthx[k][j] * t1[j][k2];
+                    S[k][k2] = h;
+                }
+            }
+            for (int k = 0; k < NT; ++k) S[k][k] = S[k][k] * 1.0001f + 1e-30f;
+            // Gaussian elimination with partial pivoting on the NT x NT system
+            int perm[kMaxTheta] = {0, 1, 2, 3};
+            bool ok = true;
+            for (int c = 0; c < NT && ok; ++c) {
+                int piv = c;
+                for (int q = c + 1; q < NT; ++q)
+                    if (fabsf(S[perm[q]][c]) > fabsf(S[perm[piv]][c])) piv = q;
+                const int tmp = perm[c];
+                perm[c] = perm[piv];
+                perm[piv] = tmp;
+                const float pv = S[perm[c]][c];
+                if (!(fabsf(pv) > 0.f)) { ok = false; break; }
+                for (int q = c + 1; q < NT; ++q) {
+                    const float f = S[perm[q]][c] / pv;
+                    for (int cc = c; cc < NT; ++cc) S[perm[q]][cc] -= f * S[perm[c]][cc];
+                    rhs[perm[q]] -= f * rhs[perm[c]];
+                }
+            }
+            for (int c = NT - 1; c >= 0; --c) {
+                float s = rhs[perm[c]];
+                for (int cc = c + 1; cc < NT; ++cc) s -= S[perm[c]][cc] * sol[cc];
+                sol[c] = ok ? s / S[perm[c]][c] : 0.f;
+            }
+            for (int k = 0; k < kMaxTheta; ++k) {
+                theta_prev[k] = theta[k];
+                float step = (k < NT && isfinite(sol[k])) ? sol[k] : 0.f;
+                if (k < NT) {
+                    const float nt = fminf(fmaxf(theta[k] + step, cfg.theta_lo[k]), cfg.theta_hi[k]);
+                    step = nt - theta[k];
+                    theta[k] = nt;
+                }
+                dtheta[k] = step;
+            }
+            ctl[1] = ctl[0];
+            ctl[2] = 1.f;
+        }
+        __syncthreads();
+        float change = 0.f;
+        for (int e = tid; e < E; e += kRefThreads) {
+            float step = -w_s[e];
+            for (int k = 0; k < NT; ++k) step -= t1[e][k] * dtheta[k];
+            x_prev[e] = xs[e];
+            const float nx = fmaxf(xs[e] + step, 0.f);
+            dx[e] = nx - xs[e];
+            xs[e] = nx;
+            change = fmaxf(change, fabsf(dx[e]));
+        }
+        // convergence: relative amplitude change and theta steps below tol
+        float xmax = 0.f;
+        for (int e = tid; e < E; e += kRefThreads) xmax = fmaxf(xmax, fabsf(xs[e]));
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            change = fmaxf(change, __shfl_xor_sync(0xffffffffu, change, s));
+            xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, s));
+        }
+        __shared__ float cmax[kRefWarps], xm[kRefWarps];
+        if (lane == 0) {
+            cmax[warp] = change;
+            xm[warp] = xmax;
+        }
+        __syncthreads();
+        float cm = 0.f, xmm = 0.f;
+        for (int w = 0; w < kRefWarps; ++w) {
+            cm = fmaxf(cm, cmax[w]);
+            xmm = fmaxf(xmm, xm[w]);
+        }
+        bool small = cm <= cfg.tol * fmaxf(xmm, 1e-30f);
+        for (int k = 0; k < NT; ++k) small = small && fabsf(dtheta[k]) <= cfg.tol * fmaxf(fabsf(cfg.theta_hi[k] - cfg.theta_lo[k]), 1e-30f);
+        __syncthreads();
+        if (iter >= cfg.max_iter) {
+            // the state was just stepped; report the last evaluated state instead (its loss is known)
+            for (int e = tid; e < E; e += kRefThreads) xs[e] = x_prev[e];
+            if (tid < NT) theta[tid] = theta_prev[tid];
+            __syncthreads();
+            break;
+        }
+        if (small && iter > 0) {
+            // converged: one more evaluation would only confirm; keep the stepped state, loss of the
+            // previous evaluation is an upper bound to within tol
+            break;
+        }
+    }
+
+    for (int e = tid; e < E; e += kRefThreads) p.x[(long long)e * p.ld_x + px] = xs[e];
+    if (tid < NT && p.theta_out) p.theta_out[(long long)tid * p.ld_x + px] = theta[tid];
+    if (tid == 0) {
+        if (p.loss_out) p.loss_out[px] = ctl[0];
+        if (p.iters_out) p.iters_out[px] = iter;
+    }
+}
+
+}  // namespace
+
+extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
+                         int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+                         const uint32_t *chan_lines_host, const int32_t *comp_start_host,
+                         const int32_t *comp_lines_host, const uint32_t *line_window_host, const float *g0inv_dev,
+                         float *x_dev, int64_t ld_x, float *theta_dev, float *loss_dev, int32_t *iters_dev,
+                         void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(spec_dev && cfg_host && lines_host && chan_lines_host && comp_start_host && comp_lines_host &&
+                   line_window_host && g0inv_dev && x_dev,
+               "mt_refine: null pointer");
+    const MtRefineConfig &cfg = *cfg_host;
+    MT_REQUIRE(cfg.n_ch > 0 && cfg.n_ch <= 8192 && cfg.ch0 >= 0 && ld_spec >= (int64_t)cfg.ch0 + cfg.n_ch,
+               "mt_refine: channel window");
+    MT_REQUIRE(cfg.n_comp >= 1 && cfg.n_comp <= kMaxComp, "mt_refine: n_comp=%d (max %d)", cfg.n_comp, kMaxComp);
+    MT_REQUIRE(cfg.n_lines >= 1 && cfg.n_lines <= kMaxLines, "mt_refine: n_lines=%d (max %d)", cfg.n_lines, kMaxLines);
+    MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= kMaxTheta, "mt_refine: n_theta=%d", cfg.n_theta);
+    MT_REQUIRE(n_px >= 0 && ld_x >= n_px && (!bkg_dev || ld_bkg >= cfg.n_ch), "mt_refine: sizes");
+    for (int l = 0; l < cfg.n_lines; ++l)
+        MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp, "mt_refine: line %d component", l);
+    if (n_px == 0) return MT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    // stage the small tables in one stream-ordered scratch allocation
+    const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
+                 b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
+                 b_lw = sizeof(uint32_t) * cfg.n_lines;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char *scratch = nullptr;
+    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw), stream));
+    char *q = scratch;
+    RefParams p{};
+    p.cfg = cfg;
+    auto stage = [&](const void *src, size_t bytes) -> const void * {
+        cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, stream);
+        const void *dst = q;
+        q += up(bytes);
+        return dst;
+    };
+    p.lines = static_cast<const MtRefineLine *>(stage(lines_host, b_lines));
+    p.chan_lines = static_cast<const uint32_t *>(stage(chan_lines_host, b_chan));
+    p.comp_start = static_cast<const int32_t *>(stage(comp_start_host, b_cs));
+    p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
+    p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
+    MT_CUDA_TRY(cudaGetLastError());
+    p.g0inv = g0inv_dev;
+    p.bkg = bkg_dev;
+    p.ld_bkg = ld_bkg;
+    p.spec = spec_dev;
+    p.ld_spec = ld_spec;
+    p.x = x_dev;
+    p.ld_x = ld_x;
+    p.theta_out = theta_dev;
+    p.loss_out = loss_dev;
+    p.iters_out = iters_dev;
+    p.n_px = n_px;
+    const size_t smem = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta);
+    if (dtype == MT_DTYPE_F32) {
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        refine_kernel<float><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);
+    } else if (dtype == MT_DTYPE_F16) {
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        refine_kernel<__half><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);
+    } else {
+        cudaFreeAsync(scratch, stream);
+        return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: dtype %d", dtype);
+    }
+    MT_CUDA_TRY(cudaGetLastError());
+    MT_CUDA_TRY(cudaFreeAsync(scratch, stream));
+    return MT_OK;
+}

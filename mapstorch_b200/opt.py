@@ -138,6 +138,7 @@ class MapFitPlan:
         self._host_out = {}
         self._neg = None
         self._last_engine = None
+        self._last_wide = False
         self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
         if self.use_snip:
             p = self.params
@@ -238,8 +239,9 @@ class MapFitPlan:
             neg = self._neg_buffers(n_px)
             neg[1].zero_()
         wide = False
-        if not self.use_snip and engine == "tensor" and spec2d.dtype == torch.float32 and not exact_counts:
-            wide = bool(spec2d[:, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0)
+        if not self.use_snip and engine == "tensor" and spec2d.dtype == torch.float32 and exact_counts is not True:
+            wide = exact_counts == "split" or bool(spec2d[:, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0)
+        self._last_wide = wide
         if wide:
             # exact for any magnitude: stream the volume as a tf32-exact high part plus remainder
             width = 2 * self.n_ch
@@ -316,11 +318,12 @@ def _make_graph(self, spec2d, out, nonneg=True, engine="tensor"):
     repeated fit: two kernel launches per step replayed without host work).  Returns the
     torch.cuda.CUDAGraph; call .replay()."""
     saved, self.timers = self.timers, None
-    self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)  # warm caches (operand packs, attributes)
+    self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)  # warm caches; checks the count range once
+    exact = "split" if self._last_wide else True             # no host sync inside the capture
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)
+        self.fit(spec2d, out=out, nonneg=nonneg, engine=engine, exact_counts=exact)
     self.timers = saved
     return graph
 
@@ -344,14 +347,19 @@ MapFitPlan.to_host = _to_host
 def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_param_vals=default_param_vals,
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
-            device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384):
+            device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384, refine=None,
+            refine_iters=12, refine_bounds=None):
     """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
 
     Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
     init_param_vals=..., fixed_param_vals=..., tune_params=False, use_snip=..., indices=...)`` on each
     pixel and running it to convergence.  Returns ``{name: amplitude map [...]}`` (linear counts, or
     log10 like the reference's tensors if as_log10) on `device`; the two scatter components are
-    always fitted, as in fit_spec (opt.py:194-200)."""
+    always fitted, as in fit_spec (opt.py:194-200).
+
+    refine: optional tuple of calibration parameters (subset of ENERGY_OFFSET, ENERGY_SLOPE, FWHM_OFFSET,
+    FWHM_FANOPRIME) to free PER PIXEL together with the amplitudes, like fit_spec(fitting_params=refine,
+    tune_params=True) per pixel; their maps, the final "loss" and "iterations" are added to the result."""
     _native.require_device()
     if not isinstance(spec_vol, torch.Tensor):
         arr = np.asarray(spec_vol)
@@ -373,11 +381,30 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         x = plan.fit(flat, nonneg=nonneg, engine=engine)
     else:
         x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px)
+    extra = {}
+    if refine:
+        # per-pixel nonlinear refinement of peak-shape parameters + amplitudes (kernel K4)
+        from mapstorch_b200.refine import refine_map
+
+        dev = flat if flat.device.type == "cuda" else flat.cuda()
+        bkg = None
+        if plan.use_snip:
+            p = plan.params
+            bkg = _bkg.snip_bkg(dev[:, plan.er[0]: plan.er[1] + 1], plan.er, *(torch.tensor(float(p[k])) for k in (
+                "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")),
+                device="cuda")
+        theta, loss, iters = refine_map(plan, dev, x, free=tuple(refine), bounds=refine_bounds, max_iter=refine_iters,
+                                        bkg=bkg)
+        extra = {name: theta[i] for i, name in enumerate(refine)}
+        extra["loss"], extra["iterations"] = loss, iters
     if as_log10:
         x = torch.log10(x)
     if torch.device(device).type != "cuda":
         x = plan.to_host(x)
     maps = {name: x[i].reshape(lead) for i, name in enumerate(plan.names)}
+    for name, val in extra.items():
+        val = val if torch.device(device).type == "cuda" else val.cpu()
+        maps[name] = val.reshape(lead)
     return (maps, plan) if return_plan else maps
 
 

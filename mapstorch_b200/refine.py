@@ -1,0 +1,133 @@
+"""Per-pixel nonlinear refinement (kernel K4) and the global-parameter fit of one spectrum.
+
+``refine_map`` frees up to four peak-shape parameters per pixel (ENERGY_OFFSET, ENERGY_SLOPE,
+FWHM_OFFSET, FWHM_FANOPRIME) together with all amplitudes -- the per-pixel version of the
+reference's ``fit_spec(..., fitting_params=[...], tune_params=True)`` (opt.py:165-327) -- starting
+from the linear solve of ``MapFitPlan.fit``.  ``fit_spec_global`` is ``fit_spec`` with
+``tune_params=True`` for one (integrated) spectrum: variable projection over the tunable calibration
+parameters, every model evaluation on the GPU (K1 basis + the non-negative solve).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from mapstorch_b200 import _native, tables
+from mapstorch_b200.default import default_energy_consts, default_elem_info, default_param_vals
+
+f32 = np.float32
+
+DEFAULT_BOUNDS = {
+    "ENERGY_OFFSET": ("abs", 0.03),       # +- keV around the global value
+    "ENERGY_SLOPE": ("rel", 0.01),        # +- 1 %
+    "FWHM_OFFSET": ("rel", 0.30),         # +- 30 %
+    "FWHM_FANOPRIME": ("rel", 0.50),      # +- 50 %
+}
+
+
+def gaussian_lines(params, names, e_consts=default_energy_consts, elem_info=default_elem_info):
+    """(energy, factor, comp, sigma_scale, e296) of every Gaussian term of model_spec's default
+    path (use_step=True with f_step == 0, use_tail=False), amplitudes excluded."""
+    p32 = {k: tables.scalar32(v) for k, v in params.items() if k in default_param_vals}
+    e0 = p32["COHERENT_SCT_ENERGY"]
+    out = []
+    for comp, name in enumerate(names):
+        if name == "COHERENT_SCT_AMPLITUDE":
+            out.append((e0, f32(1.0), comp, f32(1.0), e0 * f32(2.96)))
+        elif name == "COMPTON_AMPLITUDE":
+            if p32["COMPTON_F_STEP"] > 0:
+                raise NotImplementedError("refinement with a Compton step term (COMPTON_F_STEP > 0)")
+            ce = tables.compton_energy(params)
+            out.append((ce, f32(1.0), comp, p32["COMPTON_FWHM_CORR"], ce * f32(2.96)))
+        else:
+            for s in e_consts[name]:
+                if s.ratio == 0 or s.energy <= 0 or not s.check_binding_energy(elem_info, e0):
+                    continue
+                mu, e = f32(s.mu_fraction), f32(s.energy)
+                f_step = np.abs(mu * (p32["F_STEP_OFFSET"] + p32["F_STEP_LINEAR"] * e))
+                if f_step > 0:
+                    raise NotImplementedError("refinement with step terms (F_STEP_* != 0)")
+                out.append((e, f32(s.ratio), comp, f32(1.0), f32(s.energy * 2.96)))
+    return out
+
+
+def refine_tables(params, names, er, free, bounds=None, k_sigma=7.0, **kw):
+    """Host tables of mt_refine for the components `names` over channels er[0]..er[1]."""
+    bounds = dict(DEFAULT_BOUNDS, **(bounds or {}))
+    lines = sorted(gaussian_lines(params, names, **kw), key=lambda t: float(t[0]))
+    n_ch = er[1] - er[0] + 1
+    p32 = {k: float(tables.scalar32(params[k])) for k in default_param_vals}
+    cfg = _native.MtRefineConfig()
+    cfg.n_ch, cfg.ch0, cfg.n_comp, cfg.n_lines, cfg.n_theta = n_ch, er[0], len(names), len(lines), len(free)
+    lo_hi = {}
+    for k, name in enumerate(free):
+        kind, width = bounds[name]
+        v = p32[name]
+        span = width if kind == "abs" else abs(v) * width
+        cfg.theta_id[k] = _native.THETA_IDS[name]
+        cfg.theta0[k], cfg.theta_lo[k], cfg.theta_hi[k] = v, v - span, v + span
+        lo_hi[name] = (v - span, v + span)
+    cfg.energy_offset, cfg.energy_slope, cfg.energy_quad = p32["ENERGY_OFFSET"], p32["ENERGY_SLOPE"], p32["ENERGY_QUADRATIC"]
+    cfg.fwhm_offset, cfg.fwhm_fanoprime = p32["FWHM_OFFSET"], p32["FWHM_FANOPRIME"]
+    # windows: widest sigma and largest energy-axis excursion the bounds allow
+    fo_hi = lo_hi.get("FWHM_OFFSET", (0, p32["FWHM_OFFSET"]))[1]
+    fa_hi = lo_hi.get("FWHM_FANOPRIME", (0, p32["FWHM_FANOPRIME"]))[1]
+    ch = np.arange(er[0], er[1] + 1, dtype=np.float64)
+    ev = p32["ENERGY_OFFSET"] + p32["ENERGY_SLOPE"] * ch + p32["ENERGY_QUADRATIC"] * ch * ch
+    shift = 0.0
+    if "ENERGY_OFFSET" in lo_hi:
+        shift += lo_hi["ENERGY_OFFSET"][1] - p32["ENERGY_OFFSET"]
+    if "ENERGY_SLOPE" in lo_hi:
+        shift += (lo_hi["ENERGY_SLOPE"][1] - p32["ENERGY_SLOPE"]) * ch.max()
+    arr = (_native.MtRefineLine * len(lines))()
+    window = np.zeros(len(lines), dtype=np.uint32)
+    first = np.full(n_ch, len(lines), dtype=np.int64)
+    last = np.zeros(n_ch, dtype=np.int64)
+    for i, (e, fac, comp, scale, e296) in enumerate(lines):
+        arr[i].energy, arr[i].factor, arr[i].comp, arr[i].sigma_scale, arr[i].e296 = float(e), float(fac), comp, float(scale), float(e296)
+        sigma = float(scale) * np.sqrt((fo_hi / 2.3548) ** 2 + float(e296) * fa_hi)
+        reach = k_sigma * sigma + shift
+        inside = np.nonzero(np.abs(ev - float(e)) <= reach)[0]
+        if inside.size:
+            lo_c, hi_c = int(inside[0]), int(inside[-1]) + 1
+            window[i] = lo_c | (hi_c << 16)
+            first[lo_c:hi_c] = np.minimum(first[lo_c:hi_c], i)
+            last[lo_c:hi_c] = np.maximum(last[lo_c:hi_c], i + 1)
+    first = np.minimum(first, last)
+    chan_lines = (first | (last << 16)).astype(np.uint32)
+    order = sorted(range(len(lines)), key=lambda i: lines[i][2])
+    comp_lines = np.array(order, dtype=np.int32)
+    counts = np.bincount([lines[i][2] for i in order], minlength=len(names))
+    comp_start = np.zeros(len(names) + 1, dtype=np.int32)
+    np.cumsum(counts, out=comp_start[1:])
+    return cfg, arr, chan_lines, comp_start, comp_lines, window
+
+
+def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=None, max_iter=12, tol=1e-6,
+               bkg=None, stream=None):
+    """Refine amplitudes x [E, P] (CUDA, from plan.fit) and the `free` parameters per pixel in place.
+
+    Returns (theta [len(free), P], loss [P], iterations [P]) on the device."""
+    if plan.n_live != len(plan.names):
+        raise NotImplementedError("refinement with components that have no open line")
+    free = list(free)
+    unknown = [f for f in free if f not in _native.THETA_IDS]
+    if unknown or len(free) > 4:
+        raise ValueError(f"free parameters must be a subset of {sorted(_native.THETA_IDS)}, got {free}")
+    cfg, lines, chan_lines, comp_start, comp_lines, window = refine_tables(plan.params, plan.names, plan.er, free, bounds)
+    cfg.max_iter, cfg.tol = int(max_iter), float(tol)
+    n_px = spec2d.shape[0]
+    if not hasattr(plan, "_g0inv32"):
+        plan._g0inv32 = torch.from_numpy(plan.hinv.astype(np.float32)).cuda()
+    theta = torch.empty((max(len(free), 1), n_px), dtype=torch.float32, device="cuda")
+    loss = torch.empty(n_px, dtype=torch.float32, device="cuda")
+    iters = torch.empty(n_px, dtype=torch.int32, device="cuda")
+    if bkg is not None and (bkg.dtype != torch.float32 or bkg.stride(1) != 1):
+        bkg = bkg.float().contiguous()
+    _native.call("mt_refine", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, spec2d.stride(0),
+                 bkg.data_ptr() if bkg is not None else None, bkg.stride(0) if bkg is not None else 0,
+                 ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p), chan_lines.ctypes.data_as(ctypes.c_void_p),
+                 comp_start.ctypes.data_as(ctypes.c_void_p), comp_lines.ctypes.data_as(ctypes.c_void_p),
+                 window.ctypes.data_as(ctypes.c_void_p), plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
+                 theta.data_ptr(), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
+    return theta[: len(free)], loss, iters

@@ -415,3 +415,74 @@ def fit_map_composed(spectra, B, snip_args=None, er=None):
     for i in bad:
         x[i] = nnls(B64, y[i].astype(np.float64), maxiter=50 * B.shape[1])[0]
     return x
+
+
+# ---- nonlinear refinement (BASELINE config 4) --------------------------------------------------
+def gaussian_model_jacobian(params, energy_range, elements_to_fit, amps):
+    """Analytic Jacobian of model_spec's default (pure Gaussian) path w.r.t. ENERGY_OFFSET,
+    ENERGY_SLOPE, FWHM_OFFSET, FWHM_FANOPRIME and the linear amplitudes, in float64.
+    Returns (model [C], d_theta [4, C], basis [C, E], names).  Formulas as in csrc/mt_refine.cu."""
+    d = _defaults()
+    names = component_names(elements_to_fit)
+    P = {k: float(p32(params, k)) for k in d.default_param_vals}
+    ch = np.arange(energy_range[0], energy_range[1] + 1, dtype=np.float64)
+    ev = P["ENERGY_OFFSET"] + P["ENERGY_SLOPE"] * ch + P["ENERGY_QUADRATIC"] * ch * ch
+    s0 = P["FWHM_OFFSET"] / 2.3548
+    basis = np.zeros((ch.size, len(names)))
+    d_ev = np.zeros(ch.size)
+    d_fo = np.zeros(ch.size)
+    d_fa = np.zeros(ch.size)
+    e0 = P["COHERENT_SCT_ENERGY"]
+    for j, name in enumerate(names):
+        if name == "COHERENT_SCT_AMPLITUDE":
+            lines = [(e0, 1.0, 1.0, e0 * 2.96)]
+        elif name == "COMPTON_AMPLITUDE":
+            ce = float(compton_energy(params))
+            lines = [(ce, 1.0, P["COMPTON_FWHM_CORR"], ce * 2.96)]
+        else:
+            lines = [(s.energy, s.ratio, 1.0, s.energy * 2.96) for s in d.default_energy_consts[name]
+                     if s.ratio != 0 and s.energy > 0 and s.check_binding_energy(d.default_elem_info, e0)]
+        for energy, fac, scale, e296 in lines:
+            base = np.sqrt(s0 * s0 + e296 * P["FWHM_FANOPRIME"])
+            sigma = base * scale
+            u = (ev - energy) / sigma
+            b = fac * P["ENERGY_SLOPE"] / (sigma * SQRT_2XPI) * np.exp(-0.5 * u * u)
+            basis[:, j] += b
+            v = amps[j] * b
+            d_ev += -v * u / sigma
+            dsg = v * (u * u - 1.0) / sigma
+            d_fo += dsg * scale * s0 / (2.3548 * base)
+            d_fa += dsg * scale * e296 / (2.0 * base)
+    model = basis @ np.asarray(amps, dtype=np.float64)
+    d_theta = np.stack([d_ev, d_ev * ch + model / P["ENERGY_SLOPE"], d_fo, d_fa])
+    return model, d_theta, basis, names
+
+
+def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bkg=None):
+    """Variable projection in float64: minimise over the free calibration parameters the NNLS
+    residual of the spectrum on the Gaussian basis -- the minimiser the reference's
+    fit_spec(fitting_params=free, tune_params=True) heads for.  Returns (theta, amplitudes, loss)."""
+    from scipy.optimize import least_squares, nnls
+
+    y = np.asarray(spectrum, dtype=np.float64)[energy_range[0]: energy_range[1] + 1]
+    if bkg is not None:
+        y = y - np.asarray(bkg, dtype=np.float64)
+    start = np.array([float(p32(params, k)) for k in free])
+    scale = np.where(start != 0, np.abs(start), 1.0)
+    n_comp = len(component_names(elements_to_fit))
+
+    def solve(theta):
+        pp = dict(params, **dict(zip(free, theta)))
+        _, _, B, _ = gaussian_model_jacobian(pp, energy_range, elements_to_fit, np.ones(n_comp))
+        x, _ = nnls(B, y, maxiter=50 * n_comp)
+        return B, x
+
+    def resid(t):
+        B, x = solve(t * scale)
+        return B @ x - y
+
+    sol = least_squares(resid, start / scale, method="trf", diff_step=1e-5, xtol=1e-12, ftol=1e-14, gtol=1e-12,
+                        max_nfev=400)
+    theta = sol.x * scale
+    B, x = solve(theta)
+    return theta, x, float(np.sum((B @ x - y) ** 2))

@@ -245,6 +245,48 @@ def gen_fit(out, quick):
         print(tag, "final loss", trace[-1], flush=True)
 
 
+def gen_refine(out, n_iter=3000):
+    """BASELINE config 4 analogue: per-spectrum fit with ENERGY_OFFSET and FWHM_OFFSET free
+    (fit_spec(fitting_params=[...], tune_params=True), opt.py:201,119), run long enough to converge,
+    plus model-Jacobian entries from torch.autograd for the analytic-Jacobian check."""
+    torch.set_num_threads(8)
+    rng = np.random.default_rng(17)
+    p = params_a()
+    truth = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + 0.004, FWHM_OFFSET=p["FWHM_OFFSET"] * 1.05)
+    spec, amps = synth_spectrum(truth, (0, 2047), ELEMS20, rng, 2.0, 3.2, flat=0.0)
+    names = list(ELEMS20) + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+    tensors, spec_fit, bkg, trace = ropt.fit_spec(
+        spec, (0, 2047), elements_to_fit=list(ELEMS20), fitting_params=["ENERGY_OFFSET", "FWHM_OFFSET"],
+        init_param_vals=p, tune_params=True, init_amp=True, use_snip=False, loss="mse", optimizer="adam",
+        n_iter=n_iter, progress_bar=False)
+    out["r_spec"] = spec
+    out["r_names"] = np.array(names)
+    out["r_param_names"] = np.array(list(p.keys()))
+    out["r_param_vals"] = np.array([p[k] for k in p], dtype=np.float64)
+    out["r_truth_offset_width"] = np.array([truth["ENERGY_OFFSET"], truth["FWHM_OFFSET"]])
+    out["r_fit_offset_width"] = np.array([tensors["ENERGY_OFFSET"].item(), tensors["FWHM_OFFSET"].item()])
+    out["r_logamps"] = np.array([tensors[n].item() for n in names], dtype=np.float64)
+    out["r_truth_logamps"] = np.array([amps[n] for n in names], dtype=np.float64)
+    out["r_spec_fit"] = spec_fit
+    out["r_trace"] = np.array(trace, dtype=np.float64)
+    print("refine final loss", trace[-1], "offset/width", out["r_fit_offset_width"], flush=True)
+    # Jacobian entries of model_spec (SURVEY appendix C.4): all log10 A = 3, defaults with E0 = 12
+    t = tens(p, {n: 3.0 for n in names})
+    for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "FWHM_FANOPRIME", "Fe", "Zn", "COMPTON_AMPLITUDE"):
+        t[k].requires_grad_(True)
+    m = rmap.model_spec(t, (0, 2047), list(ELEMS20))
+    chans = [100, 300, 534, 535, 600, 720, 900, 1000, 1003]
+    jac = []
+    for c in chans:
+        grads = torch.autograd.grad(m[c], [t[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET",
+                                                          "FWHM_FANOPRIME", "Fe", "Zn", "COMPTON_AMPLITUDE")],
+                                    retain_graph=True, allow_unused=True)
+        jac.append([0.0 if g is None else g.item() for g in grads])
+    out["j_channels"] = np.array(chans)
+    out["j_values"] = np.array(jac)
+    out["j_model"] = m.detach().numpy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-fit", action="store_true")
@@ -259,6 +301,12 @@ def main():
         fn(out)
         np.savez_compressed(HERE / f"{name}_golden.npz", **out)
         print("wrote", name, (HERE / f"{name}_golden.npz").stat().st_size, flush=True)
+    if args.only == "refine":
+        out = {}
+        gen_refine(out)
+        np.savez_compressed(HERE / "refine_golden.npz", **out)
+        print("wrote refine", (HERE / "refine_golden.npz").stat().st_size, flush=True)
+        return
     if not args.skip_fit and args.only in ("", "fit"):
         out = {}
         gen_fit(out, args.quick_fit)

@@ -1,0 +1,101 @@
+"""K4 (mt_refine): per-pixel nonlinear refinement against the float64 variable-projection oracle and
+the reference's converged fit_spec(fitting_params=[ENERGY_OFFSET, FWHM_OFFSET], tune_params=True)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+ELEMS20 = "Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As".split()
+
+
+def load_ref():
+    g = np.load(GOLDEN / "refine_golden.npz")
+    p = dict(zip([str(k) for k in g["r_param_names"]], [float(v) for v in g["r_param_vals"]]))
+    return g, p, [str(n) for n in g["r_names"]]
+
+
+def test_refinement_reaches_the_reference_minimum():
+    from mapstorch_b200 import opt
+
+    g, p, names = load_ref()
+    maps = opt.fit_map(g["r_spec"].reshape(1, -1), (0, 2047), names[:-2], init_param_vals=p, use_snip=False,
+                       refine=("ENERGY_OFFSET", "FWHM_OFFSET"), refine_iters=20, device="cpu")
+    ref_theta = g["r_fit_offset_width"]
+    assert abs(float(maps["ENERGY_OFFSET"]) - ref_theta[0]) < 5e-6
+    assert abs(float(maps["FWHM_OFFSET"]) / ref_theta[1] - 1) < 5e-5
+    # objective: not worse than the reference's final loss (SURVEY appendix C.4 ii)
+    assert float(maps["loss"]) <= g["r_trace"][-1] * (1 + 2e-5)
+    ref_amp = dict(zip(names, 10.0 ** g["r_logamps"]))
+    big = max(ref_amp.values())
+    for n in names:
+        if ref_amp[n] > 1e-3 * big:
+            assert abs(float(maps[n]) / ref_amp[n] - 1) < 1e-4, n
+
+
+def test_refinement_matches_variable_projection_oracle_on_perturbed_pixels():
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(4)
+    n_px = 6
+    names = mo.component_names(ELEMS20)
+    specs, truths = [], []
+    for i in range(n_px):
+        shift, widen = rng.uniform(-0.006, 0.006), rng.uniform(0.93, 1.08)
+        pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + shift, FWHM_OFFSET=p["FWHM_OFFSET"] * widen)
+        amps = 10.0 ** rng.uniform(2.0, 3.2, size=len(names))
+        model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+        specs.append(rng.poisson(model).astype(np.float32))
+        truths.append((pp["ENERGY_OFFSET"], pp["FWHM_OFFSET"]))
+    y = np.stack(specs)
+    maps = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, refine=("ENERGY_OFFSET", "FWHM_OFFSET"),
+                       refine_iters=20, device="cpu")
+    again = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, refine=("ENERGY_OFFSET", "FWHM_OFFSET"),
+                        refine_iters=20, device="cpu")
+    for k in maps:
+        assert torch.equal(maps[k], again[k]), k  # deterministic reductions
+    for i in range(n_px):
+        theta, x, loss = mo.refine_spectrum(y[i], p, er, ELEMS20)
+        assert abs(float(maps["ENERGY_OFFSET"][i]) - theta[0]) < 1e-5, i
+        assert abs(float(maps["FWHM_OFFSET"][i]) / theta[1] - 1) < 1e-4, i
+        assert float(maps["loss"][i]) <= loss * (1 + 2e-5), i
+        mine = np.array([float(maps[n][i]) for n in names])
+        interior = x > 1e-3 * x.max()
+        assert (np.abs(mine - x)[interior] / x[interior]).max() < 2e-4, i
+        assert int(maps["iterations"][i]) <= 20
+        # and the refinement matters: the linear fit at the global parameters is visibly worse
+    lin = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, device="cpu")
+    lin_x = np.stack([lin[n].numpy() for n in names], axis=1)
+    _, _, B, _ = mo.gaussian_model_jacobian(p, er, ELEMS20, np.ones(len(names)))
+    lin_loss = ((y - lin_x @ B.T) ** 2).sum(axis=1)
+    assert np.all(maps["loss"].numpy() < lin_loss)
+
+
+def test_refinement_with_four_free_parameters_and_background():
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(8)
+    names = mo.component_names(ELEMS20)
+    pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + 0.003, ENERGY_SLOPE=p["ENERGY_SLOPE"] * 1.0004,
+              FWHM_OFFSET=p["FWHM_OFFSET"] * 1.04, FWHM_FANOPRIME=p["FWHM_FANOPRIME"] * 1.1)
+    amps = 10.0 ** rng.uniform(2.5, 3.5, size=len(names))
+    model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+    y = rng.poisson(model + 2.0).astype(np.float32).reshape(1, -1).repeat(3, axis=0)
+    free = ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "FWHM_FANOPRIME")
+    maps = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=True, refine=free, refine_iters=30, device="cpu")
+    pr = [p[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")]
+    bkg = mo.snip_bkg(y[0], er, *pr)
+    theta, x, loss = mo.refine_spectrum(y[0], p, er, ELEMS20, free=free, bkg=bkg)
+    assert float(maps["loss"][0]) <= loss * (1 + 1e-4)
+    assert abs(float(maps["ENERGY_SLOPE"][0]) / theta[1] - 1) < 2e-5
+    assert abs(float(maps["FWHM_OFFSET"][0]) / theta[2] - 1) < 5e-3
+    assert torch.equal(maps["Fe"][0], maps["Fe"][2])
