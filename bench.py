@@ -36,6 +36,11 @@ WORKLOADS = {
     "c3": dict(rows=128, width=1024, n_ch=4096, dtype="f32", elems="ELEMS30", snip=True, flat=3.0,
                desc="BASELINE config 3 row shard: 128x1024x4096 fp32 per GPU (8 GPUs = the 1024x1024x4096 map), "
                     "30 elements + 2 scatter peaks, SNIP background"),
+    # BASELINE config 4: 512x512x2048 fp32, 20 elements, per-pixel refinement of peak offset / width
+    "c4": dict(rows=512, width=512, n_ch=2048, dtype="f32", elems="ELEMS20", snip=False, flat=0.0,
+               refine=("ENERGY_OFFSET", "FWHM_OFFSET"), refine_iters=12,
+               desc="BASELINE config 4: 512x512x2048 fp32, 20 elements + 2 scatter peaks, per-pixel Gauss-Newton "
+                    "refinement of ENERGY_OFFSET and FWHM_OFFSET + amplitudes (<= 12 iterations)"),
 }
 
 
@@ -110,7 +115,19 @@ def build_workload(name, rank, world, device):
     truth = synth.truth_maps(len(plan.names), w["rows"], w["width"], seed=1234, row0=rank * w["rows"],
                              total_rows=world * w["rows"], device=device)
     dtype = torch.float16 if w["dtype"] == "f16" else torch.float32
-    vol = synth.poisson_volume(plan.basis, truth, dtype=dtype, flat=w["flat"], seed=99 + rank)
+    if w.get("refine"):
+        # row bands with their own energy offset / peak width, so that the refinement has work to do
+        vol = torch.empty((w["rows"], w["width"], w["n_ch"]), dtype=dtype, device=device)
+        bands = 8
+        rows = w["rows"] // bands
+        for b in range(bands):
+            pb = dict(params, ENERGY_OFFSET=params["ENERGY_OFFSET"] + 0.004 * (b - 3.5) / 3.5,
+                      FWHM_OFFSET=params["FWHM_OFFSET"] * (1 + 0.05 * (b - 3.5) / 3.5))
+            band_plan = opt.MapFitPlan(er, elems, pb, use_snip=False)
+            synth.poisson_volume(band_plan.basis, truth[:, b * rows:(b + 1) * rows], dtype=dtype, flat=w["flat"],
+                                 seed=99 + rank * bands + b, out=vol[b * rows:(b + 1) * rows].reshape(-1, w["n_ch"]))
+    else:
+        vol = synth.poisson_volume(plan.basis, truth, dtype=dtype, flat=w["flat"], seed=99 + rank)
     return w, elems, params, er, plan, truth, vol
 
 
@@ -218,11 +235,16 @@ def main():
         except Exception as exc:  # pragma: no cover - depends on the driver
             print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
 
+    refine_state = {}
+
     def step(gather=True, eager=False):
         if graph is not None and not eager:
             graph.replay()
         else:
             plan.fit(flat, out=out)
+        if w.get("refine"):
+            from mapstorch_b200.refine import refine_map
+            refine_state["out"] = refine_map(plan, flat, out, free=w["refine"], max_iter=w["refine_iters"])
         if world > 1 and gather:
             return gather_maps(out, total_rows, w["width"])
         return out
@@ -311,7 +333,7 @@ def main():
 
         def e2e_step():
             maps = opt.fit_map(host.reshape(vol.shape), er, elems, init_param_vals=params, use_snip=w["snip"],
-                               device="cpu")
+                               device="cpu", refine=w.get("refine"), refine_iters=w.get("refine_iters", 12))
             return maps
 
         e2e_step()
@@ -339,6 +361,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graph is not None,
                 "ms_per_step_eager_launch": ms_eager / args.steps, "roofline": roofline, "cpu_baseline": cb,
                 "fit_only_px_s": world * n_px / (ms_fit_only / args.steps * 1e-3),
+                "refine": ({"free": list(w["refine"]), "mean_iterations": float(refine_state["out"][2].float().mean()),
+                            "mean_loss": float(refine_state["out"][1].mean())} if w.get("refine") else None),
                 "check_vs_float64_lstsq": check}
         print(json.dumps(line), flush=True)
     if world > 1:
