@@ -271,7 +271,7 @@ def main():
         step()
     # accuracy of what is being timed: amplitudes against the ground truth (Poisson-limited) and
     # against a float64 solve of a pixel sample
-    got = step(gather=False)
+    got = plan.fit(flat, out=out).clone()
     sample = torch.arange(0, n_px, max(1, n_px // 512), device=device)[:512]
     y64 = flat[sample].double()
     if w["snip"]:
