@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner must not land on stdout next to the JSON line
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -57,6 +57,19 @@ typedef struct MtTerm {
     float amp;     /* faktor of the term (ratio * 10**logA / normalisation [* f_step | f_tail]) */
 } MtTerm;
 
+/* Extra destinations of the element maps on OTHER GPUs of the box (NVLink peer memory): every value
+ * the kernels store to x_dev[i] is also stored to peer[k][i] for k < n_peers and, if multicast is
+ * non-NULL, to multicast[i] (an NVSwitch multicast mapping: one store lands on every GPU).  The
+ * pointers address buffers with the same layout as x_dev (torch symmetric memory).  This fuses the
+ * all-gather of the maps into the epilogue of the fit. */
+#define MT_MAX_PEERS 8
+typedef struct MtPeers {
+    int32_t n_peers;
+    int32_t reserved;
+    float *peer[MT_MAX_PEERS];
+    float *multicast;
+} MtPeers;
+
 int mt_abi_version(void);
 const char *mt_last_error(void);
 
@@ -113,7 +126,8 @@ int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t l
                     int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                     int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                     const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
-                    int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev, void *stream);
+                    int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
+                    const MtPeers *peers_host /* optional */, void *stream);
 
 /* Same contract on CUDA cores (no tensor cores, fp32 weights [n_comp][ld_w]); exists for
  * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */
@@ -128,12 +142,14 @@ int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int6
  * already non-negative are untouched.  n_fixed_dev (optional, may be NULL): int32 counter,
  * incremented once per pixel that needed the fix-up. */
 int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
-                  const double *hinv_dev, int32_t *n_fixed_dev, void *stream);
+                  const double *hinv_dev, int32_t *n_fixed_dev, const MtPeers *peers_host /* optional */,
+                  void *stream);
 
 /* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
  * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]). */
 int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
-                 int32_t n_comp, const double *g_dev, const double *hinv_dev, void *stream);
+                 int32_t n_comp, const double *g_dev, const double *hinv_dev,
+                 const MtPeers *peers_host /* optional */, void *stream);
 
 /* ---- K4: batched per-pixel nonlinear refinement (BASELINE config 4) ----------------------------
  * Replaces fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:165-327) applied per pixel:

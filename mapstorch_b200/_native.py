@@ -44,6 +44,11 @@ class MtRefineConfig(ctypes.Structure):
                 ("tol", ctypes.c_float)]
 
 
+class MtPeers(ctypes.Structure):
+    _fields_ = [("n_peers", ctypes.c_int32), ("reserved", ctypes.c_int32), ("peer", ctypes.c_void_p * 8),
+                ("multicast", ctypes.c_void_p)]
+
+
 THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3}
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
@@ -56,10 +61,10 @@ SIGNATURES = {
     "mt_model_sum": [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp],
     "mt_snip": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
     "mt_fit_contract": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp,
-                        _i64, _i64, _vp, _vp, _vp],
-    "mt_nnls_list": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp],
+                        _i64, _i64, _vp, _vp, _vp, _vp],
+    "mt_nnls_list": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp],
-    "mt_nnls_fixup": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp],
+    "mt_nnls_fixup": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
 }
 

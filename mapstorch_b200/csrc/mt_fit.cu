@@ -44,6 +44,7 @@ struct FitParams {
     long long px_offset;  // added to local pixel numbers written to neg_list
     int *neg_list;        // optional: pixels whose solution has a negative component
     int *neg_count;
+    MtPeers peers;        // extra destinations on other GPUs (n_peers == 0 and multicast == NULL: none)
     float *x;
     const float *colscale;
     int n_tiles;
@@ -212,7 +213,14 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                             if (e < p.n_comp) {
                                 const float v = cs[e] * acc[j];
                                 negative |= (v < 0.f);
-                                p.x[(long long)e * p.ld_x + px] = v;
+                                const long long at = (long long)e * p.ld_x + px;
+                                p.x[at] = v;
+                                // fused gather of the maps: same value to the peers' buffers over NVLink
+                                for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = v;
+                                if (p.peers.multicast)
+                                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
+                                                 "f"(v)
+                                                 : "memory");
                             }
                         }
                     }
@@ -354,7 +362,8 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                                int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                                int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                                const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
-                               int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev, void *stream_) {
+                               int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
+                               const MtPeers *peers_host, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
     MT_REQUIRE(dtype == MT_DTYPE_F32 || dtype == MT_DTYPE_F16, "mt_fit_contract: dtype %d", dtype);
@@ -388,6 +397,11 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.px_offset = px_offset;
     p.neg_list = neg_list_dev;
     p.neg_count = neg_count_dev;
+    if (peers_host) {
+        MT_REQUIRE(peers_host->n_peers >= 0 && peers_host->n_peers <= MT_MAX_PEERS, "mt_fit_contract: n_peers=%d",
+                   peers_host->n_peers);
+        p.peers = *peers_host;
+    }
     p.x = x_dev;
     p.colscale = colscale_dev;
     p.bke = kRowBytes / es;

@@ -63,3 +63,44 @@ def allreduce_spectrum(int_spec_local, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(int_spec_local, group=group)
     return int_spec_local
+
+
+class PeerMaps:
+    """Element maps of the WHOLE grid on every GPU, filled by the fit kernels themselves.
+
+    The buffer [E, n_rows * width] lives in torch symmetric memory, so every rank holds pointers to
+    every other rank's copy (and, on NVSwitch systems, one multicast address that reaches all of
+    them).  ``plan.fit(shard, out=maps.local, peers=maps.peers)`` makes the K3 epilogue and the
+    non-negative fix-up store each amplitude into all copies while the contraction is still
+    streaming -- the all-gather of SURVEY.md 8e without a separate collective; ``barrier()`` then
+    orders the remote stores before anybody reads ``maps.full``."""
+
+    def __init__(self, n_comp, n_rows, width, group=None, multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from mapstorch_b200 import _native
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.full = symm_mem.empty((n_comp, n_rows * width), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.full.zero_()
+        self.handle = symm_mem.rendezvous(self.full, group)
+        r0, r1 = shard_rows(n_rows, self.rank, self.world)
+        self.local = self.full[:, r0 * width: r1 * width]
+        offset = 4 * r0 * width
+        self.peers = _native.MtPeers()
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
+        self.multicast = bool(mc)
+        if mc:
+            self.peers.n_peers = 0
+            self.peers.multicast = mc + offset
+        else:
+            others = [int(ptr) for r, ptr in enumerate(self.handle.buffer_ptrs) if r != self.rank]
+            self.peers.n_peers = len(others)
+            for k, ptr in enumerate(others):
+                self.peers.peer[k] = ptr + offset
+            self.peers.multicast = None
+
+    def barrier(self):
+        """All ranks' stores issued so far on the current stream are visible everywhere afterwards."""
+        self.handle.barrier()

@@ -11,6 +11,8 @@ reference's per-spectrum Adam loop is replaced by
 
 which is what the reference's fit converges to.  No CPU compute path exists.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -91,6 +93,18 @@ def digit_planes(w64, n_planes=N_PLANES, bits=DIGIT_BITS):
         planes.append(digit)
         rest = (rest - digit) * (2.0 ** bits)
     return scale.astype(np.float32), np.stack(planes)
+
+
+def _shift_peers(peers, n_px):
+    """The same peer destinations, advanced by n_px pixels (fp32 elements)."""
+    if peers is None or n_px == 0:
+        return peers
+    moved = _native.MtPeers()
+    moved.n_peers = peers.n_peers
+    for k in range(peers.n_peers):
+        moved.peer[k] = peers.peer[k] + 4 * n_px
+    moved.multicast = peers.multicast + 4 * n_px if peers.multicast else None
+    return moved
 
 
 class MapFitPlan:
@@ -178,19 +192,20 @@ class MapFitPlan:
         return self._neg
 
     # -- the fit -----------------------------------------------------------------------------------
-    def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0):
+    def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0, peers=None):
         """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
         if self.timers is not None:
             s = stream if stream is not None else torch.cuda.current_stream()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record(s)
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset)
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset, peers)
             t1.record(s)
             self.timers.append((t0, t1, spec2d.shape[0]))
         else:
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset)
+            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset, peers)
 
-    def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0):
+    def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0,
+                          peers=None):
         n_px, n_ch_total, ld = spec2d.shape[0], spec2d.shape[1], spec2d.stride(0)
         es = spec2d.element_size()
         tma_ok = (ld * es) % 16 == 0 and spec2d.data_ptr() % 16 == 0
@@ -204,8 +219,11 @@ class MapFitPlan:
                          n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
                          self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), x.data_ptr(), x.stride(0),
                          int(px_offset), neg[0].data_ptr() if neg is not None else None,
-                         neg[1].data_ptr() if neg is not None else None, _native.stream_ptr(stream))
+                         neg[1].data_ptr() if neg is not None else None,
+                         ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
         elif engine == "simt":
+            if peers is not None:
+                raise _native.NativeError(-3, "peer-memory destinations need the tensor-core path")
             if repeat != 1:
                 raise _native.NativeError(-3, "the CUDA-core contraction expects an unsplit residual")
             w = self._pinv_f32(n_ch_total, col0)
@@ -215,7 +233,8 @@ class MapFitPlan:
         else:
             raise ValueError(f"unknown engine {engine!r}")
 
-    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None):
+    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None,
+            peers=None):
         """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
         rows in `self.names` order (components without an open line stay 0).
 
@@ -223,7 +242,11 @@ class MapFitPlan:
         counts below 2048 exactly.  fp16 volumes satisfy that by construction and the SNIP path
         splits its residual exactly; for fp32 volumes without SNIP, None (default) checks the
         maximum on the device (one extra read of the volume and a host sync) and routes volumes
-        with larger values through an exact hi/lo split; True skips the check."""
+        with larger values through an exact hi/lo split; True skips the check.
+
+        peers: optional _native.MtPeers whose pointers address, on the other GPUs of the box, the
+        element of their map buffers that corresponds to out[0, 0]; the kernels then store every
+        amplitude there as well (dist.PeerMaps) -- the all-gather of the maps fused into the fit."""
         if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
             raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
         if spec2d.shape[1] <= self.er[1]:
@@ -232,6 +255,8 @@ class MapFitPlan:
         if out is None:
             out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
         dense = self.n_live == n_all
+        if peers is not None and not dense:
+            raise NotImplementedError("peer-memory destinations with components that have no open line")
         x = out if dense else torch.empty((self.n_live, n_px), dtype=torch.float32, device="cuda")
         # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
         neg = None
@@ -254,9 +279,10 @@ class MapFitPlan:
                 hi = (y.view(torch.int32) & -8192).view(torch.float32)
                 scratch[:n, : self.n_ch] = hi
                 scratch[:n, self.n_ch:] = y - hi
-                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2, 0, width, engine, stream, neg, p0)
+                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2, 0, width, engine, stream, neg, p0,
+                               _shift_peers(peers, p0))
         elif not self.use_snip:
-            self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg)
+            self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg, 0, peers)
         else:
             lohi, n_pass = self._snip
             hilo = engine == "tensor"
@@ -269,18 +295,19 @@ class MapFitPlan:
                 n = min(chunk, n_px - p0)
                 _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass, self.boxcar_size,
                                  scratch[:n], mode, stream)
-                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0)
+                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
+                               _shift_peers(peers, p0))
         if nonneg and n_px:
             if self._last_engine == "tensor" and neg is not None:
                 _native.call("mt_nnls_list", x.data_ptr(), x.stride(0), neg[0].data_ptr(), neg[1].data_ptr(),
                              self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
-                             _native.stream_ptr(stream))
+                             ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
                 if n_fixed is not None:
                     n_fixed.copy_(neg[1])
             else:
                 _native.call("mt_nnls_fixup", x.data_ptr(), x.stride(0), n_px, self.n_live, self.gram_dev.data_ptr(),
                              self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
-                             _native.stream_ptr(stream))
+                             ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
         if not dense:
             out[torch.as_tensor(self.live, device="cuda")] = x
         return out
