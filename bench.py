@@ -168,7 +168,7 @@ def cpu_baseline(w, params, er, elems, budget_s=12.0, threads=None):
             "reference_adam_500it_px_s": adam}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     from mapstorch_b200 import synth
@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
             "config": {"workload": w["desc"], "name": args.workload},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -205,11 +205,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="gather the maps with NCCL instead of peer-memory stores")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner must not land on stdout next to the JSON line
+    # libraries (NCCL's version banner) write to fd 1; keep stdout for the ONE JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -229,8 +236,15 @@ def main():
     out = torch.zeros((n_comp, n_px), dtype=torch.float32, device=device)
     total_rows = world * w["rows"]
 
+    peer_maps = None
+    if world > 1 and not w["snip"] and not args.nccl_gather:
+        try:
+            from mapstorch_b200.dist import PeerMaps
+            peer_maps = PeerMaps(n_comp, total_rows, w["width"])
+        except Exception as exc:  # pragma: no cover - needs symmetric memory support
+            print(f"bench: peer-memory maps unavailable ({exc}); gathering with NCCL", file=sys.stderr)
     graph = None
-    if not args.no_graph:
+    if not args.no_graph and world == 1:
         try:
             graph = plan.make_graph(flat, out)
         except Exception as exc:  # pragma: no cover - depends on the driver
@@ -239,6 +253,11 @@ def main():
     refine_state = {}
 
     def step(gather=True, eager=False):
+        if peer_maps is not None and gather:
+            # fused: the fit kernels store the amplitudes into every GPU's map buffer (NVLink multicast)
+            plan.fit(flat, out=peer_maps.local, peers=peer_maps.peers)
+            peer_maps.barrier()
+            return peer_maps.full
         if graph is not None and not eager:
             graph.replay()
         else:
@@ -358,14 +377,16 @@ def main():
                            "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
                            "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
                            "step": "fit of the resident shard (contraction + non-negative fix-up)" +
-                                   (" + all-gather of the element maps" if world > 1 else "")},
+                                   ("" if world == 1 else " + element maps stored into every GPU's buffer by the fit kernels "
+                                    f"(NVLink {'multicast' if peer_maps.multicast else 'peer'} stores) + barrier" if peer_maps is not None
+                                    else " + NCCL all-gather of the element maps")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graph is not None,
                 "ms_per_step_eager_launch": ms_eager / args.steps, "roofline": roofline, "cpu_baseline": cb,
                 "fit_only_px_s": world * n_px / (ms_fit_only / args.steps * 1e-3),
                 "refine": ({"free": list(w["refine"]), "mean_iterations": float(refine_state["out"][2].float().mean()),
                             "mean_loss": float(refine_state["out"][1].mean())} if w.get("refine") else None),
                 "check_vs_float64_lstsq": check}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

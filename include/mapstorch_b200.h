@@ -32,6 +32,11 @@ extern "C" {
 #define MT_ERR_UNSUPPORTED (-3) /* shape or dtype outside what the kernels cover */
 #define MT_ERR_NO_DEVICE (-4)   /* current device is not sm_100 */
 
+/* layout of the amplitude array x */
+#define MT_X_ELEMENT_MAJOR 0 /* x[e * ld_x + p]: one contiguous map per component */
+#define MT_X_PIXEL_MAJOR 1   /* x[p * ld_x + e]: one contiguous 16-byte aligned record per pixel; ld_x % 4 == 0,
+                                ld_x >= e_pad (columns >= n_comp are written as zeros) */
+
 /* storage type of a spectral volume */
 #define MT_DTYPE_F32 0
 #define MT_DTYPE_F16 1
@@ -118,14 +123,14 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
  *            values); columns outside the fitted channel range hold zeros.  e_pad multiple of 8,
  *            n_planes*e_pad a multiple of 16 and <= 256.
  * k_begin,k_end: channel window (elements) the kernel streams; rounded outwards to 128-byte blocks.
- * x_dev    : fp32, element-major: x_dev[e*ld_x + p] for e < n_comp, p < n_px.
+ * x_dev    : fp32 amplitudes in `x_layout` (MT_X_*), e < n_comp, p < n_px.
  * neg_list_dev / neg_count_dev (optional, both or neither): the epilogue appends px_offset + p of
  *            every pixel whose solution has a negative component to neg_list_dev (capacity >= n_px)
  *            and bumps *neg_count_dev (caller zeroes it); consumed by mt_nnls_list. */
 int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                     int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                     int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
-                    const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
+                    const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x, int32_t x_layout,
                     int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
                     const MtPeers *peers_host /* optional */, void *stream);
 
@@ -133,7 +138,7 @@ int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t l
  * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */
 int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                          int32_t k_begin, int32_t k_end, const float *w_dev, int64_t ld_w,
-                         int32_t n_comp, float *x_dev, int64_t ld_x, void *stream);
+                         int32_t n_comp, float *x_dev, int64_t ld_x, int32_t x_layout, void *stream);
 
 /* Batched per-pixel non-negative fix-up of the least-squares amplitudes: minimise
  * (x-xu)^T G (x-xu) s.t. x >= 0 with G = B^T B shared by all pixels (the converged answer of
@@ -141,13 +146,13 @@ int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int6
  * fp64 [n_comp][n_comp] row-major, n_comp <= 104.  Pixels whose unconstrained solution is
  * already non-negative are untouched.  n_fixed_dev (optional, may be NULL): int32 counter,
  * incremented once per pixel that needed the fix-up. */
-int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
+int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64_t n_px, int32_t n_comp, const double *g_dev,
                   const double *hinv_dev, int32_t *n_fixed_dev, const MtPeers *peers_host /* optional */,
                   void *stream);
 
 /* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
  * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]). */
-int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
+int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *list_dev, const int32_t *count_dev,
                  int32_t n_comp, const double *g_dev, const double *hinv_dev,
                  const MtPeers *peers_host /* optional */, void *stream);
 

@@ -11,6 +11,7 @@ MT_OK = 0
 MT_DTYPE_F32, MT_DTYPE_F16 = 0, 1
 MT_TERM_GAUSS, MT_TERM_STEP, MT_TERM_TAIL = 0, 1, 2
 MT_SNIP_BACKGROUND, MT_SNIP_RESIDUAL, MT_SNIP_RESIDUAL_HILO = 0, 1, 2
+MT_X_ELEMENT_MAJOR, MT_X_PIXEL_MAJOR = 0, 1
 
 _LIB_NAME = "libmapstorch_b200.so"
 _lib = None
@@ -61,10 +62,10 @@ SIGNATURES = {
     "mt_model_sum": [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp],
     "mt_snip": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
     "mt_fit_contract": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp,
-                        _i64, _i64, _vp, _vp, _vp, _vp],
-    "mt_nnls_list": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
-    "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp],
-    "mt_nnls_fixup": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+                        _i64, _i32, _i64, _vp, _vp, _vp, _vp],
+    "mt_nnls_list": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+    "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp],
+    "mt_nnls_fixup": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
 }
 

@@ -23,6 +23,7 @@
 // maximum instead -- measured, see DESIGN.md.
 // Bound: HBM (C*sizeof(in) + E*4 bytes per pixel); tensor-pipe use stays well below peak.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "mt_common.cuh"
@@ -44,6 +45,7 @@ struct FitParams {
     long long px_offset;  // added to local pixel numbers written to neg_list
     int *neg_list;        // optional: pixels whose solution has a negative component
     int *neg_count;
+    int pixel_major;      // x layout: 0 = x[e*ld_x + p], 1 = x[p*ld_x + e]
     MtPeers peers;        // extra destinations on other GPUs (n_peers == 0 and multicast == NULL: none)
     float *x;
     const float *colscale;
@@ -207,20 +209,46 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                         for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], p.plane_ratio, part[j]);
                     }
                     if (px < p.n_px) {
+                        float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int e = c0 + j;
-                            if (e < p.n_comp) {
-                                const float v = cs[e] * acc[j];
-                                negative |= (v < 0.f);
-                                const long long at = (long long)e * p.ld_x + px;
-                                p.x[at] = v;
-                                // fused gather of the maps: same value to the peers' buffers over NVLink
-                                for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = v;
-                                if (p.peers.multicast)
-                                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
-                                                 "f"(v)
-                                                 : "memory");
+                            v[j] = cs[c0 + j] * acc[j];  // cs is 0 for padding columns
+                            negative |= (v[j] < 0.f);
+                        }
+                        if (p.pixel_major) {
+                            // one record per pixel: two 128-bit stores per 8 components, also to the peers
+                            const long long at = px * p.ld_x + c0;
+                            const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+                            *reinterpret_cast<float4 *>(p.x + at) = a;
+                            *reinterpret_cast<float4 *>(p.x + at + 4) = b;
+                            for (int k = 0; k < p.peers.n_peers; ++k) {
+                                *reinterpret_cast<float4 *>(p.peers.peer[k] + at) = a;
+                                *reinterpret_cast<float4 *>(p.peers.peer[k] + at + 4) = b;
+                            }
+                            if (p.peers.multicast) {
+                                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                                 p.peers.multicast + at),
+                                             "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                                             : "memory");
+                                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                                 p.peers.multicast + at + 4),
+                                             "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                                             : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int e = c0 + j;
+                                if (e < p.n_comp) {
+                                    const long long at = (long long)e * p.ld_x + px;
+                                    p.x[at] = v[j];
+                                    // fused gather of the maps: same value to the peers' buffers over NVLink
+                                    for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = v[j];
+                                    if (p.peers.multicast)
+                                        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
+                                                     "f"(v[j])
+                                                     : "memory");
+                                }
                             }
                         }
                     }
@@ -269,7 +297,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fit_contract_simt_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int k_begin, int k_end,
                          const float *__restrict__ w, long long ld_w, int n_comp, float *__restrict__ x,
-                         long long ld_x) {
+                         long long ld_x, int pixel_major) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long px0 = warp_global * kSimtPx;
@@ -299,7 +327,8 @@ fit_contract_simt_kernel(const T *__restrict__ spec, long long n_px, long long l
                 float v = acc[i][j];
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-                if (lane == 0 && px0 + i < n_px && e0 + j < n_comp) x[(long long)(e0 + j) * ld_x + px0 + i] = v;
+                if (lane == 0 && px0 + i < n_px && e0 + j < n_comp)
+                    x[pixel_major ? (px0 + i) * ld_x + (e0 + j) : (long long)(e0 + j) * ld_x + px0 + i] = v;
             }
     }
 }
@@ -362,7 +391,7 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                                int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                                int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                                const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
-                               int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
+                               int32_t x_layout, int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
                                const MtPeers *peers_host, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
@@ -379,7 +408,11 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                    n_planes * e_pad <= 256,
                "mt_fit_contract: e_pad=%d n_comp=%d n_planes=%d (need n_planes*e_pad a multiple of 16, <= 256)",
                e_pad, n_comp, n_planes);
-    MT_REQUIRE(ld_x >= n_px, "mt_fit_contract: ld_x=%lld < n_px", (long long)ld_x);
+    if (x_layout == MT_X_PIXEL_MAJOR)
+        MT_REQUIRE(ld_x >= e_pad && ld_x % 4 == 0 && ((uintptr_t)x_dev & 15) == 0,
+                   "mt_fit_contract: pixel-major x needs ld_x >= e_pad, ld_x %% 4 == 0 and a 16-byte aligned base");
+    else
+        MT_REQUIRE(x_layout == MT_X_ELEMENT_MAJOR && ld_x >= n_px, "mt_fit_contract: ld_x=%lld < n_px", (long long)ld_x);
     if ((ld_spec * es) % 16 || (ld_w * es) % 16 || ((uintptr_t)spec_dev & 15) || ((uintptr_t)wpack_dev & 15))
         return mt::fail(MT_ERR_UNSUPPORTED,
                         "mt_fit_contract: TMA needs 16-byte aligned base pointers and row pitches "
@@ -395,6 +428,7 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.n_px = n_px;
     p.ld_x = ld_x;
     p.px_offset = px_offset;
+    p.pixel_major = x_layout == MT_X_PIXEL_MAJOR;
     p.neg_list = neg_list_dev;
     p.neg_count = neg_count_dev;
     if (peers_host) {
@@ -419,6 +453,10 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64;
     p.n_stages = (int)((kSmemLimit - fixed) / p.stage_bytes);
     if (p.n_stages > 12) p.n_stages = 12;
+    if (const char *cap = getenv("MT_FIT_MAX_STAGES")) {  // tuning knob (e.g. to leave shared memory to a co-resident kernel)
+        const int c = atoi(cap);
+        if (c >= 2 && c < p.n_stages) p.n_stages = c;
+    }
     MT_REQUIRE(p.n_stages >= 2, "mt_fit_contract: tile does not fit shared memory");
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * m_tiles * p.n_mma)) cols <<= 1;
@@ -444,23 +482,24 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
 
 extern "C" int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                                     int32_t k_begin, int32_t k_end, const float *w_dev, int64_t ld_w,
-                                    int32_t n_comp, float *x_dev, int64_t ld_x, void *stream_) {
+                                    int32_t n_comp, float *x_dev, int64_t ld_x, int32_t x_layout, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && w_dev && x_dev, "mt_fit_contract_simt: null pointer");
     MT_REQUIRE(n_px >= 0 && 0 <= k_begin && k_begin < k_end && k_end <= ld_spec && k_end <= ld_w && n_comp >= 1 &&
-                   ld_x >= n_px,
+                   ld_x >= (x_layout == MT_X_PIXEL_MAJOR ? (int64_t)n_comp : n_px),
                "mt_fit_contract_simt: bad sizes");
+    const int pm = x_layout == MT_X_PIXEL_MAJOR;
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const long long warps = (n_px + kSimtPx - 1) / kSimtPx;
     const unsigned grid = (unsigned)((warps + 7) / 8);
     if (dtype == MT_DTYPE_F32)
         fit_contract_simt_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(spec_dev), n_px, ld_spec,
-                                                                  k_begin, k_end, w_dev, ld_w, n_comp, x_dev, ld_x);
+                                                                  k_begin, k_end, w_dev, ld_w, n_comp, x_dev, ld_x, pm);
     else if (dtype == MT_DTYPE_F16)
         fit_contract_simt_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half *>(spec_dev), n_px,
                                                                    ld_spec, k_begin, k_end, w_dev, ld_w, n_comp,
-                                                                   x_dev, ld_x);
+                                                                   x_dev, ld_x, pm);
     else
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_fit_contract_simt: dtype %d", dtype);
     MT_CUDA_TRY(cudaGetLastError());

@@ -49,12 +49,13 @@ __device__ bool chol_solve(const double *M, int ld, const unsigned char *idx, in
 }
 
 template <int EMAX>
-__device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, int E, const double *G,
+__device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major, long long px, int E, const double *G,
                           const double *H, int *__restrict__ n_fixed, const MtPeers &peers);
 
 template <int EMAX>
 __global__ void __launch_bounds__(kNnlsThreads)
-nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, const double *__restrict__ g_dev,
+nnls_fixup_kernel(float *__restrict__ x, long long ld_x, int pixel_major, long long n_px, int E,
+                  const double *__restrict__ g_dev,
                   const double *__restrict__ h_dev, int *__restrict__ n_fixed, const int *__restrict__ list,
                   const int *__restrict__ list_count, const MtPeers peers) {
     extern __shared__ double mats[];  // G[E*E], H[E*E]
@@ -68,18 +69,19 @@ nnls_fixup_kernel(float *__restrict__ x, long long ld_x, long long n_px, int E, 
     const long long n_items = list ? (long long)*list_count : n_px;
     for (long long item = (long long)blockIdx.x * kNnlsThreads + threadIdx.x; item < n_items;
          item += (long long)gridDim.x * kNnlsThreads)
-        fix_pixel<EMAX>(x, ld_x, list ? (long long)list[item] : item, E, G, H, n_fixed, peers);
+        fix_pixel<EMAX>(x, ld_x, pixel_major, list ? (long long)list[item] : item, E, G, H, n_fixed, peers);
 }
 
 template <int EMAX>
-__device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, int E, const double *G,
+__device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major, long long px, int E, const double *G,
                           const double *H, int *__restrict__ n_fixed, const MtPeers &peers) {
+    const long long se = pixel_major ? 1 : ld_x, base = pixel_major ? px * ld_x : px;  // x[base + e * se]
     constexpr int HALF = EMAX / 2;
     double xu[EMAX];
     bool any_neg = false;
     double xmax = 0.0;
     for (int e = 0; e < E; ++e) {
-        xu[e] = (double)x[(long long)e * ld_x + px];
+        xu[e] = (double)x[base + e * se];
         any_neg |= (xu[e] < 0.0);
         xmax = fmax(xmax, fabs(xu[e]));
     }
@@ -188,9 +190,26 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, i
             }
         }
     }
+    if (pixel_major) {
+        // one 16-byte aligned record per pixel: 128-bit stores, also to the peers / multicast mapping
+        for (int e0 = 0; e0 < E; e0 += 4) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = (e0 + j < E && free_[e0 + j]) ? (float)fmax(xs[e0 + j], 0.0) : 0.f;
+            const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+            const long long at = base + e0;
+            *reinterpret_cast<float4 *>(x + at) = v;
+            for (int k = 0; k < peers.n_peers; ++k) *reinterpret_cast<float4 *>(peers.peer[k] + at) = v;
+            if (peers.multicast)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(peers.multicast + at),
+                             "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+        }
+        return;
+    }
     for (int e = 0; e < E; ++e) {
         const float out = (float)(free_[e] ? fmax(xs[e], 0.0) : 0.0);
-        const long long at = (long long)e * ld_x + px;
+        const long long at = base + e * se;
         x[at] = out;
         for (int k = 0; k < peers.n_peers; ++k) peers.peer[k][at] = out;  // keep the peers' copies in step
         if (peers.multicast)
@@ -199,7 +218,7 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, long long px, i
 }
 
 template <int EMAX>
-int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
+int launch_nnls(float *x, int64_t ld_x, int pixel_major, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
                 const int *list, const int *list_count, const MtPeers &peers, cudaStream_t stream) {
     auto kern = nnls_fixup_kernel<EMAX>;
     const size_t smem = sizeof(double) * 2 * (size_t)E * E;
@@ -211,12 +230,12 @@ int launch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, co
         if (dev < 16) smem_set[dev] = (int)smem;
     }
     const unsigned grid = list ? (unsigned)(mt::num_sms() * 8) : (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
-    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, peers);
+    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
 
-int dispatch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
+int dispatch_nnls(float *x, int64_t ld_x, int x_layout, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
                   const int *list, const int *list_count, const MtPeers *peers_host, cudaStream_t stream) {
     MtPeers peers{};
     if (peers_host) {
@@ -224,32 +243,39 @@ int dispatch_nnls(float *x, int64_t ld_x, int64_t n_px, int E, const double *g, 
                    peers_host->n_peers);
         peers = *peers_host;
     }
-    if (E <= 16) return launch_nnls<16>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 32) return launch_nnls<32>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 64) return launch_nnls<64>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 104) return launch_nnls<104>(x, ld_x, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
+    MT_REQUIRE(x_layout == MT_X_ELEMENT_MAJOR ||
+                   (x_layout == MT_X_PIXEL_MAJOR && ld_x >= ((E + 3) & ~3) && ld_x % 4 == 0 && ((uintptr_t)x & 15) == 0),
+               "non-negative solve: x_layout=%d ld_x=%lld", x_layout, (long long)ld_x);
+    const int pixel_major = x_layout == MT_X_PIXEL_MAJOR;
+    if (E <= 16) return launch_nnls<16>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
+    if (E <= 32) return launch_nnls<32>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
+    if (E <= 64) return launch_nnls<64>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
+    if (E <= 104) return launch_nnls<104>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "non-negative solve: n_comp=%d > 104", E);
 }
 
 }  // namespace
 
-extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int64_t n_px, int32_t n_comp, const double *g_dev,
+extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64_t n_px, int32_t n_comp,
+                             const double *g_dev,
                              const double *hinv_dev, int32_t *n_fixed_dev, const MtPeers *peers_host, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(x_dev && g_dev && hinv_dev, "mt_nnls_fixup: null pointer");
-    MT_REQUIRE(n_px >= 0 && n_comp >= 1 && ld_x >= n_px, "mt_nnls_fixup: bad sizes");
+    MT_REQUIRE(n_px >= 0 && n_comp >= 1 && (x_layout == MT_X_PIXEL_MAJOR || ld_x >= n_px), "mt_nnls_fixup: bad sizes");
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    return dispatch_nnls(x_dev, ld_x, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, nullptr, nullptr, peers_host, stream);
+    return dispatch_nnls(x_dev, ld_x, x_layout, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, nullptr, nullptr, peers_host,
+                         stream);
 }
 
-extern "C" int mt_nnls_list(float *x_dev, int64_t ld_x, const int32_t *list_dev, const int32_t *count_dev,
+extern "C" int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *list_dev,
+                            const int32_t *count_dev,
                             int32_t n_comp, const double *g_dev, const double *hinv_dev, const MtPeers *peers_host,
                             void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(x_dev && list_dev && count_dev && g_dev && hinv_dev, "mt_nnls_list: null pointer");
     MT_REQUIRE(n_comp >= 1, "mt_nnls_list: n_comp=%d", n_comp);
-    return dispatch_nnls(x_dev, ld_x, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, peers_host,
+    return dispatch_nnls(x_dev, ld_x, x_layout, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, peers_host,
                          static_cast<cudaStream_t>(stream_));
 }
 

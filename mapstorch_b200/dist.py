@@ -75,19 +75,28 @@ class PeerMaps:
     streaming -- the all-gather of SURVEY.md 8e without a separate collective; ``barrier()`` then
     orders the remote stores before anybody reads ``maps.full``."""
 
-    def __init__(self, n_comp, n_rows, width, group=None, multicast=True):
+    def __init__(self, n_comp, n_rows, width, group=None, multicast=True, layout="pe", e_pad=None):
         import torch.distributed._symmetric_memory as symm_mem
 
         from mapstorch_b200 import _native
 
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.full = symm_mem.empty((n_comp, n_rows * width), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.layout, self.n_comp = layout, n_comp
+        device = torch.device("cuda", torch.cuda.current_device())
+        r0, r1 = shard_rows(n_rows, self.rank, self.world)
+        if layout == "pe":
+            # one 16-byte aligned record per pixel: the kernels' stores (and the multicast) are 128-bit wide
+            e_pad = e_pad or -(-n_comp // 16) * 16
+            self.full = symm_mem.empty((n_rows * width, e_pad), dtype=torch.float32, device=device)
+            self.local = self.full[r0 * width: r1 * width]
+            offset = 4 * r0 * width * e_pad
+        else:
+            self.full = symm_mem.empty((n_comp, n_rows * width), dtype=torch.float32, device=device)
+            self.local = self.full[:, r0 * width: r1 * width]
+            offset = 4 * r0 * width
         self.full.zero_()
         self.handle = symm_mem.rendezvous(self.full, group)
-        r0, r1 = shard_rows(n_rows, self.rank, self.world)
-        self.local = self.full[:, r0 * width: r1 * width]
-        offset = 4 * r0 * width
         self.peers = _native.MtPeers()
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
         self.multicast = bool(mc)
@@ -100,6 +109,11 @@ class PeerMaps:
             for k, ptr in enumerate(others):
                 self.peers.peer[k] = ptr + offset
             self.peers.multicast = None
+
+    def component(self, index, n_rows, width):
+        """[n_rows, width] map of one component (a strided view for the pixel-major layout)."""
+        flat = self.full[:, index] if self.layout == "pe" else self.full[index]
+        return flat.reshape(n_rows, width)
 
     def barrier(self):
         """All ranks' stores issued so far on the current stream are visible everywhere afterwards."""

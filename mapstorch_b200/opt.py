@@ -95,15 +95,16 @@ def digit_planes(w64, n_planes=N_PLANES, bits=DIGIT_BITS):
     return scale.astype(np.float32), np.stack(planes)
 
 
-def _shift_peers(peers, n_px):
-    """The same peer destinations, advanced by n_px pixels (fp32 elements)."""
+def _shift_peers(peers, n_px, px_stride=1):
+    """The same peer destinations, advanced by n_px pixels (px_stride fp32 elements per pixel)."""
     if peers is None or n_px == 0:
         return peers
     moved = _native.MtPeers()
     moved.n_peers = peers.n_peers
+    step = 4 * n_px * px_stride
     for k in range(peers.n_peers):
-        moved.peer[k] = peers.peer[k] + 4 * n_px
-    moved.multicast = peers.multicast + 4 * n_px if peers.multicast else None
+        moved.peer[k] = peers.peer[k] + step
+    moved.multicast = peers.multicast + step if peers.multicast else None
     return moved
 
 
@@ -153,6 +154,9 @@ class MapFitPlan:
         self._neg = None
         self._last_engine = None
         self._last_wide = False
+        self._side = None
+        self.pipeline = False
+        self._pixel_major = False
         self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
         if self.use_snip:
             p = self.params
@@ -184,14 +188,21 @@ class MapFitPlan:
             self._packs[key] = torch.from_numpy(w).cuda()
         return self._packs[key]
 
-    def _neg_buffers(self, n_px):
-        """(pixel list, counter) the K3 epilogue fills; grown on demand, reused across calls."""
-        if self._neg is None or self._neg[0].numel() < n_px:
+    def _neg_buffers(self, n_px, n_counters=1):
+        """(pixel list, counters) the K3 epilogue fills; grown on demand, reused across calls."""
+        if self._neg is None or self._neg[0].numel() < n_px or self._neg[1].numel() < n_counters:
             self._neg = (torch.empty(n_px, dtype=torch.int32, device="cuda"),
-                         torch.zeros(1, dtype=torch.int32, device="cuda"))
-        return self._neg
+                         torch.zeros(max(n_counters, 64), dtype=torch.int32, device="cuda"))
+        return self._neg[0], self._neg[1][:n_counters]
 
     # -- the fit -----------------------------------------------------------------------------------
+    def _x_args(self, x):
+        """(pointer, leading dimension, layout code) of an amplitude array in either layout."""
+        return x.data_ptr(), x.stride(0), (_native.MT_X_PIXEL_MAJOR if self._pixel_major else _native.MT_X_ELEMENT_MAJOR)
+
+    def _x_chunk(self, x, p0, n):
+        return x[p0: p0 + n] if self._pixel_major else x[:, p0: p0 + n]
+
     def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0, peers=None):
         """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
         if self.timers is not None:
@@ -217,7 +228,7 @@ class MapFitPlan:
             pack, scale = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat)
             _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
                          n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
-                         self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), x.data_ptr(), x.stride(0),
+                         self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), *self._x_args(x),
                          int(px_offset), neg[0].data_ptr() if neg is not None else None,
                          neg[1].data_ptr() if neg is not None else None,
                          ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
@@ -228,36 +239,13 @@ class MapFitPlan:
                 raise _native.NativeError(-3, "the CUDA-core contraction expects an unsplit residual")
             w = self._pinv_f32(n_ch_total, col0)
             _native.call("mt_fit_contract_simt", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
-                         int(k_begin), int(k_end), w.data_ptr(), w.stride(0), self.n_live, x.data_ptr(),
-                         x.stride(0), _native.stream_ptr(stream))
+                         int(k_begin), int(k_end), w.data_ptr(), w.stride(0), self.n_live, *self._x_args(x),
+                         _native.stream_ptr(stream))
         else:
             raise ValueError(f"unknown engine {engine!r}")
 
-    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None,
-            peers=None):
-        """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
-        rows in `self.names` order (components without an open line stay 0).
-
-        exact_counts: the tensor-core operands (fp16 / tf32) hold 11 significant bits, i.e. integer
-        counts below 2048 exactly.  fp16 volumes satisfy that by construction and the SNIP path
-        splits its residual exactly; for fp32 volumes without SNIP, None (default) checks the
-        maximum on the device (one extra read of the volume and a host sync) and routes volumes
-        with larger values through an exact hi/lo split; True skips the check.
-
-        peers: optional _native.MtPeers whose pointers address, on the other GPUs of the box, the
-        element of their map buffers that corresponds to out[0, 0]; the kernels then store every
-        amplitude there as well (dist.PeerMaps) -- the all-gather of the maps fused into the fit."""
-        if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
-            raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
-        if spec2d.shape[1] <= self.er[1]:
-            raise ValueError(f"spectra have {spec2d.shape[1]} channels, energy_range ends at {self.er[1]}")
-        n_px, n_all = spec2d.shape[0], len(self.names)
-        if out is None:
-            out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
-        dense = self.n_live == n_all
-        if peers is not None and not dense:
-            raise NotImplementedError("peer-memory destinations with components that have no open line")
-        x = out if dense else torch.empty((self.n_live, n_px), dtype=torch.float32, device="cuda")
+    def _fit_serial(self, spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers):
+        n_px = spec2d.shape[0]
         # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
         neg = None
         if nonneg and engine == "tensor" and n_px:
@@ -279,8 +267,8 @@ class MapFitPlan:
                 hi = (y.view(torch.int32) & -8192).view(torch.float32)
                 scratch[:n, : self.n_ch] = hi
                 scratch[:n, self.n_ch:] = y - hi
-                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2, 0, width, engine, stream, neg, p0,
-                               _shift_peers(peers, p0))
+                self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2, 0, width, engine, stream, neg, p0,
+                               _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
         elif not self.use_snip:
             self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg, 0, peers)
         else:
@@ -295,19 +283,100 @@ class MapFitPlan:
                 n = min(chunk, n_px - p0)
                 _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass, self.boxcar_size,
                                  scratch[:n], mode, stream)
-                self._contract(scratch[:n], x[:, p0: p0 + n], 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
-                               _shift_peers(peers, p0))
+                self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
+                               _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
         if nonneg and n_px:
             if self._last_engine == "tensor" and neg is not None:
-                _native.call("mt_nnls_list", x.data_ptr(), x.stride(0), neg[0].data_ptr(), neg[1].data_ptr(),
+                _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
                              self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
                              ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
                 if n_fixed is not None:
                     n_fixed.copy_(neg[1])
             else:
-                _native.call("mt_nnls_fixup", x.data_ptr(), x.stride(0), n_px, self.n_live, self.gram_dev.data_ptr(),
+                _native.call("mt_nnls_fixup", *self._x_args(x), n_px, self.n_live, self.gram_dev.data_ptr(),
                              self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
                              ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
+
+    def _fit_pipelined(self, spec2d, x, n_fixed, peers, rounds_per_chunk=4):
+        """Contraction and non-negative solve overlapped: the volume is cut into chunks of whole
+        waves of the persistent kernel (148 CTAs x 256 pixels), chunk k's fix-up runs on a side
+        stream while chunk k+1 streams from HBM (the solve is latency bound, the contraction
+        bandwidth bound, and the contraction leaves room on every SM for the solve's CTAs)."""
+        n_px = spec2d.shape[0]
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        sms = torch.cuda.get_device_properties(spec2d.device).multi_processor_count
+        chunk = sms * 256 * rounds_per_chunk
+        starts = list(range(0, n_px, chunk))
+        lists, counts = self._neg_buffers(n_px, len(starts))
+        counts.zero_()
+        self._last_wide = False
+        for c, p0 in enumerate(starts):
+            n = min(chunk, n_px - p0)
+            self._contract(spec2d[p0: p0 + n], self._x_chunk(x, p0, n), self.er[0], 1, self.er[0], self.er[1] + 1, "tensor",
+                           None, (lists[p0: p0 + n], counts[c: c + 1]), p0, _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                _native.call("mt_nnls_list", *self._x_args(x), lists[p0: p0 + n].data_ptr(),
+                             counts[c: c + 1].data_ptr(), self.n_live, self.gram_dev.data_ptr(),
+                             self.hinv_dev.data_ptr(), ctypes.byref(peers) if peers is not None else None,
+                             _native.stream_ptr(side))
+        joined = torch.cuda.Event()
+        joined.record(side)
+        main.wait_event(joined)
+        if n_fixed is not None:
+            n_fixed.copy_(counts.sum().reshape(1))
+
+    def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None,
+            peers=None, layout="ep"):
+        """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
+        rows in `self.names` order (components without an open line stay 0).
+
+        exact_counts: the tensor-core operands (fp16 / tf32) hold 11 significant bits, i.e. integer
+        counts below 2048 exactly.  fp16 volumes satisfy that by construction and the SNIP path
+        splits its residual exactly; for fp32 volumes without SNIP, None (default) checks the
+        maximum on the device (one extra read of the volume and a host sync) and routes volumes
+        with larger values through an exact hi/lo split; True skips the check.
+
+        peers: optional _native.MtPeers whose pointers address, on the other GPUs of the box, the
+        element of their map buffers that corresponds to out[0, 0]; the kernels then store every
+        amplitude there as well (dist.PeerMaps) -- the all-gather of the maps fused into the fit.
+
+        layout: "ep" (default) returns x [E, P], one contiguous map per component; "pe" returns
+        x [P, e_pad], one 16-byte aligned record per pixel (columns >= E are zero) -- the layout
+        whose stores are 128-bit wide, used for the peer-memory gather."""
+        if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
+            raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
+        if spec2d.shape[1] <= self.er[1]:
+            raise ValueError(f"spectra have {spec2d.shape[1]} channels, energy_range ends at {self.er[1]}")
+        n_px, n_all = spec2d.shape[0], len(self.names)
+        dense = self.n_live == n_all
+        self._pixel_major = layout == "pe"
+        if self._pixel_major:
+            if not dense:
+                raise NotImplementedError("pixel-major output with components that have no open line")
+            if out is None:
+                out = torch.zeros((n_px, self.e_pad), dtype=torch.float32, device="cuda")
+            if out.shape[0] != n_px or out.stride(0) < self.e_pad or out.stride(0) % 4 or out.stride(1) != 1:
+                raise ValueError("pixel-major out must be [P, >= e_pad] with a row pitch that is a multiple of 4")
+        elif out is None:
+            out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
+        if peers is not None and not dense:
+            raise NotImplementedError("peer-memory destinations with components that have no open line")
+        x = out if dense else torch.empty((self.n_live, n_px), dtype=torch.float32, device="cuda")
+        # measured on B200 (c5 shard): chunking costs the contraction more (0.77 vs 0.72 ms) than the
+        # overlap hides (0.09 ms), so the pipelined variant is opt-in
+        pipelined = (self.pipeline and nonneg and engine == "tensor" and n_px > 0 and not self.use_snip and stream is None
+                     and (spec2d.dtype == torch.float16 or exact_counts is True)
+                     and (spec2d.stride(0) * spec2d.element_size()) % 16 == 0 and spec2d.data_ptr() % 16 == 0)
+        if pipelined:
+            self._fit_pipelined(spec2d, x, n_fixed, peers)
+        else:
+            self._fit_serial(spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers)
         if not dense:
             out[torch.as_tensor(self.live, device="cuda")] = x
         return out

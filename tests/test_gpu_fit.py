@@ -227,3 +227,25 @@ def test_fp32_counts_above_2048_take_the_exact_split_path():
     # the unchecked direct path truncates operands: visibly worse, which is why the check exists
     bad = plan.fit(dev, nonneg=False, exact_counts=True).cpu().numpy().T
     assert (np.abs(bad - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() > 1e-5
+
+
+def test_pixel_major_layout_is_the_same_fit():
+    from mapstorch_b200 import opt
+
+    p = params12(4096)
+    er = (0, 4095)
+    y, names = synth(p, er, ELEMS30, 700, seed=77, lo=0.0, hi=2.5)
+    plan = opt.MapFitPlan(er, ELEMS30, p, use_snip=False)
+    dev = torch.from_numpy(y).half().cuda()
+    ep = plan.fit(dev)
+    pe = plan.fit(dev, layout="pe")
+    assert pe.shape == (700, plan.e_pad) and torch.equal(pe[:, : len(names)].T, ep)
+    ep_s = plan.fit(dev, engine="simt")
+    pe_s = plan.fit(dev, engine="simt", layout="pe")
+    assert torch.equal(pe_s[:, : len(names)].T, ep_s)
+    # 12 components: e_pad = 16, padding columns stay zero
+    y2, names2 = synth(params12(), (0, 2047), ELEMS10, 130, seed=78)
+    plan2 = opt.MapFitPlan((0, 2047), ELEMS10, params12(), use_snip=False)
+    pe2 = plan2.fit(torch.from_numpy(y2).cuda(), layout="pe", exact_counts=True)
+    assert pe2.shape == (130, 16) and float(pe2[:, 12:].abs().max()) == 0.0
+    assert torch.equal(pe2[:, :12].T, plan2.fit(torch.from_numpy(y2).cuda(), exact_counts=True))

@@ -14,9 +14,10 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 rows, width, n_ch = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (64, 512, 4096)))
+lo, hi = (float(a) for a in (sys.argv[4:6] if len(sys.argv) > 5 else (0.5, 2.5)))
 p = synth.benchmark_params(n_ch)
 plan = opt.MapFitPlan((0, n_ch - 1), synth.ELEMS30, p, use_snip=False)
-truth = synth.truth_maps(len(plan.names), rows, width, seed=5, row0=rank * rows, total_rows=world * rows, device=dev, lo=0.5, hi=2.5)
+truth = synth.truth_maps(len(plan.names), rows, width, seed=5, row0=rank * rows, total_rows=world * rows, device=dev, lo=lo, hi=hi)
 vol = synth.poisson_volume(plan.basis, truth, dtype=torch.float16, seed=100 + rank).reshape(-1, n_ch)
 n_comp, n_px = len(plan.names), vol.shape[0]
 local = torch.zeros((n_comp, n_px), device=dev)
@@ -38,17 +39,25 @@ def nccl_step():
     return gather_maps(local, world * rows, width)
 
 results = {"nccl_ms": timed(nccl_step), "fit_only_ms": timed(lambda: plan.fit(vol, out=local))}
-for mc in (True, False):
+for mc, layout in ((True, "pe"), (False, "pe"), (True, "ep")):
     try:
-        maps = PeerMaps(n_comp, world * rows, width, multicast=mc)
+        maps = PeerMaps(n_comp, world * rows, width, multicast=mc, layout=layout, e_pad=plan.e_pad)
+        kw = dict(out=maps.local, layout=layout)
         def step():
-            plan.fit(vol, out=maps.local, peers=maps.peers)
+            plan.fit(vol, peers=maps.peers, **kw)
             maps.barrier()
         step(); torch.cuda.synchronize()
-        same = torch.equal(maps.full, ref)
-        results[f"peer_multicast={mc}"] = {"used_multicast": maps.multicast, "bit_identical_to_nccl": same, "ms": timed(step)}
+        got = maps.full[:, :n_comp].T if layout == "pe" else maps.full
+        same = torch.equal(got, ref)
+        results[f"peer_multicast={mc}_{layout}"] = {
+            "used_multicast": maps.multicast, "bit_identical_to_nccl": same, "ms": timed(step),
+            "no_barrier_ms": timed(lambda: plan.fit(vol, peers=maps.peers, **kw)),
+            "contract_only_ms": timed(lambda: plan.fit(vol, peers=maps.peers, nonneg=False, **kw)),
+            "contract_local_ms": timed(lambda: plan.fit(vol, nonneg=False, **kw)),
+            "fit_local_ms": timed(lambda: plan.fit(vol, **kw))}
     except Exception as exc:
-        results[f"peer_multicast={mc}"] = f"FAILED: {type(exc).__name__}: {exc}"
+        results[f"peer_multicast={mc}_{layout}"] = f"FAILED: {type(exc).__name__}: {exc}"
 if rank == 0:
-    print("world", world, "px/rank", n_px, results, flush=True)
+    import json
+    print("world", world, "px/rank", n_px, json.dumps(results, indent=1), flush=True)
 dist.destroy_process_group()
