@@ -254,7 +254,7 @@ def main():
 
     def step(gather=True, eager=False):
         if peer_maps is not None and gather:
-            # fused: the fit kernels store the amplitudes into every GPU's map buffer (NVLink multicast)
+            # fused: the fit kernels store the amplitudes into rank 0's map buffer over NVLink
             plan.fit(flat, out=peer_maps.local, peers=peer_maps.peers)
             peer_maps.barrier()
             return peer_maps.full
@@ -377,8 +377,8 @@ def main():
                            "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
                            "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
                            "step": "fit of the resident shard (contraction + non-negative fix-up)" +
-                                   ("" if world == 1 else " + element maps stored into every GPU's buffer by the fit kernels "
-                                    f"(NVLink {'multicast' if peer_maps.multicast else 'peer'} stores) + barrier" if peer_maps is not None
+                                   ("" if world == 1 else " + element maps gathered on rank 0 by the fit kernels' own stores "
+                                    f"(NVLink peer stores, mode {peer_maps.mode}) + barrier" if peer_maps is not None
                                     else " + NCCL all-gather of the element maps")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graph is not None,
                 "ms_per_step_eager_launch": ms_eager / args.steps, "roofline": roofline, "cpu_baseline": cb,

@@ -66,27 +66,33 @@ def allreduce_spectrum(int_spec_local, group=None):
 
 
 class PeerMaps:
-    """Element maps of the WHOLE grid on every GPU, filled by the fit kernels themselves.
+    """Element maps of the WHOLE grid assembled over NVLink by the fit kernels themselves.
 
-    The buffer [E, n_rows * width] lives in torch symmetric memory, so every rank holds pointers to
-    every other rank's copy (and, on NVSwitch systems, one multicast address that reaches all of
-    them).  ``plan.fit(shard, out=maps.local, peers=maps.peers)`` makes the K3 epilogue and the
-    non-negative fix-up store each amplitude into all copies while the contraction is still
-    streaming -- the all-gather of SURVEY.md 8e without a separate collective; ``barrier()`` then
-    orders the remote stores before anybody reads ``maps.full``."""
+    The buffer lives in torch symmetric memory, so every rank holds pointers to every other rank's
+    copy.  ``plan.fit(shard, out=maps.local, peers=maps.peers)`` makes the K3 epilogue and the
+    non-negative fix-up store each amplitude of the rank's shard into the destination copies while
+    the contraction is still streaming -- the gather of SURVEY.md 8e without a separate collective;
+    ``barrier()`` then orders the remote stores before anybody reads ``maps.full``.
 
-    def __init__(self, n_comp, n_rows, width, group=None, multicast=True, layout="pe", e_pad=None):
+    mode "gather"    : every rank stores into rank `root`'s buffer (one peer store per value);
+                       only the root ends up with the full maps.  Measured best on 8 GPUs.
+    mode "allgather" : every rank stores into all other ranks' buffers (world-1 peer stores).
+    mode "multicast" : one store to the NVSwitch multicast mapping reaches every rank.  Cheap for
+                       the coalesced epilogue stores, slow for the scattered fix-up stores, and
+                       stores of consecutive kernels are NOT ordered at the destinations (measured:
+                       stale values on 8 GPUs) -- kept for experiments only."""
+
+    def __init__(self, n_comp, n_rows, width, group=None, mode="gather", root=0, layout="ep", e_pad=None):
         import torch.distributed._symmetric_memory as symm_mem
 
         from mapstorch_b200 import _native
 
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.layout, self.n_comp = layout, n_comp
+        self.layout, self.n_comp, self.mode, self.root = layout, n_comp, mode, root
         device = torch.device("cuda", torch.cuda.current_device())
         r0, r1 = shard_rows(n_rows, self.rank, self.world)
         if layout == "pe":
-            # one 16-byte aligned record per pixel: the kernels' stores (and the multicast) are 128-bit wide
             e_pad = e_pad or -(-n_comp // 16) * 16
             self.full = symm_mem.empty((n_rows * width, e_pad), dtype=torch.float32, device=device)
             self.local = self.full[r0 * width: r1 * width]
@@ -98,17 +104,28 @@ class PeerMaps:
         self.full.zero_()
         self.handle = symm_mem.rendezvous(self.full, group)
         self.peers = _native.MtPeers()
-        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0) if multicast else 0
-        self.multicast = bool(mc)
-        if mc:
-            self.peers.n_peers = 0
+        self.peers.n_peers = 0
+        self.peers.multicast = None
+        self.multicast = False
+        if mode == "multicast":
+            mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            if not mc:
+                raise RuntimeError("this system has no NVLink multicast support")
             self.peers.multicast = mc + offset
+            self.multicast = True
         else:
-            others = [int(ptr) for r, ptr in enumerate(self.handle.buffer_ptrs) if r != self.rank]
-            self.peers.n_peers = len(others)
-            for k, ptr in enumerate(others):
-                self.peers.peer[k] = ptr + offset
-            self.peers.multicast = None
+            if mode == "gather":
+                targets = [root] if self.rank != root else []
+            elif mode == "allgather":
+                targets = [r for r in range(self.world) if r != self.rank]
+            else:
+                raise ValueError(f"unknown PeerMaps mode {mode!r}")
+            self.peers.n_peers = len(targets)
+            for k, r in enumerate(targets):
+                self.peers.peer[k] = int(self.handle.buffer_ptrs[r]) + offset
+
+    def has_full_maps(self):
+        return self.mode != "gather" or self.rank == self.root
 
     def component(self, index, n_rows, width):
         """[n_rows, width] map of one component (a strided view for the pixel-major layout)."""
