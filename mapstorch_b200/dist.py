@@ -124,6 +124,35 @@ class PeerMaps:
             for k, r in enumerate(targets):
                 self.peers.peer[k] = int(self.handle.buffer_ptrs[r]) + offset
 
+    def fit_chunked(self, plan, spec2d, rounds_per_chunk=4, **fit_kw):
+        """Fit the rank's shard in chunks of whole waves of the persistent kernel and copy every
+        finished chunk of the maps to the root's buffer on a side stream, so that the NVLink
+        traffic of chunk k overlaps the contraction of chunk k+1.  The kernels store locally only
+        (no scattered remote stores from the fix-up), the copies are coalesced."""
+        if self.layout != "ep":
+            raise NotImplementedError("chunked gather uses the element-major layout")
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
+            self._root_view = self.handle.get_buffer(self.root, tuple(self.full.shape), torch.float32)
+        n_px = spec2d.shape[0]
+        sms = torch.cuda.get_device_properties(spec2d.device).multi_processor_count
+        chunk = sms * 256 * rounds_per_chunk
+        g0 = self.local.storage_offset() - self.full.storage_offset()  # first pixel of this rank in the full map
+        for p0 in range(0, n_px, chunk):
+            n = min(chunk, n_px - p0)
+            plan.fit(spec2d[p0: p0 + n], out=self.local[:, p0: p0 + n], **fit_kw)
+            if self.rank != self.root:
+                done = torch.cuda.Event()
+                done.record(main)
+                self._side.wait_event(done)
+                with torch.cuda.stream(self._side):
+                    self._root_view[:, g0 + p0: g0 + p0 + n].copy_(self.local[:, p0: p0 + n], non_blocking=True)
+        if self.rank != self.root:
+            joined = torch.cuda.Event()
+            joined.record(self._side)
+            main.wait_event(joined)
+
     def has_full_maps(self):
         return self.mode != "gather" or self.rank == self.root
 

@@ -57,6 +57,18 @@ for mc, layout in (("gather", "ep"), ("allgather", "ep"), ("multicast", "ep")):
             "fit_local_ms": timed(lambda: plan.fit(vol, **kw))}
     except Exception as exc:
         results[f"peer_multicast={mc}_{layout}"] = f"FAILED: {type(exc).__name__}: {exc}"
+try:
+    maps = PeerMaps(n_comp, world * rows, width, mode="gather")
+    maps.peers.n_peers = 0  # kernels store locally; the chunks are copied to the root on a side stream
+    for rounds in (2, 4, 7):
+        def step():
+            maps.fit_chunked(plan, vol, rounds_per_chunk=rounds)
+            maps.barrier()
+        step(); torch.cuda.synchronize()
+        same = torch.equal(maps.full, ref) if rank == 0 else None
+        results[f"chunked_copy_rounds={rounds}"] = {"bit_identical_to_nccl_on_rank0": same, "ms": timed(step)}
+except Exception as exc:
+    results["chunked_copy"] = f"FAILED: {type(exc).__name__}: {exc}"
 if rank == 0:
     import json
     print("world", world, "px/rank", n_px, json.dumps(results, indent=1), flush=True)
