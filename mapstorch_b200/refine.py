@@ -131,3 +131,104 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
                  window.ctypes.data_as(ctypes.c_void_p), plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
                  theta.data_ptr(), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
     return theta[: len(free)], loss, iters
+
+
+# ---- fit_spec(tune_params=True): global calibration fit of one spectrum -------------------------
+def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals, fixed_param_vals,
+                    indices, use_snip, n_iter, e_consts, elem_info, detector_type, escape_factor, device, verbose):
+    """``fit_spec`` with ``tune_params=True`` (opt.py:165-327) on the GPU.
+
+    The reference runs Adam on all tunable calibration parameters and log-amplitudes at once.  Here the
+    amplitudes are projected out (for given calibration parameters they are the non-negative
+    least-squares solution) and the remaining small problem is solved by
+    Levenberg-Marquardt with forward-difference Jacobians; every evaluation runs K1 (basis), K2 (SNIP,
+    which depends on the calibration too) and the non-negative solve on the device."""
+    from mapstorch_b200 import bkg as _bkg, map as _map
+    from mapstorch_b200.default import default_fitting_params, default_learning_rates
+    from mapstorch_b200.opt import create_tensors
+
+    _native.require_device()
+    er = (int(energy_range[0]), int(energy_range[1]))
+    spec = int_spec.detach().float().cpu().numpy() if isinstance(int_spec, torch.Tensor) else np.asarray(int_spec, dtype=np.float32)
+    y = torch.from_numpy(np.ascontiguousarray(spec[er[0]: er[1] + 1])).cuda()
+    params = dict(default_param_vals)
+    params.update({k: (v.item() if isinstance(v, torch.Tensor) else float(v)) for k, v in init_param_vals.items()
+                   if k in default_param_vals})
+    params.update({k: (v.item() if isinstance(v, torch.Tensor) else float(v)) for k, v in fixed_param_vals.items()
+                   if k in default_param_vals})
+    free = [p for p in default_fitting_params if p in set(fitting_params) and p not in fixed_param_vals]
+    elements = list(dict.fromkeys(list(elements_to_fit)))
+    idx = None if indices is None else torch.as_tensor(np.asarray(indices), device="cuda")
+    scale = np.array([10.0 * default_learning_rates.get(p, default_learning_rates["default_lr"]) for p in free])
+    state = {}
+
+    def evaluate(theta):
+        pp = dict(params, **dict(zip(free, (float(t) for t in theta))))
+        basis, names = _map.element_basis(pp, er, elements, e_consts, elem_info, detector_type, escape_factor)
+        if use_snip:
+            bkg = _bkg.snip_bkg(y, er, *(torch.tensor(float(pp[k])) for k in (
+                "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")),
+                device="cuda")
+        else:
+            bkg = torch.zeros_like(y)
+        target = (y - bkg).double()
+        bm = basis.double() if idx is None else basis.double()[:, idx]
+        tm = target if idx is None else target[idx]
+        live = (bm * bm).sum(dim=1) > 0
+        bl = bm[live]
+        gram = bl @ bl.T
+        hinv = torch.linalg.inv(gram)
+        hinv = 0.5 * (hinv + hinv.T)
+        x_live = (hinv @ (bl @ tm)).float().reshape(-1, 1).contiguous()
+        _native.call("mt_nnls_fixup", x_live.data_ptr(), x_live.stride(0), _native.MT_X_ELEMENT_MAJOR, 1,
+                     int(live.sum()), gram.contiguous().data_ptr(), hinv.contiguous().data_ptr(), None, None,
+                     _native.stream_ptr())
+        x = torch.zeros(len(names), dtype=torch.float64, device="cuda")
+        x[live] = x_live.reshape(-1).double()
+        resid = x @ bm - tm
+        return resid, dict(x=x, names=names, basis=basis, bkg=bkg, params=pp)
+
+    theta = np.array([params[p] for p in free], dtype=np.float64)
+    resid, info = evaluate(theta)
+    loss = float(resid @ resid)
+    trace = [loss]
+    lam = 1e-3
+    for it in range(max(1, min(int(n_iter), 60)) if free else 0):
+        cols = []
+        for k in range(len(free)):
+            t2 = theta.copy()
+            t2[k] += 0.05 * scale[k]
+            r2, _ = evaluate(t2)
+            cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
+        jac = torch.stack(cols, dim=1)
+        jtj = (jac.T @ jac).cpu().numpy()
+        jtr = (jac.T @ resid).cpu().numpy()
+        improved = False
+        for _ in range(8):
+            try:
+                step = np.linalg.solve(jtj + lam * (np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))), -jtr)
+            except np.linalg.LinAlgError:
+                lam *= 10
+                continue
+            cand = theta + step * scale
+            r_new, info_new = evaluate(cand)
+            loss_new = float(r_new @ r_new)
+            if loss_new < loss:
+                rel = (loss - loss_new) / max(loss, 1e-30)
+                theta, resid, info, loss = cand, r_new, info_new, loss_new
+                lam = max(lam / 5, 1e-9)
+                improved = True
+                break
+            lam *= 5
+        trace.append(loss)
+        if verbose:
+            print(f"fit_spec_global iter {it}: loss {loss:.6g} lambda {lam:.2g}")
+        if not improved or rel < 1e-10:
+            break
+
+    pp, names, x = info["params"], info["names"], info["x"]
+    tensors, _ = create_tensors(names, free, pp, {k: pp[k] for k in pp if k not in free}, tune_params=True, device=device)
+    for n, a in zip(names, x.float()):
+        tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
+    spec_fit = (x.float() @ info["basis"]).reshape(-1)
+    return tensors, spec_fit.cpu().numpy(), info["bkg"].cpu().numpy(), trace

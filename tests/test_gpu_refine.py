@@ -101,3 +101,25 @@ def test_refinement_with_four_free_parameters_and_background():
     assert abs(float(maps["ENERGY_SLOPE"][0]) / theta[1] - 1) < 1e-4
     assert abs(float(maps["FWHM_OFFSET"][0]) / theta[2] - 1) < 3e-2
     assert torch.equal(maps["Fe"][0], maps["Fe"][2])
+
+
+def test_fit_spec_with_tuned_parameters_recovers_calibration():
+    """fit_spec(tune_params=True): the global calibration fit (BASELINE config 1's call) on the GPU
+    reaches an objective at least as low as the reference's converged Adam run."""
+    from mapstorch_b200 import opt
+
+    g, p, names = load_ref()
+    tensors, spec_fit, bkg, trace = opt.fit_spec(g["r_spec"], (0, 2047), names[:-2], fitting_params=["ENERGY_OFFSET", "FWHM_OFFSET"],
+                                                 init_param_vals=p, tune_params=True, use_snip=False, n_iter=30)
+    assert trace[-1] <= g["r_trace"][-1] * (1 + 1e-5) and trace[-1] < trace[0]
+    ref = g["r_fit_offset_width"]
+    assert abs(float(tensors["ENERGY_OFFSET"]) - ref[0]) < 2e-5
+    assert abs(float(tensors["FWHM_OFFSET"]) / ref[1] - 1) < 2e-4
+    assert tensors["ENERGY_OFFSET"].requires_grad and not tensors["ENERGY_SLOPE"].requires_grad
+    assert np.abs(spec_fit - g["r_spec_fit"]).max() <= 2e-3 * g["r_spec_fit"].max()
+    ref_log = dict(zip(names, g["r_logamps"]))
+    assert abs(float(tensors["Fe"]) - ref_log["Fe"]) < 1e-4
+    # all twelve default tunables at once, with SNIP, on a cropped range (the CLI's defaults)
+    t2, fit2, bkg2, trace2 = opt.fit_spec(g["r_spec"], (50, 1450), names[:-2], init_param_vals=p, tune_params=True,
+                                          use_snip=True, n_iter=15)
+    assert trace2[-1] < trace2[0] and fit2.shape == (1401,) and bkg2.shape == (1401,)
