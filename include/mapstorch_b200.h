@@ -126,13 +126,16 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
  * x_dev    : fp32 amplitudes in `x_layout` (MT_X_*), e < n_comp, p < n_px.
  * neg_list_dev / neg_count_dev (optional, both or neither): the epilogue appends px_offset + p of
  *            every pixel whose solution has a negative component to neg_list_dev (capacity >= n_px)
- *            and bumps *neg_count_dev (caller zeroes it); consumed by mt_nnls_list. */
+ *            and bumps *neg_count_dev (caller zeroes it); consumed by mt_nnls_list.
+ * hinv32_dev (optional; needs e_pad <= 32, element-major x and the list): G^-1 in fp32 [n_comp][n_comp].
+ *            The epilogue then applies the non-negative fix-up itself whenever a pixel's zero set has
+ *            at most two components (closed form, registers only) and lists only the remaining pixels. */
 int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,
                     int32_t n_ch_total, int32_t k_begin, int32_t k_end, const void *wpack_dev,
                     int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                     const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x, int32_t x_layout,
                     int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
-                    const MtPeers *peers_host /* optional */, void *stream);
+                    const float *hinv32_dev, const MtPeers *peers_host /* optional */, void *stream);
 
 /* Same contract on CUDA cores (no tensor cores, fp32 weights [n_comp][ld_w]); exists for
  * shapes/alignments TMA cannot address and as an on-device cross-check of mt_fit_contract. */

@@ -46,6 +46,7 @@ struct FitParams {
     int *neg_list;        // optional: pixels whose solution has a negative component
     int *neg_count;
     int pixel_major;      // x layout: 0 = x[e*ld_x + p], 1 = x[p*ld_x + e]
+    const float *hinv32;  // optional G^-1 (fp32 [n_comp][n_comp]): non-negative fix-up in the epilogue
     MtPeers peers;        // extra destinations on other GPUs (n_peers == 0 and multicast == NULL: none)
     float *x;
     const float *colscale;
@@ -75,6 +76,94 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             }
         }
     }
+}
+
+// Non-negative fix-up of one pixel inside the epilogue, registers only: block principal pivoting
+// restricted to zero sets of at most two components (closed-form 1x1 / 2x2 Schur complements on
+// H = G^-1, SURVEY.md 0.4 / csrc/mt_nnls.cu).  Returns false when the pixel needs a larger zero set
+// or does not settle within a few pivots; the caller then leaves the unconstrained values in place
+// and lists the pixel for the general solver (mt_nnls_list).
+__device__ __forceinline__ bool fixup_small(float (&x)[32], int E, const float *hs) {
+    float xu[32];
+    unsigned A = 0u;
+    float xmax = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        xu[e] = x[e];
+        if (e < E) {
+            A |= (xu[e] < 0.f) ? (1u << e) : 0u;
+            xmax = fmaxf(xmax, fabsf(xu[e]));
+        }
+    }
+    const float tol = 1e-7f * xmax;
+    bool settled = false;
+    for (int iter = 0; iter < 6; ++iter) {
+        const int n = __popc(A);
+        if (n > 2) break;
+        if (n == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = xu[e];
+            unsigned V = 0u;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (e < E && xu[e] < -tol) V |= 1u << e;
+            if (V == 0u) {
+                settled = true;
+                break;
+            }
+            A = V;
+            continue;
+        }
+        const int a = __ffs(A) - 1, b = 31 - __clz(A);
+        float xa = 0.f, xb = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            xa = (e == a) ? xu[e] : xa;
+            xb = (e == b) ? xu[e] : xb;
+        }
+        // strongly overlapping components make H_AA nearly singular (z large, corrections cancel):
+        // the small solve and the update run in fp64, H itself is kept in fp32
+        const double haa = hs[a * E + a], hbb = hs[b * E + b], hab = hs[a * E + b];
+        double za, zb;
+        if (n == 1) {
+            za = (double)xa / haa;
+            zb = 0.0;
+        } else {
+            const double det = haa * hbb - hab * hab;
+            za = (hbb * xa - hab * xb) / det;
+            zb = (haa * xb - hab * xa) / det;
+        }
+        // duals on the zero set are -z (in units of x / H); primal on the free set
+        const double tol_y = (double)tol / fmin(haa, hbb);
+        unsigned V = 0u;
+        if (-za < -tol_y) V |= 1u << a;
+        if (n == 2 && -zb < -tol_y) V |= 1u << b;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            if (e < E) {
+                if ((A >> e) & 1u) {
+                    x[e] = 0.f;
+                } else {
+                    const float v = (float)((double)xu[e] - (double)hs[e * E + a] * za - (double)hs[e * E + b] * zb);
+                    x[e] = v;
+                    if (v < -tol) V |= 1u << e;
+                }
+            }
+        }
+        if (V == 0u) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = fmaxf(x[e], 0.f);
+            settled = true;
+            break;
+        }
+        A ^= V;
+    }
+    if (!settled) {
+        // hand the UNCONSTRAINED solution to the general solver
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = xu[e];
+    }
+    return settled;
 }
 
 template <int KIND, int M_TILES>
@@ -117,6 +206,9 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         tmem_relinquish();
     }
     for (int e = threadIdx.x; e < p.e_pad; e += kFitThreads) cs[e] = (e < p.n_comp) ? p.colscale[e] : 0.f;
+    float *hs = cs + p.e_pad;  // G^-1 for the in-epilogue fix-up (only if p.hinv32)
+    if (p.hinv32)
+        for (int i = threadIdx.x; i < p.n_comp * p.n_comp; i += kFitThreads) hs[i] = p.hinv32[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -190,6 +282,73 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (p.hinv32 != nullptr) {
+                // ---- whole pixels in registers: drain TMEM for both sub-tiles first and hand the
+                // accumulator back to the MMA warp, then fix small zero sets and store ----
+                float xv[M_TILES][32];
+#pragma unroll
+                for (int mt = 0; mt < M_TILES; ++mt) {
+                    const uint32_t taddr =
+                        tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+#pragma unroll
+                    for (int c0 = 0; c0 < 32; c0 += 8) {
+                        if (c0 < p.e_pad) {
+                            float a8[8], part[8];
+                            tmem_ld8(taddr + (uint32_t)((p.n_planes - 1) * p.e_pad + c0), a8);
+                            tmem_ld_wait();
+                            for (int d = p.n_planes - 2; d >= 0; --d) {
+                                tmem_ld8(taddr + (uint32_t)(d * p.e_pad + c0), part);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) a8[j] = fmaf(a8[j], p.plane_ratio, part[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) xv[mt][c0 + j] = cs[c0 + j] * a8[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) xv[mt][c0 + j] = 0.f;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+#pragma unroll
+                for (int mt = 0; mt < M_TILES; ++mt) {
+                    const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
+                    bool any_neg = false;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) any_neg |= (xv[mt][e] < 0.f);
+                    bool negative = false;
+                    if (any_neg && px < p.n_px) negative = !fixup_small(xv[mt], p.n_comp, hs);
+                    if (px < p.n_px) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            if (e < p.n_comp) {
+                                const long long at = (long long)e * p.ld_x + px;
+                                p.x[at] = xv[mt][e];
+                                for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = xv[mt][e];
+                                if (p.peers.multicast)
+                                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
+                                                 "f"(xv[mt][e])
+                                                 : "memory");
+                            }
+                        }
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, negative);
+                    if (ballot != 0u) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(p.neg_count, __popc(ballot));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (negative) p.neg_list[base + __popc(ballot & ((1u << lane) - 1u))] = (int)(p.px_offset + px);
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+                continue;
+            }
 #pragma unroll
             for (int mt = 0; mt < M_TILES; ++mt) {
                 const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
@@ -392,7 +551,7 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                                int64_t ld_w, int32_t e_pad, int32_t n_comp, int32_t n_planes,
                                const float *colscale_dev, float plane_ratio, float *x_dev, int64_t ld_x,
                                int32_t x_layout, int64_t px_offset, int32_t *neg_list_dev, int32_t *neg_count_dev,
-                               const MtPeers *peers_host, void *stream_) {
+                               const float *hinv32_dev, const MtPeers *peers_host, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && wpack_dev && colscale_dev && x_dev, "mt_fit_contract: null pointer");
     MT_REQUIRE(dtype == MT_DTYPE_F32 || dtype == MT_DTYPE_F16, "mt_fit_contract: dtype %d", dtype);
@@ -429,6 +588,11 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.ld_x = ld_x;
     p.px_offset = px_offset;
     p.pixel_major = x_layout == MT_X_PIXEL_MAJOR;
+    if (hinv32_dev) {
+        MT_REQUIRE(e_pad <= 32 && x_layout == MT_X_ELEMENT_MAJOR && neg_list_dev,
+                   "mt_fit_contract: the in-epilogue fix-up needs e_pad <= 32, element-major x and a fallback list");
+        p.hinv32 = hinv32_dev;
+    }
     p.neg_list = neg_list_dev;
     p.neg_count = neg_count_dev;
     if (peers_host) {
@@ -450,7 +614,8 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     const int block_rows = kTileRows * m_tiles;
     p.n_tiles = (int)((n_px + block_rows - 1) / block_rows);
     p.stage_bytes = (uint32_t)(m_tiles * kSubTileBytes + p.n_mma * kRowBytes);
-    const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64;
+    const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64 +
+                         (hinv32_dev ? 4 * (size_t)n_comp * n_comp : 0);
     p.n_stages = (int)((kSmemLimit - fixed) / p.stage_bytes);
     if (p.n_stages > 12) p.n_stages = 12;
     if (const char *cap = getenv("MT_FIT_MAX_STAGES")) {  // tuning knob (e.g. to leave shared memory to a co-resident kernel)

@@ -59,6 +59,8 @@ nnls_fixup_kernel(float *__restrict__ x, long long ld_x, int pixel_major, long l
                   const double *__restrict__ h_dev, int *__restrict__ n_fixed, const int *__restrict__ list,
                   const int *__restrict__ list_count, const MtPeers peers) {
     extern __shared__ double mats[];  // G[E*E], H[E*E]
+    // list mode: blocks beyond the (device-side) item count have nothing to do
+    if (list && (long long)blockIdx.x * kNnlsThreads >= (long long)*list_count) return;
     double *G = mats, *H = mats + E * E;
     for (int i = threadIdx.x; i < E * E; i += kNnlsThreads) {
         G[i] = g_dev[i];

@@ -156,6 +156,8 @@ class MapFitPlan:
         self._last_wide = False
         self._side = None
         self.pipeline = False
+        self.epilogue_fixup = True  # K3 epilogue fixes pixels whose zero set has <= 2 components itself
+        self._h32 = None
         self._pixel_major = False
         self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
         if self.use_snip:
@@ -187,6 +189,11 @@ class MapFitPlan:
             w[:, col0: col0 + self.n_ch] = self.pinv.astype(np.float32)
             self._packs[key] = torch.from_numpy(w).cuda()
         return self._packs[key]
+
+    def _hinv32(self):
+        if self._h32 is None:
+            self._h32 = torch.from_numpy(self.hinv.astype(np.float32)).cuda()
+        return self._h32
 
     def _neg_buffers(self, n_px, n_counters=1):
         """(pixel list, counters) the K3 epilogue fills; grown on demand, reused across calls."""
@@ -231,6 +238,8 @@ class MapFitPlan:
                          self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), *self._x_args(x),
                          int(px_offset), neg[0].data_ptr() if neg is not None else None,
                          neg[1].data_ptr() if neg is not None else None,
+                         self._hinv32().data_ptr() if (neg is not None and self.epilogue_fixup and self.e_pad <= 32
+                                                       and not self._pixel_major) else None,
                          ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
         elif engine == "simt":
             if peers is not None:

@@ -237,9 +237,18 @@ def test_pixel_major_layout_is_the_same_fit():
     y, names = synth(p, er, ELEMS30, 700, seed=77, lo=0.0, hi=2.5)
     plan = opt.MapFitPlan(er, ELEMS30, p, use_snip=False)
     dev = torch.from_numpy(y).half().cuda()
+    plan.epilogue_fixup = False  # same (fp64, list-driven) non-negative solve for both layouts
     ep = plan.fit(dev)
     pe = plan.fit(dev, layout="pe")
     assert pe.shape == (700, plan.e_pad) and torch.equal(pe[:, : len(names)].T, ep)
+    # the in-epilogue fp32 fix-up of small zero sets agrees with the fp64 solver to fp32 rounding
+    plan.epilogue_fixup = True
+    fused = plan.fit(dev)
+    assert float(((fused - ep).abs() / ep.abs().max(dim=0, keepdim=True).values).max()) <= 3e-5
+    basis = plan.basis.double()
+    y64 = dev.double()
+    obj = lambda x: ((y64 - x.double().T @ basis) ** 2).sum(dim=1)
+    assert bool((obj(fused) <= obj(ep) * (1 + 1e-9) + 1e-6).all())
     ep_s = plan.fit(dev, engine="simt")
     pe_s = plan.fit(dev, engine="simt", layout="pe")
     assert torch.equal(pe_s[:, : len(names)].T, ep_s)
