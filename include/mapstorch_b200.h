@@ -154,8 +154,11 @@ int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64_t n_px, in
                   void *stream);
 
 /* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
- * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]). */
+ * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]).  short_list != 0 selects
+ * the warp-per-pixel variant (n_comp <= 32, element-major), which minimises the latency of a solve
+ * and is the right choice when the K3 epilogue has already fixed most pixels. */
 int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *list_dev, const int32_t *count_dev,
+                 int32_t short_list,
                  int32_t n_comp, const double *g_dev, const double *hinv_dev,
                  const MtPeers *peers_host /* optional */, void *stream);
 

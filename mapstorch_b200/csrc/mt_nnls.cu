@@ -237,6 +237,111 @@ int launch_nnls(float *x, int64_t ld_x, int pixel_major, int64_t n_px, int E, co
     return MT_OK;
 }
 
+
+// ---- warp-per-pixel variant for SHORT lists ---------------------------------------------------
+// When the K3 epilogue has already fixed the pixels with small zero sets, only a few hundred
+// pixels per GPU are left and the latency of one solve is what counts: here one warp owns a pixel,
+// lane e owns component e (E <= 32), the zero set's system H_AA z = xu_A is solved by Gauss-Jordan
+// with row r in lane r's registers, x_F = xu_F - H_FA z, duals on A are -z.  fp64, registers and
+// shuffles only; H = G^-1 in shared memory.
+constexpr int kListWarps = 4;
+
+__global__ void __launch_bounds__(kListWarps * 32)
+nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ list,
+                 const int *__restrict__ count, int E, const double *__restrict__ h_dev, const MtPeers peers) {
+    extern __shared__ double Hs[];  // [E*E]
+    const int n_items = *count;
+    if (blockIdx.x * kListWarps >= n_items) return;
+    for (int i = threadIdx.x; i < E * E; i += blockDim.x) Hs[i] = h_dev[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kListWarps + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kListWarps;
+    const bool valid = lane < E;
+    double hmin = valid ? Hs[lane * E + lane] : 1e300;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) hmin = fmin(hmin, __shfl_xor_sync(0xffffffffu, hmin, s));
+
+    for (int item = warp_global; item < n_items; item += n_warps) {
+        const long long px = list[item];
+        const double xu = valid ? (double)x[(long long)lane * ld_x + px] : 0.0;
+        double xmax = fabs(xu);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, s));
+        const double tol_x = 1e-12 * xmax, tol_y = 1e-12 * xmax / hmin;
+        unsigned A = __ballot_sync(0xffffffffu, valid && xu < 0.0);
+        double xs = xu;
+        int ninf = E + 1, backup = 3;
+        for (int iter = 0; iter < 4 * E + 8 && A != 0u; ++iter) {
+            const int n = __popc(A);
+            const int a = (lane < n) ? (int)__fns(A, 0, lane + 1) : 0;  // component of my system row
+            double v = __shfl_sync(0xffffffffu, xu, a);
+            double M[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                M[c] = 0.0;
+                if (c < n) {
+                    const int ac = __shfl_sync(0xffffffffu, a, c);
+                    M[c] = (lane < n) ? Hs[a * E + ac] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < n) {
+                    const double pkk = __shfl_sync(0xffffffffu, M[k], k);
+                    const double pv = __shfl_sync(0xffffffffu, v, k);
+                    const double f = (lane != k && lane < n) ? M[k] / pkk : 0.0;
+#pragma unroll
+                    for (int c = k + 1; c < 32; ++c) {
+                        if (c < n) {
+                            const double pc = __shfl_sync(0xffffffffu, M[c], k);
+                            M[c] -= f * pc;
+                        }
+                    }
+                    v -= f * pv;
+                }
+            }
+            double diag = 1.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c == lane) diag = M[c];
+            const double z = (lane < n) ? v / diag : 0.0;
+            const bool active = (A >> lane) & 1u;
+            xs = xu;
+            for (int r = 0; r < n; ++r) {
+                const int ar = __shfl_sync(0xffffffffu, a, r);
+                const double zr = __shfl_sync(0xffffffffu, z, r);
+                if (valid && !active) xs -= Hs[lane * E + ar] * zr;
+            }
+            const double zmine = __shfl_sync(0xffffffffu, z, __popc(A & ((1u << lane) - 1u)));
+            if (active) xs = -zmine;
+            const bool bad = valid && (active ? (xs < -tol_y) : (xs < -tol_x));
+            const unsigned V = __ballot_sync(0xffffffffu, bad);
+            const int nb = __popc(V);
+            if (nb == 0) break;
+            unsigned flip = V;
+            if (nb < ninf) {
+                ninf = nb;
+                backup = 3;
+            } else if (backup > 0) {
+                --backup;
+            } else {
+                flip = 1u << (31 - __clz(V));
+            }
+            A ^= flip;
+        }
+        if (valid) {
+            const bool active = (A >> lane) & 1u;
+            const float out = active ? 0.f : (float)fmax(xs, 0.0);
+            const long long at = (long long)lane * ld_x + px;
+            x[at] = out;
+            for (int k = 0; k < peers.n_peers; ++k) peers.peer[k][at] = out;
+            if (peers.multicast)
+                asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.multicast + at), "f"(out) : "memory");
+        }
+    }
+}
+
 int dispatch_nnls(float *x, int64_t ld_x, int x_layout, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
                   const int *list, const int *list_count, const MtPeers *peers_host, cudaStream_t stream) {
     MtPeers peers{};
@@ -271,12 +376,22 @@ extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64
 }
 
 extern "C" int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *list_dev,
-                            const int32_t *count_dev,
+                            const int32_t *count_dev, int32_t short_list,
                             int32_t n_comp, const double *g_dev, const double *hinv_dev, const MtPeers *peers_host,
                             void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(x_dev && list_dev && count_dev && g_dev && hinv_dev, "mt_nnls_list: null pointer");
     MT_REQUIRE(n_comp >= 1, "mt_nnls_list: n_comp=%d", n_comp);
+    if (short_list && n_comp <= 32 && x_layout == MT_X_ELEMENT_MAJOR) {
+        MtPeers peers{};
+        if (peers_host) peers = *peers_host;
+        cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+        const size_t smem = sizeof(double) * (size_t)n_comp * n_comp;
+        nnls_warp_kernel<<<mt::num_sms() * 8, kListWarps * 32, smem, stream>>>(x_dev, ld_x, list_dev, count_dev, n_comp,
+                                                                             hinv_dev, peers);
+        MT_CUDA_TRY(cudaGetLastError());
+        return MT_OK;
+    }
     return dispatch_nnls(x_dev, ld_x, x_layout, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, peers_host,
                          static_cast<cudaStream_t>(stream_));
 }

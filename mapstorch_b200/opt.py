@@ -297,7 +297,7 @@ class MapFitPlan:
         if nonneg and n_px:
             if self._last_engine == "tensor" and neg is not None:
                 _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
-                             self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
+                             int(self.epilogue_fixup and self.e_pad <= 32), self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
                              ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
                 if n_fixed is not None:
                     n_fixed.copy_(neg[1])
@@ -331,7 +331,7 @@ class MapFitPlan:
             side.wait_event(done)
             with torch.cuda.stream(side):
                 _native.call("mt_nnls_list", *self._x_args(x), lists[p0: p0 + n].data_ptr(),
-                             counts[c: c + 1].data_ptr(), self.n_live, self.gram_dev.data_ptr(),
+                             counts[c: c + 1].data_ptr(), int(self.epilogue_fixup and self.e_pad <= 32), self.n_live, self.gram_dev.data_ptr(),
                              self.hinv_dev.data_ptr(), ctypes.byref(peers) if peers is not None else None,
                              _native.stream_ptr(side))
         joined = torch.cuda.Event()
