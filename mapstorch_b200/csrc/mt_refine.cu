@@ -20,6 +20,7 @@
 // fixed point is the true minimiser.  Model terms are the Gaussian lines of model_spec's default
 // path (map.py:152-208 with f_step = 0, elastic, Compton Gaussian); exp dominates (MUFU bound).
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "mt_common.cuh"
 
@@ -38,6 +39,7 @@ struct RefParams {
     const int32_t *comp_start;      // [n_comp + 1] into comp_lines
     const int32_t *comp_lines;      // line indices grouped by component
     const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
+    const int32_t *line_off;        // [n_lines + 1]: offset of each line's window in the cached basis values
     const float *g0inv;             // [n_comp][n_comp]
     const float *bkg;
     long long ld_bkg;
@@ -64,17 +66,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename T>
+template <typename T, bool CACHE>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefParams p) {
-    extern __shared__ float dyn[];  // r[n_ch], d[n_theta][n_ch]
+    extern __shared__ float dyn[];  // r[n_ch], d[n_theta][n_ch], cached basis values of every line window
     const MtRefineConfig &cfg = p.cfg;
     const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines, NT = cfg.n_theta;
     float *r_s = dyn;
     float *d_s = dyn + n_ch;
+    float *b_s = dyn + (size_t)n_ch * (1 + NT);  // unit-amplitude line values, filled by B1, reused by B2
 
     __shared__ float l_inv_sigma[kMaxLines], l_unit[kMaxLines], l_coef[kMaxLines], l_dfo[kMaxLines],
-        l_dfa[kMaxLines];
+        l_dfa[kMaxLines], l_energy[kMaxLines];
+    __shared__ uint32_t l_win[kMaxLines];
+    __shared__ int l_off[kMaxLines];
     __shared__ float xs[kMaxComp], x_prev[kMaxComp], dx[kMaxComp], gx[kMaxComp], w_s[kMaxComp];
     __shared__ float hthx[kMaxTheta][kMaxComp], t1[kMaxComp][kMaxTheta];
     __shared__ float part[kRefWarps][1 + kMaxTheta + kMaxTheta * kMaxTheta];
@@ -99,6 +104,11 @@ refine_kernel(const RefParams p) {
     if (tid == 0) {
         ctl[1] = 3.0e38f;  // loss_prev
         ctl[2] = 1.f;      // alpha
+    }
+    for (int l = tid; l < L; l += kRefThreads) {
+        l_energy[l] = p.lines[l].energy;
+        l_win[l] = p.line_window[l];
+        l_off[l] = p.line_off[l];
     }
     __syncthreads();
 
@@ -139,9 +149,13 @@ refine_kernel(const RefParams p) {
             const uint32_t range = __ldg(p.chan_lines + c);
             float m = 0.f, d_ev = 0.f, d_fo = 0.f, d_fa = 0.f;
             for (int l = (int)(range & 0xffffu); l < (int)(range >> 16); ++l) {
+                const uint32_t win = l_win[l];
+                if (c < (int)(win & 0xffffu) || c >= (int)(win >> 16)) continue;  // outside this line's window
                 const float is = l_inv_sigma[l];
-                const float u = (ev - __ldg(&p.lines[l].energy)) * is;
-                const float v = l_coef[l] * expf(-0.5f * u * u);
+                const float u = (ev - l_energy[l]) * is;
+                const float g = __expf(-0.5f * u * u);
+                if (CACHE) b_s[l_off[l] + c - (int)(win & 0xffffu)] = l_unit[l] * g;
+                const float v = l_coef[l] * g;
                 m += v;
                 d_ev -= v * u * is;
                 const float dsg = v * (u * u - 1.f) * is;
@@ -178,13 +192,18 @@ refine_kernel(const RefParams p) {
             float g = 0.f, h[kMaxTheta] = {0.f, 0.f, 0.f, 0.f};
             for (int j = p.comp_start[e]; j < p.comp_start[e + 1]; ++j) {
                 const int l = p.comp_lines[j];
-                const uint32_t win = __ldg(p.line_window + l);
-                const float is = l_inv_sigma[l], unit = l_unit[l], el = __ldg(&p.lines[l].energy);
+                const uint32_t win = l_win[l];
+                const float *bl = b_s + l_off[l] - (int)(win & 0xffffu);
+                const float is = l_inv_sigma[l], unit = l_unit[l], el = l_energy[l];
                 for (int c = (int)(win & 0xffffu) + lane; c < (int)(win >> 16); c += 32) {
-                    const float cg = (float)(cfg.ch0 + c);
-                    const float ev = off + slope * cg + cfg.energy_quad * (cg * cg);
-                    const float u = (ev - el) * is;
-                    const float b = unit * expf(-0.5f * u * u);
+                    float b;
+                    if (CACHE) {
+                        b = bl[c];
+                    } else {
+                        const float cg = (float)(cfg.ch0 + c);
+                        const float u = (off + slope * cg + cfg.energy_quad * (cg * cg) - el) * is;
+                        b = unit * __expf(-0.5f * u * u);
+                    }
                     g += b * r_s[c];
 #pragma unroll
                     for (int k = 0; k < kMaxTheta; ++k)
@@ -356,12 +375,13 @@ refine_kernel(const RefParams p) {
 extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
                          int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
                          const uint32_t *chan_lines_host, const int32_t *comp_start_host,
-                         const int32_t *comp_lines_host, const uint32_t *line_window_host, const float *g0inv_dev,
+                         const int32_t *comp_lines_host, const uint32_t *line_window_host,
+                         const int32_t *line_off_host, const float *g0inv_dev,
                          float *x_dev, int64_t ld_x, float *theta_dev, float *loss_dev, int32_t *iters_dev,
                          void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && cfg_host && lines_host && chan_lines_host && comp_start_host && comp_lines_host &&
-                   line_window_host && g0inv_dev && x_dev,
+                   line_window_host && line_off_host && g0inv_dev && x_dev,
                "mt_refine: null pointer");
     const MtRefineConfig &cfg = *cfg_host;
     MT_REQUIRE(cfg.n_ch > 0 && cfg.n_ch <= 8192 && cfg.ch0 >= 0 && ld_spec >= (int64_t)cfg.ch0 + cfg.n_ch,
@@ -378,10 +398,10 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     // stage the small tables in one stream-ordered scratch allocation
     const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
-                 b_lw = sizeof(uint32_t) * cfg.n_lines;
+                 b_lw = sizeof(uint32_t) * cfg.n_lines, b_lo = sizeof(int32_t) * (cfg.n_lines + 1);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char *scratch = nullptr;
-    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw), stream));
+    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_lo), stream));
     char *q = scratch;
     RefParams p{};
     p.cfg = cfg;
@@ -396,6 +416,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.comp_start = static_cast<const int32_t *>(stage(comp_start_host, b_cs));
     p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
     p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
+    p.line_off = static_cast<const int32_t *>(stage(line_off_host, b_lo));
     MT_CUDA_TRY(cudaGetLastError());
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
@@ -408,13 +429,24 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.loss_out = loss_dev;
     p.iters_out = iters_dev;
     p.n_px = n_px;
-    const size_t smem = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta);
+    const size_t smem_base = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta);
+    const size_t smem_cache = smem_base + sizeof(float) * (size_t)line_off_host[cfg.n_lines];
+    if (smem_base > 200 * 1024)
+        return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: %zu bytes of shared memory needed (channels x free parameters)",
+                        smem_base);
+    // caching the line values halves the exp count but costs occupancy; measured slower on B200 (c4), opt-in
+    const char *env = getenv("MT_REFINE_CACHE");
+    const bool cache = env && atoi(env) != 0 && smem_cache <= 200 * 1024;
+    const size_t smem = cache ? smem_cache : smem_base;
+#define MT_LAUNCH_REFINE(T, C)                                                                                        \
+    do {                                                                                                               \
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        refine_kernel<T, C><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                         \
+    } while (0)
     if (dtype == MT_DTYPE_F32) {
-        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        refine_kernel<float><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);
+        if (cache) MT_LAUNCH_REFINE(float, true); else MT_LAUNCH_REFINE(float, false);
     } else if (dtype == MT_DTYPE_F16) {
-        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        refine_kernel<__half><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);
+        if (cache) MT_LAUNCH_REFINE(__half, true); else MT_LAUNCH_REFINE(__half, false);
     } else {
         cudaFreeAsync(scratch, stream);
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: dtype %d", dtype);

@@ -100,7 +100,10 @@ def refine_tables(params, names, er, free, bounds=None, k_sigma=7.0, **kw):
     counts = np.bincount([lines[i][2] for i in order], minlength=len(names))
     comp_start = np.zeros(len(names) + 1, dtype=np.int32)
     np.cumsum(counts, out=comp_start[1:])
-    return cfg, arr, chan_lines, comp_start, comp_lines, window
+    lengths = (window >> 16).astype(np.int64) - (window & 0xFFFF).astype(np.int64)
+    line_off = np.zeros(len(lines) + 1, dtype=np.int32)
+    np.cumsum(lengths, out=line_off[1:])
+    return cfg, arr, chan_lines, comp_start, comp_lines, window, line_off
 
 
 def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=None, max_iter=12, tol=1e-6,
@@ -114,7 +117,8 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
     unknown = [f for f in free if f not in _native.THETA_IDS]
     if unknown or len(free) > 4:
         raise ValueError(f"free parameters must be a subset of {sorted(_native.THETA_IDS)}, got {free}")
-    cfg, lines, chan_lines, comp_start, comp_lines, window = refine_tables(plan.params, plan.names, plan.er, free, bounds)
+    cfg, lines, chan_lines, comp_start, comp_lines, window, line_off = refine_tables(plan.params, plan.names, plan.er,
+                                                                                  free, bounds)
     cfg.max_iter, cfg.tol = int(max_iter), float(tol)
     n_px = spec2d.shape[0]
     if not hasattr(plan, "_g0inv32"):
@@ -128,7 +132,8 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
                  bkg.data_ptr() if bkg is not None else None, bkg.stride(0) if bkg is not None else 0,
                  ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p), chan_lines.ctypes.data_as(ctypes.c_void_p),
                  comp_start.ctypes.data_as(ctypes.c_void_p), comp_lines.ctypes.data_as(ctypes.c_void_p),
-                 window.ctypes.data_as(ctypes.c_void_p), plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
+                 window.ctypes.data_as(ctypes.c_void_p), line_off.ctypes.data_as(ctypes.c_void_p),
+                 plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
                  theta.data_ptr(), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
     return theta[: len(free)], loss, iters
 
