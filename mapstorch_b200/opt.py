@@ -449,6 +449,31 @@ MapFitPlan.make_graph = _make_graph
 MapFitPlan.to_host = _to_host
 
 
+_PLAN_CACHE = {}
+
+
+def _cached_plan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info, detector_type,
+                 escape_factor):
+    """Plans depend only on the global parameters; keep the last few (a dataset is usually fitted slab
+    by slab, or map after map, with the same calibration)."""
+    try:
+        key = (tuple(int(v) for v in energy_range), tuple(elements_to_fit),
+               tuple(sorted((k, float(v)) for k, v in params.items() if k in default_param_vals)),
+               None if indices is None else np.asarray(indices).tobytes(), bool(use_snip), id(e_consts), id(elem_info),
+               detector_type, float(escape_factor), torch.cuda.current_device())
+    except (TypeError, ValueError):
+        key = None
+    if key is not None and key in _PLAN_CACHE:
+        return _PLAN_CACHE[key]
+    plan = MapFitPlan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info, detector_type,
+                      escape_factor)
+    if key is not None:
+        if len(_PLAN_CACHE) >= 8:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
 def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_param_vals=default_param_vals,
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
@@ -480,8 +505,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     if plan is None:
         params = dict(init_param_vals)
         params.update(fixed_param_vals)
-        plan = MapFitPlan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
-                          detector_type, escape_factor)
+        plan = _cached_plan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
+                            detector_type, escape_factor)
     if flat.device.type == "cuda":
         x = plan.fit(flat, nonneg=nonneg, engine=engine)
     else:
