@@ -66,12 +66,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename T, bool CACHE>
+template <typename T, bool CACHE, int NT>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefParams p) {
     extern __shared__ float dyn[];  // r[n_ch], d[n_theta][n_ch], cached basis values of every line window
     const MtRefineConfig &cfg = p.cfg;
-    const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines, NT = cfg.n_theta;
+    const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines;  // NT (free parameters) is a template argument
     float *r_s = dyn;
     float *d_s = dyn + n_ch;
     float *b_s = dyn + (size_t)n_ch * (1 + NT);  // unit-amplitude line values, filled by B1, reused by B2
@@ -438,10 +438,20 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     const char *env = getenv("MT_REFINE_CACHE");
     const bool cache = env && atoi(env) != 0 && smem_cache <= 200 * 1024;
     const size_t smem = cache ? smem_cache : smem_base;
-#define MT_LAUNCH_REFINE(T, C)                                                                                        \
-    do {                                                                                                               \
-        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        refine_kernel<T, C><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                         \
+#define MT_LAUNCH_REFINE_NT(T, C, N)                                                                                    \
+    do {                                                                                                                 \
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        refine_kernel<T, C, N><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                        \
+    } while (0)
+#define MT_LAUNCH_REFINE(T, C)                                  \
+    do {                                                        \
+        switch (cfg.n_theta) {                                  \
+            case 0: MT_LAUNCH_REFINE_NT(T, C, 0); break;        \
+            case 1: MT_LAUNCH_REFINE_NT(T, C, 1); break;        \
+            case 2: MT_LAUNCH_REFINE_NT(T, C, 2); break;        \
+            case 3: MT_LAUNCH_REFINE_NT(T, C, 3); break;        \
+            default: MT_LAUNCH_REFINE_NT(T, C, 4); break;       \
+        }                                                       \
     } while (0)
     if (dtype == MT_DTYPE_F32) {
         if (cache) MT_LAUNCH_REFINE(float, true); else MT_LAUNCH_REFINE(float, false);

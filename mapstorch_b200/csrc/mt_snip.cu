@@ -33,6 +33,17 @@ __device__ __forceinline__ float clip(float a, float b, float c) {
     return fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), c);
 }
 
+// 128-bit shared-memory accesses with explicit 32-bit addresses (keeps the address arithmetic of the
+// pass loop to one shift + add per neighbour)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // KCH channels per thread (n_ch <= kSnipThreads * KCH); 4 pixels per CTA.
 template <typename T, int KCH>
 __global__ void __launch_bounds__(kSnipThreads, (KCH <= 4 ? 3 : (KCH <= 8 ? 2 : 1)))
@@ -101,37 +112,35 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
     }
 
     // ---- clipping passes (bkg.py:53-66, 104-112), Jacobi style ------------------------------
-    uint32_t tab[KCH], tab_next[KCH];
+    uint32_t tab[KCH];
 #pragma unroll
     for (int k = 0; k < KCH; ++k) {
         const int i = tid + k * kSnipThreads;
         tab[k] = (n_pass > 0 && i < n_ch) ? __ldg(lohi + i) : 0u;
     }
     __syncthreads();
+    const uint32_t sb_base = static_cast<uint32_t>(__cvta_generic_to_shared(sb));
     for (int pass = 0; pass < n_pass; ++pass) {
         const uint32_t *next = lohi + (long long)(pass + 1) * n_ch;
+        const bool more = pass + 1 < n_pass;
+        // channels past n_ch carry index word 0: they read channel 0 and their result is never stored
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
             const int i = tid + k * kSnipThreads;
-            tab_next[k] = (pass + 1 < n_pass && i < n_ch) ? __ldg(next + i) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < KCH; ++k) {
-            const int i = tid + k * kSnipThreads;
-            if (i < n_ch) {
-                const float4 a = sb[tab[k] & 0xffffu], b = sb[tab[k] >> 16];
-                cur[k].x = clip(a.x, b.x, cur[k].x);
-                cur[k].y = clip(a.y, b.y, cur[k].y);
-                cur[k].z = clip(a.z, b.z, cur[k].z);
-                cur[k].w = clip(a.w, b.w, cur[k].w);
-            }
+            const float4 a = lds128(sb_base + ((tab[k] & 0xffffu) << 4));
+            const float4 b = lds128(sb_base + ((tab[k] >> 12) & 0xffff0u));
+            // this word is consumed: fetch the next pass's (from L2) behind the rest of the pass
+            tab[k] = (more && i < n_ch) ? __ldg(next + i) : 0u;
+            cur[k].x = clip(a.x, b.x, cur[k].x);
+            cur[k].y = clip(a.y, b.y, cur[k].y);
+            cur[k].z = clip(a.z, b.z, cur[k].z);
+            cur[k].w = clip(a.w, b.w, cur[k].w);
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
             const int i = tid + k * kSnipThreads;
-            if (i < n_ch) sb[i] = cur[k];
-            tab[k] = tab_next[k];
+            if (i < n_ch) sts128(sb_base + ((uint32_t)i << 4), cur[k]);
         }
         __syncthreads();
     }
