@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true", help="gather the maps with NCCL instead of peer-memory stores")
+    ap.add_argument("--gather", default="owner", choices=["owner", "gather", "allgather"],
+                    help="peer-memory exchange of the element maps: every component assembled on its owner GPU "
+                         "(balanced all-to-all, default), everything on rank 0, or everything everywhere")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     # libraries (NCCL's version banner) write to fd 1; keep stdout for the ONE JSON line
@@ -240,7 +243,7 @@ def main():
     if world > 1 and not w["snip"] and not args.nccl_gather:
         try:
             from mapstorch_b200.dist import PeerMaps
-            peer_maps = PeerMaps(n_comp, total_rows, w["width"])
+            peer_maps = PeerMaps(n_comp, total_rows, w["width"], mode=args.gather)
         except Exception as exc:  # pragma: no cover - needs symmetric memory support
             print(f"bench: peer-memory maps unavailable ({exc}); gathering with NCCL", file=sys.stderr)
     graph = None
@@ -254,7 +257,7 @@ def main():
 
     def step(gather=True, eager=False):
         if peer_maps is not None and gather:
-            # fused: the fit kernels store the amplitudes into rank 0's map buffer over NVLink
+            # fused: the fit kernels store the amplitudes into the destination GPUs' map buffers over NVLink
             plan.fit(flat, out=peer_maps.local, peers=peer_maps.peers)
             peer_maps.barrier()
             return peer_maps.full
@@ -377,8 +380,10 @@ def main():
                            "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
                            "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
                            "step": "fit of the resident shard (contraction + non-negative fix-up)" +
-                                   ("" if world == 1 else " + element maps gathered on rank 0 by the fit kernels' own stores "
-                                    f"(NVLink peer stores, mode {peer_maps.mode}) + barrier" if peer_maps is not None
+                                   ("" if world == 1 else " + element maps assembled over NVLink by the fit kernels' own peer stores "
+                                    + {"owner": "(every component's full map on its owner GPU: balanced all-to-all)",
+                                       "gather": "(all maps on rank 0)", "allgather": "(all maps on every GPU)"}[peer_maps.mode]
+                                    + " + barrier" if peer_maps is not None
                                     else " + NCCL all-gather of the element maps")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graph is not None,
                 "ms_per_step_eager_launch": ms_eager / args.steps, "roofline": roofline, "cpu_baseline": cb,

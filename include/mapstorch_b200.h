@@ -68,11 +68,17 @@ typedef struct MtTerm {
  * pointers address buffers with the same layout as x_dev (torch symmetric memory).  This fuses the
  * all-gather of the maps into the epilogue of the fit. */
 #define MT_MAX_PEERS 8
+#define MT_MAX_OWNED 32
 typedef struct MtPeers {
     int32_t n_peers;
-    int32_t reserved;
+    int32_t n_owned; /* > 0: per-component destinations below are used (element-major x, n_comp <= 32) */
     float *peer[MT_MAX_PEERS];
     float *multicast;
+    /* "component owner" exchange: component e of pixel p is additionally stored to owner_row[e][p]
+     * (NULL: no extra store), a row of the buffer of the GPU that assembles the full map of e.  Every GPU
+     * then receives only its own components from the others: a balanced all-to-all, (N-1)/N of the map
+     * bytes per GPU instead of N-1 times at a single root. */
+    float *owner_row[MT_MAX_OWNED];
 } MtPeers;
 
 int mt_abi_version(void);

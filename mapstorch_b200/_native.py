@@ -46,8 +46,8 @@ class MtRefineConfig(ctypes.Structure):
 
 
 class MtPeers(ctypes.Structure):
-    _fields_ = [("n_peers", ctypes.c_int32), ("reserved", ctypes.c_int32), ("peer", ctypes.c_void_p * 8),
-                ("multicast", ctypes.c_void_p)]
+    _fields_ = [("n_peers", ctypes.c_int32), ("n_owned", ctypes.c_int32), ("peer", ctypes.c_void_p * 8),
+                ("multicast", ctypes.c_void_p), ("owner_row", ctypes.c_void_p * 32)]
 
 
 THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3}

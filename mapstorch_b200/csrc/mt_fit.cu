@@ -327,6 +327,12 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                             if (e < p.n_comp) {
                                 const long long at = (long long)e * p.ld_x + px;
                                 p.x[at] = xv[mt][e];
+                                if (p.peers.n_owned > 0) {
+                                    // component-owner exchange: this pixel's value goes to the GPU that
+                                    // assembles the map of component e (its row starts at this rank's offset)
+                                    float *row = p.peers.owner_row[e];
+                                    if (row) row[px] = xv[mt][e];
+                                }
                                 for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = xv[mt][e];
                                 if (p.peers.multicast)
                                     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
@@ -598,6 +604,8 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     if (peers_host) {
         MT_REQUIRE(peers_host->n_peers >= 0 && peers_host->n_peers <= MT_MAX_PEERS, "mt_fit_contract: n_peers=%d",
                    peers_host->n_peers);
+        MT_REQUIRE(peers_host->n_owned == 0 || (hinv32_dev && n_comp <= MT_MAX_OWNED),
+                   "mt_fit_contract: per-component destinations need the in-epilogue fix-up path (n_comp <= 32)");
         p.peers = *peers_host;
     }
     p.x = x_dev;

@@ -335,6 +335,7 @@ nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ 
             const float out = active ? 0.f : (float)fmax(xs, 0.0);
             const long long at = (long long)lane * ld_x + px;
             x[at] = out;
+            if (peers.n_owned > 0 && peers.owner_row[lane]) peers.owner_row[lane][px] = out;
             for (int k = 0; k < peers.n_peers; ++k) peers.peer[k][at] = out;
             if (peers.multicast)
                 asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.multicast + at), "f"(out) : "memory");

@@ -74,8 +74,13 @@ class PeerMaps:
     the contraction is still streaming -- the gather of SURVEY.md 8e without a separate collective;
     ``barrier()`` then orders the remote stores before anybody reads ``maps.full``.
 
+    mode "owner"     : component e is assembled on rank e % world (its "owner"): every rank stores its
+                       pixels of component e into the owner's buffer, a balanced all-to-all in which
+                       each GPU receives (world-1)/world of ONE share of the maps instead of world-1
+                       shares at a single root.  ``owned`` lists this rank's components, ``full`` is
+                       [ceil(E/world), P_total] with row j = component owned[j].
     mode "gather"    : every rank stores into rank `root`'s buffer (one peer store per value);
-                       only the root ends up with the full maps.  Measured best on 8 GPUs.
+                       only the root ends up with the full maps (root inbound bound on 8 GPUs).
     mode "allgather" : every rank stores into all other ranks' buffers (world-1 peer stores).
     mode "multicast" : one store to the NVSwitch multicast mapping reaches every rank.  Cheap for
                        the coalesced epilogue stores, slow for the scattered fix-up stores, and
@@ -92,7 +97,16 @@ class PeerMaps:
         self.layout, self.n_comp, self.mode, self.root = layout, n_comp, mode, root
         device = torch.device("cuda", torch.cuda.current_device())
         r0, r1 = shard_rows(n_rows, self.rank, self.world)
-        if layout == "pe":
+        self.owned = list(range(n_comp))
+        if mode == "owner":
+            if layout != "ep" or n_comp > 32:
+                raise NotImplementedError("owner mode: element-major layout, at most 32 components")
+            n_rows_own = -(-n_comp // self.world)
+            self.owned = [e for e in range(n_comp) if e % self.world == self.rank]
+            self.full = symm_mem.empty((n_rows_own, n_rows * width), dtype=torch.float32, device=device)
+            self.local = torch.zeros((n_comp, (r1 - r0) * width), dtype=torch.float32, device=device)
+            offset = 4 * r0 * width
+        elif layout == "pe":
             e_pad = e_pad or -(-n_comp // 16) * 16
             self.full = symm_mem.empty((n_rows * width, e_pad), dtype=torch.float32, device=device)
             self.local = self.full[r0 * width: r1 * width]
@@ -107,7 +121,14 @@ class PeerMaps:
         self.peers.n_peers = 0
         self.peers.multicast = None
         self.multicast = False
-        if mode == "multicast":
+        self.peers.n_owned = 0
+        if mode == "owner":
+            self.peers.n_owned = n_comp
+            row_bytes = 4 * n_rows * width
+            for e in range(n_comp):
+                owner, slot = e % self.world, e // self.world
+                self.peers.owner_row[e] = int(self.handle.buffer_ptrs[owner]) + slot * row_bytes + offset
+        elif mode == "multicast":
             mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
             if not mc:
                 raise RuntimeError("this system has no NVLink multicast support")
@@ -154,7 +175,7 @@ class PeerMaps:
             main.wait_event(joined)
 
     def has_full_maps(self):
-        return self.mode != "gather" or self.rank == self.root
+        return self.mode in ("allgather", "multicast") or (self.mode == "gather" and self.rank == self.root)
 
     def component(self, index, n_rows, width):
         """[n_rows, width] map of one component (a strided view for the pixel-major layout)."""

@@ -100,11 +100,13 @@ def _shift_peers(peers, n_px, px_stride=1):
     if peers is None or n_px == 0:
         return peers
     moved = _native.MtPeers()
-    moved.n_peers = peers.n_peers
+    moved.n_peers, moved.n_owned = peers.n_peers, peers.n_owned
     step = 4 * n_px * px_stride
     for k in range(peers.n_peers):
         moved.peer[k] = peers.peer[k] + step
     moved.multicast = peers.multicast + step if peers.multicast else None
+    for e in range(peers.n_owned):
+        moved.owner_row[e] = peers.owner_row[e] + 4 * n_px if peers.owner_row[e] else None
     return moved
 
 
