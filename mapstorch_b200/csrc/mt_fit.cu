@@ -47,6 +47,7 @@ struct FitParams {
     int *neg_count;
     int pixel_major;      // x layout: 0 = x[e*ld_x + p], 1 = x[p*ld_x + e]
     const float *hinv32;  // optional G^-1 (fp32 [n_comp][n_comp]): non-negative fix-up in the epilogue
+    int reg_path;         // epilogue keeps the whole pixel in registers (e_pad <= 32, element-major)
     MtPeers peers;        // extra destinations on other GPUs (n_peers == 0 and multicast == NULL: none)
     float *x;
     const float *colscale;
@@ -282,7 +283,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            if (p.hinv32 != nullptr) {
+            if (p.reg_path) {
                 // ---- whole pixels in registers: drain TMEM for both sub-tiles first and hand the
                 // accumulator back to the MMA warp, then fix small zero sets and store ----
                 float xv[M_TILES][32];
@@ -319,8 +320,8 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                     bool any_neg = false;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) any_neg |= (xv[mt][e] < 0.f);
-                    bool negative = false;
-                    if (any_neg && px < p.n_px) negative = !fixup_small(xv[mt], p.n_comp, hs);
+                    bool negative = any_neg && px < p.n_px;
+                    if (negative && p.hinv32 != nullptr) negative = !fixup_small(xv[mt], p.n_comp, hs);
                     if (px < p.n_px) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
@@ -342,7 +343,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                         }
                     }
                     const unsigned ballot = __ballot_sync(0xffffffffu, negative);
-                    if (ballot != 0u) {
+                    if (ballot != 0u && p.neg_list != nullptr) {
                         int base = 0;
                         if (lane == 0) base = atomicAdd(p.neg_count, __popc(ballot));
                         base = __shfl_sync(0xffffffffu, base, 0);
@@ -599,13 +600,14 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
                    "mt_fit_contract: the in-epilogue fix-up needs e_pad <= 32, element-major x and a fallback list");
         p.hinv32 = hinv32_dev;
     }
+    p.reg_path = (hinv32_dev != nullptr) || (peers_host && peers_host->n_owned > 0);
     p.neg_list = neg_list_dev;
     p.neg_count = neg_count_dev;
     if (peers_host) {
         MT_REQUIRE(peers_host->n_peers >= 0 && peers_host->n_peers <= MT_MAX_PEERS, "mt_fit_contract: n_peers=%d",
                    peers_host->n_peers);
-        MT_REQUIRE(peers_host->n_owned == 0 || (hinv32_dev && n_comp <= MT_MAX_OWNED),
-                   "mt_fit_contract: per-component destinations need the in-epilogue fix-up path (n_comp <= 32)");
+        MT_REQUIRE(peers_host->n_owned == 0 || (e_pad <= 32 && x_layout == MT_X_ELEMENT_MAJOR),
+                   "mt_fit_contract: per-component destinations need n_comp <= 32 and element-major x");
         p.peers = *peers_host;
     }
     p.x = x_dev;

@@ -117,6 +117,8 @@ class PeerMaps:
             offset = 4 * r0 * width
         self.full.zero_()
         self.handle = symm_mem.rendezvous(self.full, group)
+        # every rank's zero-fill must have completed before any peer starts storing into the buffer
+        self.handle.barrier()
         self.peers = _native.MtPeers()
         self.peers.n_peers = 0
         self.peers.multicast = None
