@@ -328,17 +328,22 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                             if (e < p.n_comp) {
                                 const long long at = (long long)e * p.ld_x + px;
                                 p.x[at] = xv[mt][e];
-                                if (p.peers.n_owned > 0) {
-                                    // component-owner exchange: this pixel's value goes to the GPU that
-                                    // assembles the map of component e (its row starts at this rank's offset)
-                                    float *row = p.peers.owner_row[e];
-                                    if (row) row[px] = xv[mt][e];
+                                // Remote copies only of FINAL values: a pixel that still goes to the general
+                                // solver is pushed by that kernel, so no destination ever sees two stores
+                                // to the same address from different kernels.
+                                if (!negative || p.neg_list == nullptr) {  // (no list: no solver follows)
+                                    if (p.peers.n_owned > 0) {
+                                        // component-owner exchange: the value goes to the GPU that assembles the
+                                        // map of component e (row pointer already offset to this rank's pixels)
+                                        float *row = p.peers.owner_row[e];
+                                        if (row) row[px] = xv[mt][e];
+                                    }
+                                    for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = xv[mt][e];
+                                    if (p.peers.multicast)
+                                        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
+                                                     "f"(xv[mt][e])
+                                                     : "memory");
                                 }
-                                for (int k = 0; k < p.peers.n_peers; ++k) p.peers.peer[k][at] = xv[mt][e];
-                                if (p.peers.multicast)
-                                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peers.multicast + at),
-                                                 "f"(xv[mt][e])
-                                                 : "memory");
                             }
                         }
                     }
