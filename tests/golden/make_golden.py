@@ -245,6 +245,69 @@ def gen_fit(out, quick):
         print(tag, "final loss", trace[-1], flush=True)
 
 
+def gen_random_tables(out, n_sets=40):
+    """Index arithmetic under randomly perturbed calibrations: CRC32 of every SNIP gather table, pass
+    counts, escape bins, amplitude-guess windows and peak ranges, all computed by the reference's own
+    code (bkg.py:57-62,83-112; map.py:142-146; opt.py:74-90; util.py:87-108)."""
+    import zlib
+    from mapstorch.constant import M_SQRT2
+
+    rng = np.random.default_rng(2024)
+    base = params_a()
+    recs = []
+    elems = ["Si", "Ca", "Fe", "Zn", "Au_L", "Pt_M", "COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+    for i in range(n_sets):
+        n_ch = int(rng.choice([1024, 2048, 4096]))
+        slope = float(rng.uniform(0.8, 1.25)) * (0.012 * 2048 / n_ch)
+        p = dict(base, ENERGY_OFFSET=float(rng.uniform(-0.05, 0.05)), ENERGY_SLOPE=slope,
+                 ENERGY_QUADRATIC=float(rng.uniform(-4e-8, 4e-8)) * (2048 / n_ch) ** 2,
+                 FWHM_OFFSET=float(rng.uniform(0.06, 0.12)), FWHM_FANOPRIME=float(rng.uniform(1e-4, 3e-4)),
+                 SNIP_WIDTH=float(rng.uniform(0.3, 1.5)), COHERENT_SCT_ENERGY=float(rng.uniform(9.0, 18.0)),
+                 COMPTON_ANGLE=float(rng.uniform(80.0, 130.0)))
+        er0 = int(rng.integers(0, 80))
+        er1 = int(n_ch - 1 - rng.integers(0, 200))
+        t = tens(p)
+        n = er1 - er0 + 1
+        local = torch.arange(n, dtype=torch.float32)
+        gidx = local + er0
+        energy = t["ENERGY_OFFSET"] + (t["ENERGY_SLOPE"] * gidx) + (t["ENERGY_QUADRATIC"] * (gidx ** 2))
+        sig = torch.clamp((t["FWHM_OFFSET"] / 2.3548) ** 2 + energy * 2.96 * t["FWHM_FANOPRIME"], min=0.0)
+        w = t["SNIP_WIDTH"] * 2.35 * torch.sqrt(sig) / t["ENERGY_SLOPE"]
+        crc, n_pass = 0, 0
+
+        def crc_of(w, crc):
+            lo = torch.clamp(local - w, 0, n - 1).to(torch.int64)
+            hi = torch.clamp(local + w, 0, n - 1).to(torch.int64)
+            return zlib.crc32((lo | (hi << 16)).numpy().astype(np.uint32).tobytes(), crc)
+
+        for _ in range(2):
+            crc = crc_of(w, crc)
+            n_pass += 1
+        while torch.max(w).item() >= 0.5:
+            crc = crc_of(w, crc)
+            n_pass += 1
+            w = w / M_SQRT2
+        ev = ev_of(t, (er0, er1))
+        delta_e = torch.mean(ev[1:] - ev[:-1]).item()
+        bins = [int(round(1.73998 / delta_e)), int(round(9.886 / delta_e))]
+        spec = np.zeros(n_ch, dtype=np.float32)
+        wins = []
+        for e in elems:
+            # replay opt.py:74-90 through the reference function on a ramp spectrum: the mean identifies the window
+            ramp = np.arange(n_ch, dtype=np.float64)
+            g = ropt.init_elem_amps(e, ramp, p["COHERENT_SCT_ENERGY"], p["ENERGY_OFFSET"], p["ENERGY_SLOPE"],
+                                    compton_angle=p["COMPTON_ANGLE"])
+            wins.append(float(g))
+        rr = rutil.get_peak_ranges(elems, p["COHERENT_SCT_ENERGY"], p["COMPTON_ANGLE"], p["ENERGY_OFFSET"],
+                                   p["ENERGY_SLOPE"], p["ENERGY_QUADRATIC"], (er0, er1))
+        rcrc = zlib.crc32(np.array(list(rr.values()), dtype=np.int64).tobytes())
+        recs.append([n_ch, er0, er1, n_pass, crc, bins[0], bins[1], rcrc] + wins +
+                    [p[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET",
+                                    "FWHM_FANOPRIME", "COHERENT_SCT_ENERGY", "COMPTON_ANGLE")])
+    out["rt_records"] = np.array(recs, dtype=np.float64)
+    out["rt_elems"] = np.array(elems)
+
+
 def gen_refine(out, n_iter=3000):
     """BASELINE config 4 analogue: per-spectrum fit with ENERGY_OFFSET and FWHM_OFFSET free
     (fit_spec(fitting_params=[...], tune_params=True), opt.py:201,119), run long enough to converge,
@@ -293,7 +356,7 @@ def main():
     ap.add_argument("--quick-fit", action="store_true")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
-    jobs = {"model": gen_model, "snip": gen_snip, "host": gen_host}
+    jobs = {"model": gen_model, "snip": gen_snip, "host": gen_host, "tables": gen_random_tables}
     for name, fn in jobs.items():
         if args.only and args.only != name:
             continue

@@ -127,3 +127,35 @@ def test_digit_planes_hold_30_bits_in_fp16_exact_integers():
     peak[peak == 0] = 1
     assert (np.abs(rebuilt - w) / peak).max() <= 2.0 ** -29
     assert np.all(np.log2(scale) == np.rint(np.log2(scale)))  # power-of-two row scales: exact
+
+
+def test_index_tables_under_random_calibrations():
+    """40 randomly perturbed calibrations (tables_golden.npz, computed by the reference): SNIP gather tables
+    (CRC32 over all passes), pass counts, escape bins, amplitude-guess windows and peak ranges are exact --
+    for the product's table compiler AND for the oracle restatement."""
+    import zlib
+    from conftest import GOLDEN
+    from mapstorch_b200.default import default_param_vals
+
+    g = np.load(GOLDEN / "tables_golden.npz")
+    elems = [str(e) for e in g["rt_elems"]]
+    for rec in g["rt_records"]:
+        n_ch, er0, er1, n_pass, crc, bin_si, bin_ge, rcrc = (int(v) for v in rec[:8])
+        wins = rec[8: 8 + len(elems)]
+        off, slope, quad, snipw, fwhm, fano, e0, angle = rec[8 + len(elems):]
+        n = er1 - er0 + 1
+        args = [torch.tensor(float(v)) for v in (off, slope, quad, snipw, fwhm, fano)]
+        tab = tables.snip_tables(n, er0, *args)
+        assert tab.shape[0] == n_pass and zlib.crc32(tab.tobytes()) == crc
+        passes = mo.snip_pass_tables(n, er0, off, slope, quad, snipw, fwhm, fano)
+        assert len(passes) == n_pass
+        assert zlib.crc32(np.stack([(lo | (hi << 16)).astype(np.uint32) for lo, hi in passes]).tobytes()) == crc
+        p = dict(default_param_vals, ENERGY_OFFSET=off, ENERGY_SLOPE=slope, ENERGY_QUADRATIC=quad)
+        ev = tables.energy_axis(p, (er0, er1))
+        for det, want in (("Si", bin_si), ("Ge", bin_ge)):
+            assert tables.escape_bins(ev, det) == (want if want < n else 0)
+        ramp = np.arange(n_ch, dtype=np.float64)
+        got = [float(opt.init_elem_amps(e, ramp, e0, off, slope, compton_angle=angle)) for e in elems]
+        assert np.array_equal(np.array(got), wins)
+        rr = util.get_peak_ranges(elems, e0, angle, off, slope, quad, (er0, er1))
+        assert zlib.crc32(np.array(list(rr.values()), dtype=np.int64).tobytes()) == rcrc
