@@ -28,6 +28,7 @@ from mapstorch_b200.default import (
 
 DIGIT_BITS = 10    # bits per operand plane of the pseudo-inverse (|digit| <= 512: exact in fp16 / tf32)
 N_PLANES = 3       # 30 bits in total
+MAX_GROUP = 80     # components per tensor-core tile: N = N_PLANES * e_pad <= 256
 PLANE_RATIO = 2.0 ** -DIGIT_BITS
 SNIP_CHUNK_PX = 32768
 
@@ -144,10 +145,12 @@ class MapFitPlan:
         self.gram, self.hinv = gram, hinv
         self.pinv = hinv @ bl  # [E_live, C]: x = pinv @ (y - bkg)
         self.n_live = len(self.live)
-        self.e_pad = max(16, -(-self.n_live // 16) * 16)  # N = N_PLANES * e_pad must be a multiple of 16
-        if N_PLANES * self.e_pad > 256:
-            raise _native.NativeError(-3, f"{self.n_live} fitted components exceed the {256 // N_PLANES} one "
-                                          "tensor-core tile holds (split the element list)")
+        # N = N_PLANES * e_pad must be a multiple of 16 and <= 256: one tensor-core tile holds 80 components;
+        # longer lists (the 93 default components at high incident energy) are contracted in groups
+        self.groups = [(g0, min(g0 + MAX_GROUP, self.n_live)) for g0 in range(0, self.n_live, MAX_GROUP)]
+        self.e_pad = max(16, -(-min(self.n_live, MAX_GROUP) // 16) * 16)
+        if self.n_live > 104:
+            raise _native.NativeError(-3, f"{self.n_live} fitted components exceed the 104 the non-negative solver holds")
         self.gram_dev = torch.from_numpy(gram).cuda()
         self.hinv_dev = torch.from_numpy(hinv).cuda()
         self._packs = {}
@@ -169,19 +172,21 @@ class MapFitPlan:
                     "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")))
 
     # -- operand packs, cached per (dtype, layout) ------------------------------------------------
-    def _pack(self, kind, n_cols, col0, repeat):
-        """wpack [N_PLANES*e_pad, n_cols]: digit planes of pinv at columns [col0, col0+n_ch)
-        (`repeat` copies back to back), in the operand dtype of the volume."""
-        key = (kind, n_cols, col0, repeat)
+    def _pack(self, kind, n_cols, col0, repeat, group=0):
+        """(wpack [N_PLANES*e_pad, n_cols], colscale, e_pad) of one component group: digit planes of its
+        pinv rows at columns [col0, col0+n_ch) (`repeat` copies back to back), in the volume's operand dtype."""
+        key = (kind, n_cols, col0, repeat, group)
         if key not in self._packs:
-            scale, planes = digit_planes(self.pinv)
+            g0, g1 = self.groups[group]
+            n, e_pad = g1 - g0, max(16, -(-(g1 - g0) // 16) * 16)
+            scale, planes = digit_planes(self.pinv[g0:g1])
             dt = np.float16 if kind == "f16" else np.float32
-            pack = np.zeros((N_PLANES * self.e_pad, n_cols), dtype=dt)
+            pack = np.zeros((N_PLANES * e_pad, n_cols), dtype=dt)
             for r in range(repeat):
                 c = col0 + r * self.n_ch
                 for d in range(N_PLANES):
-                    pack[d * self.e_pad: d * self.e_pad + self.n_live, c: c + self.n_ch] = planes[d]
-            self._packs[key] = (torch.from_numpy(pack).cuda(), torch.from_numpy(scale).cuda())
+                    pack[d * e_pad: d * e_pad + n, c: c + self.n_ch] = planes[d]
+            self._packs[key] = (torch.from_numpy(pack).cuda(), torch.from_numpy(scale).cuda(), e_pad)
         return self._packs[key]
 
     def _pinv_f32(self, n_cols, col0):
@@ -234,15 +239,19 @@ class MapFitPlan:
         self._last_engine = engine
         if engine == "tensor":
             kind = "f16" if spec2d.dtype == torch.float16 else "tf32"
-            pack, scale = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat)
-            _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
-                         n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), self.e_pad,
-                         self.n_live, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), *self._x_args(x),
-                         int(px_offset), neg[0].data_ptr() if neg is not None else None,
-                         neg[1].data_ptr() if neg is not None else None,
-                         self._hinv32().data_ptr() if (neg is not None and self.epilogue_fixup and self.e_pad <= 32
-                                                       and not self._pixel_major) else None,
-                         ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
+            if len(self.groups) > 1 and (self._pixel_major or peers is not None):
+                raise NotImplementedError("more than 80 components: element-major output without peer stores only")
+            for gi, (g0, g1) in enumerate(self.groups):
+                pack, scale, e_pad = self._pack(kind, -(-n_ch_total // 8) * 8, col0, repeat, gi)
+                xg = x if len(self.groups) == 1 else x[g0:g1]
+                _native.call("mt_fit_contract", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, ld,
+                             n_ch_total, int(k_begin), int(k_end), pack.data_ptr(), pack.stride(0), e_pad,
+                             g1 - g0, N_PLANES, scale.data_ptr(), float(PLANE_RATIO), *self._x_args(xg),
+                             int(px_offset), neg[0].data_ptr() if neg is not None else None,
+                             neg[1].data_ptr() if neg is not None else None,
+                             self._hinv32().data_ptr() if (neg is not None and self.epilogue_fixup and self.e_pad <= 32
+                                                           and not self._pixel_major) else None,
+                             ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
         elif engine == "simt":
             if peers is not None:
                 raise _native.NativeError(-3, "peer-memory destinations need the tensor-core path")
@@ -259,7 +268,7 @@ class MapFitPlan:
         n_px = spec2d.shape[0]
         # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
         neg = None
-        if nonneg and engine == "tensor" and n_px:
+        if nonneg and engine == "tensor" and n_px and len(self.groups) == 1:
             neg = self._neg_buffers(n_px)
             neg[1].zero_()
         wide = False

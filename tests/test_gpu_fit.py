@@ -258,3 +258,34 @@ def test_pixel_major_layout_is_the_same_fit():
     pe2 = plan2.fit(torch.from_numpy(y2).cuda(), layout="pe", exact_counts=True)
     assert pe2.shape == (130, 16) and float(pe2[:, 12:].abs().max()) == 0.0
     assert torch.equal(pe2[:, :12].T, plan2.fit(torch.from_numpy(y2).cuda(), exact_counts=True))
+
+
+def test_all_default_components_at_high_incident_energy():
+    """85 live components at 17.5 keV: more than one tensor-core tile (80) -> contracted in two groups,
+    non-negative solve by the general kernel.  Checked against float64 NNLS on the oracle basis."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_fitting_elems, default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=17.5)
+    er = (0, 2047)
+    elems = [e for e in default_fitting_elems if e not in ("COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE")]
+    plan = opt.MapFitPlan(er, elems, p, use_snip=False)
+    assert plan.n_live == 85 and len(plan.groups) == 2 and len(plan.names) == 93
+    B, names = mo.basis(p, er, elems)
+    assert names == plan.names
+    rng = np.random.default_rng(12)
+    live = np.abs(B).sum(axis=0) > 0
+    amps = np.where(live, 10.0 ** rng.uniform(1.0, 3.0, size=(24, len(names))), 0.0)
+    y = rng.poisson(amps @ B.astype(np.float64).T).astype(np.float32)
+    x = plan.fit(torch.from_numpy(y).cuda(), nonneg=False).cpu().numpy().T
+    ref = mo.fit_lstsq(y, B[:, live])
+    assert (np.abs(x[:, live] - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() <= 2e-5  # cond(G) ~ 9e3 here
+    assert not x[:, ~live].any()
+    xn = plan.fit(torch.from_numpy(y).cuda(), nonneg=True).cpu().numpy().T
+    refn = mo.fit_nnls(y, B[:, live])
+    assert (xn >= 0).all()
+    assert (np.abs(xn[:, live] - refn) / refn.max(axis=1, keepdims=True)).max() <= 1e-3
+    r_mine = ((y - xn @ B.T.astype(np.float64)) ** 2).sum(axis=1)
+    r_ref = ((y - refn @ B[:, live].T.astype(np.float64)) ** 2).sum(axis=1)
+    assert np.all(r_mine <= r_ref * (1 + 1e-4))
