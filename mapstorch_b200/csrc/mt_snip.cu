@@ -82,19 +82,26 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
         const int i = tid + k * kSnipThreads;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n_ch) {
-            for (int j = -half; j <= half; ++j) {
-                const int q = i + j;
-                if (q >= 0 && q < n_ch) {
-                    const float4 v = sb[q];
+            if (boxcar == 5 && i >= 2 && i + 2 < n_ch) {
+                // the default window, away from the edges: five unconditional 128-bit loads
+#pragma unroll
+                for (int j = -2; j <= 2; ++j) {
+                    const float4 v = sb[i + j];
                     acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, wgt));
                     acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, wgt));
                     acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, wgt));
                     acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, wgt));
-                } else {  // the zero padding still takes part in the sum (adds +0)
-                    acc.x = __fadd_rn(acc.x, 0.f);
-                    acc.y = __fadd_rn(acc.y, 0.f);
-                    acc.z = __fadd_rn(acc.z, 0.f);
-                    acc.w = __fadd_rn(acc.w, 0.f);
+                }
+            } else {
+                for (int j = -half; j <= half; ++j) {
+                    const int q = i + j;
+                    if (q >= 0 && q < n_ch) {  // zero padding contributes +0
+                        const float4 v = sb[q];
+                        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, wgt));
+                        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, wgt));
+                        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, wgt));
+                        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, wgt));
+                    }
                 }
             }
             acc.x = finite_or_zero(log1pf(acc.x));
@@ -136,6 +143,7 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
             cur[k].z = clip(a.z, b.z, cur[k].z);
             cur[k].w = clip(a.w, b.w, cur[k].w);
         }
+        if (!more) break;  // the result of the last pass stays in registers
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
