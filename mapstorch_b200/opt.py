@@ -414,7 +414,13 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
     bufs = [torch.empty((chunk, n_ch), dtype=host2d.dtype, device="cuda") for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    for i, p0 in enumerate(range(0, n_px, chunk)):
+    # fp32 volumes without SNIP: the operand-exactness check (counts < 2048) must not stall the pipeline, so
+    # every slab is fitted optimistically, its maximum lands in a device flag, and the (rare) slabs that turn
+    # out to hold larger counts are redone through the exact split path after ONE synchronisation at the end
+    check = host2d.dtype == torch.float32 and not self.use_snip and engine == "tensor"
+    starts = list(range(0, n_px, chunk))
+    too_big = torch.zeros(len(starts), dtype=torch.bool, device="cuda") if check else None
+    for i, p0 in enumerate(starts):
         b, n = i & 1, min(chunk, n_px - p0)
         with torch.cuda.stream(copier):
             if i >= 2:
@@ -422,8 +428,17 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
             bufs[b][:n].copy_(host2d[p0: p0 + n], non_blocking=True)
             copied[b].record(copier)
         compute.wait_event(copied[b])
-        self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine)
+        if check:
+            too_big[i] = bufs[b][:n, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0
+        self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
+                 exact_counts=True if check else None)
         consumed[b].record(compute)
+    if check:
+        for i in torch.nonzero(too_big).flatten().tolist():
+            p0 = starts[i]
+            n = min(chunk, n_px - p0)
+            bufs[0][:n].copy_(host2d[p0: p0 + n])
+            self.fit(bufs[0][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine, exact_counts="split")
     for buf in bufs:
         buf.record_stream(compute)
     return out
@@ -527,15 +542,21 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         # per-pixel nonlinear refinement of peak-shape parameters + amplitudes (kernel K4)
         from mapstorch_b200.refine import refine_map
 
-        dev = flat if flat.device.type == "cuda" else flat.cuda()
-        bkg = None
-        if plan.use_snip:
-            p = plan.params
-            bkg = _bkg.snip_bkg(dev[:, plan.er[0]: plan.er[1] + 1], plan.er, *(torch.tensor(float(p[k])) for k in (
-                "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")),
-                device="cuda")
-        theta, loss, iters = refine_map(plan, dev, x, free=tuple(refine), bounds=refine_bounds, max_iter=refine_iters,
-                                        bkg=bkg)
+        # slab by slab, so that neither a host volume nor the SNIP background has to be resident as a whole
+        n_px = flat.shape[0]
+        theta = torch.empty((len(refine), n_px), dtype=torch.float32, device="cuda")
+        loss = torch.empty(n_px, dtype=torch.float32, device="cuda")
+        iters = torch.empty(n_px, dtype=torch.int32, device="cuda")
+        p = plan.params
+        snip_args = [torch.tensor(float(p[k])) for k in (
+            "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")]
+        for p0 in range(0, n_px, SNIP_CHUNK_PX):
+            p1 = min(p0 + SNIP_CHUNK_PX, n_px)
+            dev = flat[p0:p1] if flat.device.type == "cuda" else flat[p0:p1].cuda()
+            bkg = _bkg.snip_bkg(dev[:, plan.er[0]: plan.er[1] + 1], plan.er, *snip_args, device="cuda") if plan.use_snip else None
+            t, l, it = refine_map(plan, dev, x[:, p0:p1], free=tuple(refine), bounds=refine_bounds,
+                                  max_iter=refine_iters, bkg=bkg)
+            theta[:, p0:p1], loss[p0:p1], iters[p0:p1] = t, l, it
         extra = {name: theta[i] for i, name in enumerate(refine)}
         extra["loss"], extra["iterations"] = loss, iters
     if as_log10:

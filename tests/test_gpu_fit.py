@@ -227,6 +227,10 @@ def test_fp32_counts_above_2048_take_the_exact_split_path():
     # the unchecked direct path truncates operands: visibly worse, which is why the check exists
     bad = plan.fit(dev, nonneg=False, exact_counts=True).cpu().numpy().T
     assert (np.abs(bad - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() > 1e-5
+    # host volumes are streamed slab by slab; only the slab with large counts is redone exactly
+    mixed = np.concatenate([np.minimum(y, 100.0), y[:50]])
+    xh = plan.fit_host(torch.from_numpy(mixed), nonneg=False, chunk_px=128).cpu().numpy().T
+    check_against(xh, mo.fit_lstsq(mixed, B), 1e-4)
 
 
 def test_pixel_major_layout_is_the_same_fit():
