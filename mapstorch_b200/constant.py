@@ -304,3 +304,84 @@ def define_constants(info_elements, pileups=None, return_dict=True):
     if return_dict:
         return {rows[i, 0].name: rows[i] for i in range(rows.shape[0])}
     return rows, names
+
+
+def _literature_ratios(row, info, slots):
+    """reset the first len(slots) ratios of a row to yield / yield(first line)"""
+    first = info.xrf_abs_yield[slots[0][0]]
+    row[0].ratio = 1.0
+    for slot, (key, _, _) in zip(row[1:], slots[1:]):
+        slot.ratio = info.xrf_abs_yield[key] / first
+
+
+# which L sub-shell scales which slot (order of _L_SLOTS): factor index 0 = L1, 1 = L2, 2 = L3
+_L_SUBSHELL_OF_SLOT = (2, 2, 1, 2, 0, 0, 1, 0, 0, 0, 2, 1)
+
+
+def read_constants(filename, info_elements, pileups=None, return_dict=True):
+    """``define_constants`` plus the edits a MAPS override file asks for (constant.py:1815-1987).
+
+    Tags are matched un-stripped at the start of a line (indented lines are comments):
+    ``ELEMENTS_WITH_PILEUP`` appends pile-up rows, ``DETECTOR_MATERIAL`` selects the Si (1) or Ge (other)
+    absorption column as ``mu_fraction``, ``BRANCHING_FAMILY_ADJUSTMENT_L`` (name + 3 factors: L1, L2, L3)
+    resets an L row to the literature ratios and scales them per sub-shell,
+    ``BRANCHING_RATIO_ADJUSTMENT_L`` (name + 12 factors) and ``BRANCHING_RATIO_ADJUSTMENT_K`` (name + 4)
+    multiply the ratios slot by slot.  The two ``TAIL_*_ADJUST_SI`` tags raise AttributeError upstream
+    (attribute access on an object-array slice); they do here too rather than silently doing something
+    the reference never did."""
+    rows, names = define_constants(info_elements, pileups, False)
+    el_names = [e.name for e in info_elements]
+
+    def find_row(label):
+        hits = np.where(names == label)[0]
+        return int(hits[0]) if hits.size else None
+
+    def base_element(label):
+        # the reference cuts two characters off whatever name it is given (meant for the "_L" suffix)
+        return el_names.index(label[:-2]) if label[:-2] in el_names else -1
+
+    with open(str(filename), "rt") as fh:
+        for line in fh:
+            if ":" not in line:
+                continue
+            pieces = line.split(":")
+            tag, value = pieces[0], "".join(pieces[1:])
+            fields = [x.strip() for x in value.split(",")]
+            if tag == "ELEMENTS_WITH_PILEUP":
+                p_rows, p_names = define_pileup_constants(info_elements, fields)
+                rows = np.vstack((rows, p_rows))
+                names = np.append(names, p_names)
+            elif tag == "DETECTOR_MATERIAL":
+                column = "Si_mu" if int(value) == 1 else "Ge_mu"
+                for slot in rows.flat:
+                    slot.mu_fraction = getattr(slot, column)
+            elif tag == "BRANCHING_FAMILY_ADJUSTMENT_L":
+                ii = find_row(fields[0])
+                if ii is not None and len(fields) == 4:
+                    factors = [float(v) for v in fields[1:4]]
+                    j = base_element(fields[0])
+                    if j > 0:
+                        _literature_ratios(rows[ii], info_elements[j], _L_SLOTS)
+                        for slot, shell in zip(rows[ii], _L_SUBSHELL_OF_SLOT):
+                            slot.ratio *= factors[shell]
+            elif tag == "BRANCHING_RATIO_ADJUSTMENT_L":
+                ii = find_row(fields[0])
+                if ii is not None and len(fields) >= 13:
+                    for jj in range(12):
+                        rows[ii, jj].ratio *= float(fields[jj + 1])
+            elif tag == "BRANCHING_RATIO_ADJUSTMENT_K":
+                ii = find_row(fields[0])
+                if ii is not None and len(fields) == 5:
+                    j = base_element(fields[0])
+                    if j > 0:
+                        _literature_ratios(rows[ii], info_elements[j], _K_SLOTS)
+                    for jj in range(4):
+                        rows[ii, jj].ratio *= float(fields[jj + 1])
+            elif tag in ("TAIL_FRACTION_ADJUST_SI", "TAIL_WIDTH_ADJUST_SI"):
+                float(value)
+                if find_row("Si") is not None:
+                    attr = "mu_fraction" if tag == "TAIL_FRACTION_ADJUST_SI" else "width_multi"
+                    raise AttributeError(f"'numpy.ndarray' object has no attribute '{attr}'")
+    if return_dict:
+        return {rows[i, 0].name: rows[i] for i in range(rows.shape[0])}
+    return rows, names

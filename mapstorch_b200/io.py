@@ -3,12 +3,24 @@
 ``read_dataset`` returns ``{"spec_vol", "elems", "int_spec"}``; ``create_dataset`` stores the
 volume energy-axis-last under ``MAPS/mca_arr`` with ``MAPS/int_spec`` and ``MAPS/channel_names``.
 HDF5 needs ``h5py``, which is imported lazily; paths ending in ``.npz`` use the same keys in a
-NumPy archive so the hot path can be exercised where no HDF5 library exists.  The MAPS
-override-file writer/parser is out of scope.
+NumPy archive so the hot path can be exercised where no HDF5 library exists.
+
+``write_override_params_file`` / ``parse_override_params_file`` (io.py:192-459, 462-547) carry
+fitted parameters and the element list to and from XRF-Maps' ``maps_fit_parameters_override.txt``.
+The file layout is data (``data/override_template.txt``, derived from the reference writer by
+``tools/export_override_template.py``); the writer only fills its fields.
 """
+import re
 import warnings
+from datetime import datetime
+from pathlib import Path
 
 import numpy as np
+
+from mapstorch_b200.default import default_fitting_elems, default_param_vals, param_name_map
+
+_TEMPLATE_PATH = Path(__file__).resolve().parent / "data" / "override_template.txt"
+_FIELD = re.compile(r"<<(@?[A-Z_0-9]+)(?:\|([^>]*))?>>")
 
 _VOL_KEYS = ("MAPS/Spectra/mca_arr", "MAPS/mca_arr")
 _ELEM_KEYS = ("MAPS/channel_names", "MAPS/XRF_Analyzed/Fitted/Channel_Names")
@@ -92,3 +104,94 @@ def create_dataset(spec_vol, energy_dim, output_path, fit_elems=None, dtype=np.f
         if names is not None:
             f.create_dataset("MAPS/channel_names", data=names)
     return output_path
+
+
+def _literal(text):
+    """fallback value of a template field, as the Python literal it was written from"""
+    try:
+        return int(text)
+    except ValueError:
+        return float(text)
+
+
+def write_override_params_file(output_path, param_values=None, elements=None, detector_material="Si",
+                               escape_factor=0.0):
+    """Write a maps_fit_parameters_override.txt (io.py:192-459).
+
+    `param_values` may use either this package's names or the file's own tags (`param_name_map`);
+    anything not given comes from `default_param_vals`.  Values are written with ``str()`` exactly as
+    passed, like the reference's f-strings.  Unknown elements / detector materials raise ValueError."""
+    if detector_material not in ["Si", "Ge"]:
+        raise ValueError(f"Detector material {detector_material} not supported")
+    is_si = detector_material == "Si"
+    if elements is not None:
+        unknown = [e for e in elements if e not in default_fitting_elems]
+        if unknown:
+            raise ValueError(f"Unsupported elements: {unknown}")
+    else:
+        elements = default_fitting_elems
+    params = default_param_vals.copy()
+    if param_values:
+        params.update({param_name_map.get(k, k): v for k, v in param_values.items()})
+    special = {
+        "@DATE": datetime.now().strftime("%Y-%m-%d %H:%M:%S.%f"),
+        "@ELEMENTS": ", ".join(elements),
+        "@DETECTOR_MATERIAL": 1 if is_si else 0,
+        "@SI_ESCAPE_FACTOR": escape_factor if is_si else 0.0,
+        "@GE_ESCAPE_FACTOR": 0.0 if is_si else escape_factor,
+        "@SI_ESCAPE_ENABLE": 1 if is_si else 0,
+        "@GE_ESCAPE_ENABLE": 0 if is_si else 1,
+    }
+
+    def fill(match):
+        key, fallback = match.group(1), match.group(2)
+        if key in special:
+            return str(special[key])
+        return str(params[key]) if key in params else str(_literal(fallback))
+
+    text = _FIELD.sub(fill, _TEMPLATE_PATH.read_text())
+    with open(output_path, "w") as fh:
+        fh.write(text)
+    return output_path
+
+
+def parse_override_params_file(file_path):
+    """Read a maps_fit_parameters_override.txt back (io.py:462-547).
+
+    Returns the numeric parameters under this package's names plus ``elements_to_fit``,
+    ``elements_with_pileup``, ``detector_material`` and the ``escape_factor`` of the enabled
+    detector.  A file that cannot be read gives a warning and the defaults, like the reference."""
+    tags = {k: k for k in default_param_vals.keys()} | param_name_map
+    params = {}
+    lists = {"ELEMENTS_TO_FIT": [], "ELEMENTS_WITH_PILEUP": []}
+    material = "Si"
+    enable = {"SI": 0, "GE": 0}
+    factor = {"SI": 0.0, "GE": 0.0}
+    try:
+        with open(file_path, "r") as fh:
+            for raw in fh.readlines():
+                line = raw.strip()
+                if not line or ":" not in line:
+                    continue
+                tag, value = (part.strip() for part in line.split(":", 1))
+                if tag == "DETECTOR_MATERIAL":
+                    material = "Ge" if int(value) == 0 else "Si"
+                elif tag in lists:
+                    lists[tag] = [e.strip() for e in value.split(",") if e.strip()]
+                elif tag in ("SI_ESCAPE_FACTOR", "GE_ESCAPE_FACTOR"):
+                    factor[tag[:2]] = float(value)
+                elif tag in ("SI_ESCAPE_ENABLE", "GE_ESCAPE_ENABLE"):
+                    enable[tag[:2]] = int(value)
+                elif tag in tags:
+                    try:
+                        params[tags[tag]] = float(value)
+                    except ValueError:
+                        pass
+    except Exception as exc:
+        warnings.warn(f"Error parsing override parameter file: {exc}")
+    params["elements_to_fit"] = lists["ELEMENTS_TO_FIT"]
+    params["elements_with_pileup"] = lists["ELEMENTS_WITH_PILEUP"]
+    params["detector_material"] = material
+    key = material.upper()
+    params["escape_factor"] = factor[key] if enable[key] == 1 else 0.0
+    return params

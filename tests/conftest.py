@@ -40,5 +40,10 @@ def fit_golden():
     return _load("fit_golden.npz")
 
 
+@pytest.fixture(scope="session")
+def override_golden():
+    return _load("override_golden.npz")
+
+
 def golden_params(g, tag):
     return dict(zip([str(k) for k in g[f"{tag}_param_names"]], [float(v) for v in g[f"{tag}_param_vals"]]))

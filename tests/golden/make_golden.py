@@ -11,6 +11,8 @@ Outputs (np.savez_compressed):
   snip_golden.npz   snip_bkg inputs+outputs and the per-pass gather indices
   fit_golden.npz    per-spectrum fit_spec(tune_params=False) runs (converged Adam) + loss traces
   host_golden.npz   init_elem_amps, get_peak_ranges, escape bins
+  override_golden.npz  override files written by the reference, what its parser and read_constants make of
+                       them, and element spectra evaluated with the edited branching ratios
 The reference ships no tests or fixtures of its own, so these are the pins.
 """
 import argparse
@@ -48,7 +50,9 @@ class _Trait:
 for _t in ("Dict", "List", "Int", "Unicode", "Bool", "Float"):
     setattr(sys.modules["traitlets"], _t, _Trait)
 
-from mapstorch import bkg as rbkg, map as rmap, opt as ropt, util as rutil  # noqa: E402
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))  # mapstorch.io imports it; only the text-file helpers are used
+
+from mapstorch import bkg as rbkg, constant as rconst, io as rio, map as rmap, opt as ropt, util as rutil  # noqa: E402
 from mapstorch.default import default_param_vals, default_fitting_elems, default_energy_consts  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
@@ -350,13 +354,90 @@ def gen_refine(out, n_iter=3000):
     out["j_model"] = m.detach().numpy()
 
 
+OVERRIDE_ELEMS = ["Fe", "Gd_L", "Pt_L", "Sn_L", "I_L", "Si_Si"]
+OVERRIDE_EXTRA = ("BRANCHING_RATIO_ADJUSTMENT_K: Pb_L, 1., 0.5, 2.0, 1.\n"
+                  "BRANCHING_FAMILY_ADJUSTMENT_L: Au_L, 0.5, 0.7, 1.1\n"
+                  "BRANCHING_RATIO_ADJUSTMENT_K: Fe, 1., 1., 1.2, 1.\n"
+                  "BRANCHING_RATIO_ADJUSTMENT_L: Nope_L, 1., 1., 1., 1., 1., 1., 1., 1., 1., 1., 1., 1.\n"
+                  "BRANCHING_RATIO_ADJUSTMENT_L: W_L, 1., 0.9, 0.8\n")
+
+
+def consts_arrays(consts):
+    names = list(consts.keys())
+    num = np.array([[[s.energy, s.ratio, s.Ge_mu, s.Si_mu, s.mu_fraction, s.width_multi] for s in consts[k]]
+                    for k in names], dtype=np.float64)
+    kinds = np.array([[s.type for s in consts[k]] for k in names], dtype=np.int64)
+    ptypes = np.array([[s.ptype for s in consts[k]] for k in names])
+    pile = np.array([[s.is_pileup for s in consts[k]] for k in names])
+    slot_names = np.array([[s.name for s in consts[k]] for k in names])
+    return {"names": np.array(names), "num": num, "type": kinds, "ptype": ptypes, "is_pileup": pile,
+            "slot_names": slot_names}
+
+
+def gen_override(out):
+    import json
+    import re
+    import tempfile
+
+    info = rconst.MapsElements().get_element_info()
+    tmp = Path(tempfile.mkdtemp())
+    cases = {
+        "A": dict(param_values=None, elements=None, detector_material="Si", escape_factor=0.0),
+        "B": dict(param_values={"ENERGY_SLOPE": 0.0123, "CAL_OFFSET_[E_OFFSET]": 7, "COMPTON_STEP": 0.25,
+                                "KB_F_TAIL_LINEAR": 3e-4, "NOT_A_TAG": 1.5, "COHERENT_SCT_ENERGY": 12.0},
+                  elements=["Fe", "Cu", "Pb_L", "Au_M", "Si_Si", "COMPTON_AMPLITUDE"], detector_material="Ge",
+                  escape_factor=0.3),
+        "D": dict(param_values={"SNIP_WIDTH": 0.75}, elements=["Ca"], detector_material="Si", escape_factor=0.07),
+    }
+    texts = {}
+    for tag, kw in cases.items():
+        path = tmp / f"{tag}.txt"
+        rio.write_override_params_file(str(path), **kw)
+        texts[tag] = path.read_text()
+        out[f"{tag}_kwargs"] = np.array(json.dumps(kw))
+    # C: case B edited by hand -- pile-ups listed, more adjustment rows (incl. unknown names, short rows)
+    texts["C"] = texts["B"].replace("ELEMENTS_WITH_PILEUP: \n", "ELEMENTS_WITH_PILEUP: Si_Si, Fe_Fe, Ca_K\n").replace(
+        "SI_ESCAPE_FACTOR:", OVERRIDE_EXTRA + "SI_ESCAPE_FACTOR:")
+    assert texts["C"] != texts["B"] and OVERRIDE_EXTRA in texts["C"]
+    t = tens(params_a(), {e: 0.0 for e in default_fitting_elems})
+    ev = ev_of(t, (0, 2047))
+    for tag, text in texts.items():
+        path = tmp / f"{tag}.txt"
+        path.write_text(text)
+        out[f"{tag}_text"] = np.array(re.sub(r"DATE: .*", "DATE: <date>", text))
+        out[f"{tag}_parsed"] = np.array(json.dumps(rio.parse_override_params_file(str(path))))
+        consts = rconst.read_constants(str(path), info)
+        for k, v in consts_arrays(consts).items():
+            out[f"{tag}_consts_{k}"] = v
+        present = [e for e in OVERRIDE_ELEMS if e in consts]
+        out[f"{tag}_spectra_elems"] = np.array(present)
+        out[f"{tag}_spectra"] = np.stack([rmap.model_elem_spec(t, e, ev, True, True, e_consts=consts).numpy()
+                                          for e in present])
+    out["spectra_ev"] = ev.numpy()
+    # rows + names form, with pile-ups passed by the caller
+    rows, names = rconst.read_constants(str(tmp / "A.txt"), info, pileups=["Si_Cl"], return_dict=False)
+    out["A_rows_names"] = np.array([str(n) for n in names])
+    out["A_rows_ratio"] = np.array([[s.ratio for s in r] for r in rows])
+    # the two tail tags raise upstream (attribute access on an object-array slice)
+    for tag_line in ("TAIL_FRACTION_ADJUST_SI: 1.5\n", "TAIL_WIDTH_ADJUST_SI: 2.0\n"):
+        path = tmp / "tail.txt"
+        path.write_text(texts["A"] + "\n" + tag_line)
+        try:
+            rconst.read_constants(str(path), info)
+            raised = "none"
+        except Exception as exc:  # noqa: BLE001
+            raised = type(exc).__name__
+        out["raises_" + tag_line.split(":")[0]] = np.array(raised)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-fit", action="store_true")
     ap.add_argument("--quick-fit", action="store_true")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
-    jobs = {"model": gen_model, "snip": gen_snip, "host": gen_host, "tables": gen_random_tables}
+    jobs = {"model": gen_model, "snip": gen_snip, "host": gen_host, "tables": gen_random_tables,
+            "override": gen_override}
     for name, fn in jobs.items():
         if args.only and args.only != name:
             continue

@@ -107,3 +107,30 @@ def test_shape_helpers(mods):
     ev = torch.arange(100, dtype=torch.float32) * 0.5
     esc = mmap.escape_peak(spec, ev, 0.1, "cpu", "Si")
     assert torch.equal(esc, torch.from_numpy(mo.escape_peak(spec.numpy(), ev.numpy(), 0.1, "Si")))
+
+
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_element_spectra_with_override_file_constants(tmp_path, override_golden, model_golden, mods, tag):
+    """e_consts edited by a MAPS override file (branching ratios, Ge absorption column, pile-ups from
+    the file) flow through K1: spectra vs the reference evaluated with ITS read_constants output."""
+    from mapstorch_b200 import constant
+
+    mmap, tables, d, mo = mods
+    g = override_golden
+    path = tmp_path / "o.txt"
+    path.write_text(str(g[f"{tag}_text"]))
+    consts = constant.read_constants(str(path), d.default_elem_info)
+    p = golden_params(model_golden, "a")
+    elems = [str(e) for e in g[f"{tag}_spectra_elems"]]
+    pp = tens(dict(p, **{e: 0.0 for e in elems}))
+    ev = torch.from_numpy(g["spectra_ev"])
+    for i, e in enumerate(elems):
+        got = mmap.model_elem_spec(pp, e, ev, True, True, e_consts=consts).numpy()
+        ref = g[f"{tag}_spectra"][i]
+        assert np.abs(got - ref).max() <= TOL * np.abs(ref).max(), (tag, e)
+    # and the edit is visible: Fe K-beta is 1.2x the default table's
+    if tag == "A":
+        base = mmap.model_elem_spec(pp, "Fe", ev, True, True).numpy()
+        kb = int(np.argmin(np.abs(g["spectra_ev"] - 7.058)))
+        assert got is not None and abs(mmap.model_elem_spec(pp, "Fe", ev, True, True, e_consts=consts).numpy()[kb]
+                                       / base[kb] - 1.2) < 0.02
