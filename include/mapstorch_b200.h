@@ -159,6 +159,17 @@ int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64_t n_px, in
                   const double *hinv_dev, int32_t *n_fixed_dev, const MtPeers *peers_host /* optional */,
                   void *stream);
 
+/* Amplitude-sparsity penalty of the MSE objective -- replaces the `l1_lambda` branch of _calculate_loss
+ * (opt.py:372-396) for the map fit.  With A >= 0 the penalty c*sum(A) is linear, so it only shifts the
+ * unconstrained amplitudes:  x[e,p] -= coef[e] * S_p,  S_p = sum_c mask[c] * (sum_{r<repeat} spec[p, col0 + r*n_ch + c])^2
+ * (the row's squared distance from the background, i.e. loss(bkg, y) of the reference), and
+ * coef[e] = l1_lambda / (2 * n_elements) * (G^-1 1)[e] is prepared by the host.  `repeat` = 2 reads the
+ * exact hi + remainder operand pair the SNIP kernel writes.  chan_mask_dev may be NULL (all channels).
+ * Follow with mt_nnls_fixup. */
+int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_t n_px, int64_t ld_spec, int32_t col0,
+                     int32_t n_ch, int32_t repeat, const float *chan_mask_dev, const float *coef_dev, float *x_dev,
+                     int64_t ld_x, int32_t x_layout, int32_t n_comp, void *stream);
+
 /* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
  * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]).  short_list != 0 selects
  * the warp-per-pixel variant (n_comp <= 32, element-major), which minimises the latency of a solve

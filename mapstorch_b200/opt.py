@@ -132,10 +132,12 @@ class MapFitPlan:
         self.basis, self.names = _map.element_basis(self.params, self.er, elements, e_consts, elem_info,
                                                     detector_type, escape_factor)
         b64 = self.basis.double().cpu().numpy()
+        self.chan_mask = None  # float 0/1 per channel of the window when `indices` restricts the fit
         if indices is not None:
             mask = np.zeros(self.n_ch, dtype=bool)
             mask[np.asarray(indices)] = True
             b64 = b64 * mask[None, :]
+            self.chan_mask = torch.from_numpy(mask.astype(np.float32)).cuda()
         # components without any open line (or fully masked) cannot be fitted: amplitude 0
         self.live = np.nonzero(np.sum(b64 * b64, axis=1) > 0)[0]
         bl = b64[self.live]
@@ -264,11 +266,23 @@ class MapFitPlan:
         else:
             raise ValueError(f"unknown engine {engine!r}")
 
-    def _fit_serial(self, spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers):
+    def _penalty_coef(self, l1_lambda):
+        """coef[e] of mt_penalty_shift: l1_lambda / (2 n_elements) * (G^-1 1)[e] for the live components;
+        n_elements counts every fitted name like the reference's len(elements) (opt.py:377-381)."""
+        coef = (float(l1_lambda) / (2.0 * max(len(self.names), 1))) * self.hinv.sum(axis=1)
+        return torch.from_numpy(coef.astype(np.float32)).cuda()
+
+    def _shift(self, operand, col0, repeat, x, coef, stream):
+        _native.call("mt_penalty_shift", operand.data_ptr(), _native.dtype_code(operand.dtype), operand.shape[0],
+                     operand.stride(0), int(col0), self.n_ch, int(repeat),
+                     self.chan_mask.data_ptr() if self.chan_mask is not None else None, coef.data_ptr(),
+                     *self._x_args(x), self.n_live, _native.stream_ptr(stream))
+
+    def _fit_serial(self, spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers, coef=None):
         n_px = spec2d.shape[0]
         # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
         neg = None
-        if nonneg and engine == "tensor" and n_px and len(self.groups) == 1:
+        if nonneg and engine == "tensor" and n_px and len(self.groups) == 1 and coef is None:
             neg = self._neg_buffers(n_px)
             neg[1].zero_()
         wide = False
@@ -289,8 +303,12 @@ class MapFitPlan:
                 scratch[:n, self.n_ch:] = y - hi
                 self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2, 0, width, engine, stream, neg, p0,
                                _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
+                if coef is not None:
+                    self._shift(scratch[:n], 0, 2, self._x_chunk(x, p0, n), coef, stream)
         elif not self.use_snip:
             self._contract(spec2d, x, self.er[0], 1, self.er[0], self.er[1] + 1, engine, stream, neg, 0, peers)
+            if coef is not None:
+                self._shift(spec2d, self.er[0], 1, x, coef, stream)
         else:
             lohi, n_pass = self._snip
             hilo = engine == "tensor"
@@ -305,6 +323,8 @@ class MapFitPlan:
                                  scratch[:n], mode, stream)
                 self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
                                _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
+                if coef is not None:
+                    self._shift(scratch[:n], 0, 2 if hilo else 1, self._x_chunk(x, p0, n), coef, stream)
         if nonneg and n_px:
             if self._last_engine == "tensor" and neg is not None:
                 _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
@@ -352,7 +372,7 @@ class MapFitPlan:
             n_fixed.copy_(counts.sum().reshape(1))
 
     def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None,
-            peers=None, layout="ep"):
+            peers=None, layout="ep", l1_lambda=0.0):
         """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
         rows in `self.names` order (components without an open line stay 0).
 
@@ -368,7 +388,13 @@ class MapFitPlan:
 
         layout: "ep" (default) returns x [E, P], one contiguous map per component; "pe" returns
         x [P, e_pad], one 16-byte aligned record per pixel (columns >= E are zero) -- the layout
-        whose stores are 128-bit wide, used for the peer-memory gather."""
+        whose stores are 128-bit wide, used for the peer-memory gather.
+
+        l1_lambda > 0 adds the reference's amplitude-sparsity penalty (opt.py:372-396) to the MSE objective:
+        the unconstrained amplitudes are shifted per pixel (mt_penalty_shift, one more read of the spectra)
+        before the non-negative solve."""
+        if l1_lambda > 0 and (not nonneg or peers is not None):
+            raise ValueError("the l1_lambda penalty needs the non-negative solve and local output")
         if spec2d.device.type != "cuda" or spec2d.dim() != 2 or spec2d.stride(1) != 1:
             raise ValueError("spec2d must be a CUDA [P, C] tensor with contiguous rows")
         if spec2d.shape[1] <= self.er[1]:
@@ -393,16 +419,17 @@ class MapFitPlan:
         pipelined = (self.pipeline and nonneg and engine == "tensor" and n_px > 0 and not self.use_snip and stream is None
                      and (spec2d.dtype == torch.float16 or exact_counts is True)
                      and (spec2d.stride(0) * spec2d.element_size()) % 16 == 0 and spec2d.data_ptr() % 16 == 0)
-        if pipelined:
+        if pipelined and not l1_lambda > 0:
             self._fit_pipelined(spec2d, x, n_fixed, peers)
         else:
-            self._fit_serial(spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers)
+            self._fit_serial(spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers,
+                             self._penalty_coef(l1_lambda) if l1_lambda > 0 else None)
         if not dense:
             out[torch.as_tensor(self.live, device="cuda")] = x
         return out
 
 
-def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
+def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0):
     """Stream a HOST volume [P, C] through the device in row slabs: slab k+1 is copied
     host->device on a second stream while slab k is being fitted (pinned host memory makes the
     copies asynchronous).  Returns x [E, P] on the device."""
@@ -431,14 +458,15 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384):
         if check:
             too_big[i] = bufs[b][:n, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0
         self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
-                 exact_counts=True if check else None)
+                 exact_counts=True if check else None, l1_lambda=l1_lambda)
         consumed[b].record(compute)
     if check:
         for i in torch.nonzero(too_big).flatten().tolist():
             p0 = starts[i]
             n = min(chunk, n_px - p0)
             bufs[0][:n].copy_(host2d[p0: p0 + n])
-            self.fit(bufs[0][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine, exact_counts="split")
+            self.fit(bufs[0][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine, exact_counts="split",
+                     l1_lambda=l1_lambda)
     for buf in bufs:
         buf.record_stream(compute)
     return out
@@ -504,7 +532,7 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
             device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384, refine=None,
-            refine_iters=12, refine_bounds=None):
+            refine_iters=12, refine_bounds=None, loss="mse", l1_lambda=0.0):
     """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
 
     Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
@@ -515,7 +543,12 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
 
     refine: optional tuple of calibration parameters (subset of ENERGY_OFFSET, ENERGY_SLOPE, FWHM_OFFSET,
     FWHM_FANOPRIME) to free PER PIXEL together with the amplitudes, like fit_spec(fitting_params=refine,
-    tune_params=True) per pixel; their maps, the final "loss" and "iterations" are added to the result."""
+    tune_params=True) per pixel; their maps, the final "loss" and "iterations" are added to the result.
+
+    l1_lambda: the reference's sparsity penalty on the amplitudes (opt.py:372-396), per pixel.  loss="l1" is
+    available for single spectra (fit_spec); per-pixel L1 maps are not built."""
+    if loss != "mse":
+        raise NotImplementedError('fit_map minimises the MSE objective; loss="l1" exists for fit_spec only')
     _native.require_device()
     if not isinstance(spec_vol, torch.Tensor):
         arr = np.asarray(spec_vol)
@@ -534,9 +567,9 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         plan = _cached_plan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
                             detector_type, escape_factor)
     if flat.device.type == "cuda":
-        x = plan.fit(flat, nonneg=nonneg, engine=engine)
+        x = plan.fit(flat, nonneg=nonneg, engine=engine, l1_lambda=l1_lambda)
     else:
-        x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px)
+        x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px, l1_lambda=l1_lambda)
     extra = {}
     if refine:
         # per-pixel nonlinear refinement of peak-shape parameters + amplitudes (kernel K4)
@@ -578,9 +611,11 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
     """Fit one spectrum (opt.py:165-327).  Returns (tensors, spec_fit, bkg, loss_trace) like the
     reference; amplitudes are log10 in the tensor dict.
 
-    With ``tune_params=False`` and the MSE loss the problem is a non-negative linear least-squares
-    solve, done directly on the GPU (what the reference's Adam loop converges to); the iteration
-    controls (optimizer, n_iter, init_amp) are accepted for source compatibility and ignored."""
+    With ``tune_params=False`` the problem is linear in the amplitudes and is solved directly on the
+    GPU -- non-negative least squares for the MSE loss (what the reference's Adam loop converges to),
+    a shifted right-hand side for the ``l1_lambda`` penalty and iteratively re-weighted solves for
+    ``loss="l1"`` (robust.py); the iteration controls (optimizer, n_iter, init_amp) are accepted for
+    source compatibility and ignored.  ``loss_trace`` holds the objective in the reference's units."""
     assert loss in ["mse", "l1"], "Loss function not supported"
     assert optimizer in ["adam", "adamw"], "Optimizer not supported"
     if tune_params:
@@ -588,9 +623,7 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
 
         return fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals,
                                fixed_param_vals, indices, use_snip, n_iter, e_consts, elem_info, detector_type,
-                               escape_factor, device, verbose)
-    if loss != "mse" or l1_lambda > 0:
-        raise NotImplementedError("only the MSE objective without L1 penalty has a direct solve (SURVEY.md 8f.4)")
+                               escape_factor, device, verbose, loss=loss, l1_lambda=l1_lambda)
     _native.require_device()
     spec = torch.as_tensor(np.asarray(int_spec, dtype=np.float32) if not isinstance(int_spec, torch.Tensor)
                            else int_spec.detach().float().cpu().numpy())
@@ -599,9 +632,6 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
                          use_snip, e_consts, elem_info, detector_type, escape_factor, return_plan=True)
     tensors, _ = create_tensors(plan.names, [], init_param_vals, fixed_param_vals, tune_params=False, device=device)
     amps = torch.stack([maps[n].reshape(()) for n in plan.names])
-    for n, a in zip(plan.names, amps):
-        tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
-    spec_fit = (amps[None, :] @ plan.basis).reshape(-1)
     cropped = spec[plan.er[0]: plan.er[1] + 1].cuda()
     if use_snip:
         p = plan.params
@@ -610,8 +640,22 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
             device="cuda")
     else:
         bkg = torch.zeros_like(cropped)
-    resid = spec_fit + bkg - cropped
-    if indices is not None:
-        resid = resid[torch.as_tensor(np.asarray(indices), device="cuda")]
-    loss_trace = [float(torch.sum(resid * resid).item())]
+    idx = None if indices is None else torch.as_tensor(np.asarray(indices), device="cuda")
+    loss_trace = []
+    if loss != "mse" or l1_lambda > 0:
+        # other objectives (opt.py:230-236, 372-396): re-weighted / shifted non-negative solves, robust.py
+        from mapstorch_b200 import robust
+
+        bm = plan.basis.double() if idx is None else plan.basis.double()[:, idx]
+        tm = (cropped - bkg).double() if idx is None else (cropped - bkg).double()[idx]
+        c = robust.penalty_constant(tm, loss, l1_lambda, len(plan.names))
+        amps = robust.solve_amplitudes(bm, tm, loss, c, loss_trace).float()
+    for n, a in zip(plan.names, amps):
+        tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
+    spec_fit = (amps[None, :] @ plan.basis).reshape(-1)
+    if not loss_trace:
+        resid = spec_fit + bkg - cropped
+        if idx is not None:
+            resid = resid[idx]
+        loss_trace = [float(torch.sum(resid * resid).item())]
     return tensors, spec_fit.cpu().numpy(), bkg.cpu().numpy(), loss_trace

@@ -140,15 +140,20 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
 
 # ---- fit_spec(tune_params=True): global calibration fit of one spectrum -------------------------
 def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals, fixed_param_vals,
-                    indices, use_snip, n_iter, e_consts, elem_info, detector_type, escape_factor, device, verbose):
+                    indices, use_snip, n_iter, e_consts, elem_info, detector_type, escape_factor, device, verbose,
+                    loss="mse", l1_lambda=0.0):
     """``fit_spec`` with ``tune_params=True`` (opt.py:165-327) on the GPU.
 
     The reference runs Adam on all tunable calibration parameters and log-amplitudes at once.  Here the
     amplitudes are projected out (for given calibration parameters they are the non-negative
     least-squares solution) and the remaining small problem is solved by
     Levenberg-Marquardt with forward-difference Jacobians; every evaluation runs K1 (basis), K2 (SNIP,
-    which depends on the calibration too) and the non-negative solve on the device."""
-    from mapstorch_b200 import bkg as _bkg, map as _map
+    which depends on the calibration too) and the non-negative solve on the device.
+
+    ``loss="l1"`` wraps that in iteratively re-weighted rounds (weights 1/max(|res|, eps), eps annealed);
+    the ``l1_lambda`` penalty c*sum(A) enters the amplitude solve as a shifted right-hand side and the
+    Levenberg-Marquardt residual vector as extra entries sqrt(c*A) (A >= 0), see robust.py."""
+    from mapstorch_b200 import bkg as _bkg, map as _map, robust
     from mapstorch_b200.default import default_fitting_params, default_learning_rates
     from mapstorch_b200.opt import create_tensors
 
@@ -165,9 +170,9 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     elements = list(dict.fromkeys(list(elements_to_fit)))
     idx = None if indices is None else torch.as_tensor(np.asarray(indices), device="cuda")
     scale = np.array([10.0 * default_learning_rates.get(p, default_learning_rates["default_lr"]) for p in free])
-    state = {}
+    robust_loss = loss == "l1"
 
-    def evaluate(theta):
+    def evaluate(theta, w=None):
         pp = dict(params, **dict(zip(free, (float(t) for t in theta))))
         basis, names = _map.element_basis(pp, er, elements, e_consts, elem_info, detector_type, escape_factor)
         if use_snip:
@@ -179,57 +184,77 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         target = (y - bkg).double()
         bm = basis.double() if idx is None else basis.double()[:, idx]
         tm = target if idx is None else target[idx]
-        live = (bm * bm).sum(dim=1) > 0
-        bl = bm[live]
-        gram = bl @ bl.T
-        hinv = torch.linalg.inv(gram)
-        hinv = 0.5 * (hinv + hinv.T)
-        x_live = (hinv @ (bl @ tm)).float().reshape(-1, 1).contiguous()
-        _native.call("mt_nnls_fixup", x_live.data_ptr(), x_live.stride(0), _native.MT_X_ELEMENT_MAJOR, 1,
-                     int(live.sum()), gram.contiguous().data_ptr(), hinv.contiguous().data_ptr(), None, None,
-                     _native.stream_ptr())
-        x = torch.zeros(len(names), dtype=torch.float64, device="cuda")
-        x[live] = x_live.reshape(-1).double()
-        resid = x @ bm - tm
-        return resid, dict(x=x, names=names, basis=basis, bkg=bkg, params=pp)
+        c = robust.penalty_constant(tm, loss, l1_lambda, len(names))
+        x = robust.weighted_nnls(bm, tm, w, c if robust_loss else 0.5 * c)
+        res = x @ bm - tm
+        vec = res if w is None else torch.sqrt(w) * res
+        if c > 0:
+            vec = torch.cat([vec, torch.sqrt((2.0 if robust_loss else 1.0) * c * x)])
+        return vec, dict(x=x, names=names, basis=basis, bkg=bkg, params=pp, res=res, bm=bm, tm=tm, c=c,
+                         objective=robust.objective(bm, tm, x, loss, c))
+
+    def run_lm(theta, w, max_it, trace):
+        resid, info = evaluate(theta, w)
+        value = float(resid @ resid)
+        lam = 1e-3
+        for it in range(max_it if free else 0):
+            cols = []
+            for k in range(len(free)):
+                t2 = theta.copy()
+                t2[k] += 0.05 * scale[k]
+                r2, _ = evaluate(t2, w)
+                cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
+            jac = torch.stack(cols, dim=1)
+            jtj = (jac.T @ jac).cpu().numpy()
+            jtr = (jac.T @ resid).cpu().numpy()
+            improved = False
+            for _ in range(8):
+                try:
+                    step = np.linalg.solve(jtj + lam * (np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))), -jtr)
+                except np.linalg.LinAlgError:
+                    lam *= 10
+                    continue
+                cand = theta + step * scale
+                r_new, info_new = evaluate(cand, w)
+                value_new = float(r_new @ r_new)
+                if value_new < value:
+                    rel = (value - value_new) / max(value, 1e-30)
+                    theta, resid, info, value = cand, r_new, info_new, value_new
+                    lam = max(lam / 5, 1e-9)
+                    improved = True
+                    break
+                lam *= 5
+            trace.append(info["objective"])
+            if verbose:
+                print(f"fit_spec_global iter {it}: objective {info['objective']:.6g} lambda {lam:.2g}")
+            if not improved or rel < 1e-10:
+                break
+        return theta, info
 
     theta = np.array([params[p] for p in free], dtype=np.float64)
-    resid, info = evaluate(theta)
-    loss = float(resid @ resid)
-    trace = [loss]
-    lam = 1e-3
-    for it in range(max(1, min(int(n_iter), 60)) if free else 0):
-        cols = []
-        for k in range(len(free)):
-            t2 = theta.copy()
-            t2[k] += 0.05 * scale[k]
-            r2, _ = evaluate(t2)
-            cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
-        jac = torch.stack(cols, dim=1)
-        jtj = (jac.T @ jac).cpu().numpy()
-        jtr = (jac.T @ resid).cpu().numpy()
-        improved = False
-        for _ in range(8):
-            try:
-                step = np.linalg.solve(jtj + lam * (np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))), -jtr)
-            except np.linalg.LinAlgError:
-                lam *= 10
-                continue
-            cand = theta + step * scale
-            r_new, info_new = evaluate(cand)
-            loss_new = float(r_new @ r_new)
-            if loss_new < loss:
-                rel = (loss - loss_new) / max(loss, 1e-30)
-                theta, resid, info, loss = cand, r_new, info_new, loss_new
-                lam = max(lam / 5, 1e-9)
-                improved = True
+    trace = []
+    budget = max(1, min(int(n_iter), 60))
+    if not robust_loss:
+        _, info0 = evaluate(theta)
+        trace.append(info0["objective"])
+        theta, info = run_lm(theta, None, budget, trace)
+    else:
+        _, info = evaluate(theta)
+        trace.append(info["objective"])
+        top = max(float(info["res"].abs().max()), 1e-30)
+        eps, floor = 1e-3 * top, 1e-10 * top
+        for rnd in range(16):
+            before = info["objective"]
+            theta, info = run_lm(theta, robust.irls_weights(info["res"], eps), min(budget, 12), trace)
+            if eps <= floor and abs(before - info["objective"]) <= 1e-8 * abs(before):
                 break
-            lam *= 5
-        trace.append(loss)
-        if verbose:
-            print(f"fit_spec_global iter {it}: loss {loss:.6g} lambda {lam:.2g}")
-        if not improved or rel < 1e-10:
-            break
+            eps = max(eps * 0.2, floor)
+        # calibration settled: converge the amplitudes of the final model all the way
+        polished = robust.solve_amplitudes(info["bm"], info["tm"], loss, info["c"])
+        value = robust.objective(info["bm"], info["tm"], polished, loss, info["c"])
+        if value <= info["objective"]:
+            info = dict(info, x=polished, objective=value)
+            trace.append(value)
 
     pp, names, x = info["params"], info["names"], info["x"]
     tensors, _ = create_tensors(names, free, pp, {k: pp[k] for k in pp if k not in free}, tune_params=True, device=device)

@@ -398,6 +398,42 @@ def fit_spec_adam(spectrum, B, bkg=None, init_log_amps=None, n_iter=500, lr=1e-2
     return a, trace
 
 
+def fit_nnls_penalised(spectrum, B, bkg=None, c=0.0):
+    """argmin_{x>=0} |x B - (y - bkg)|^2 + c*sum(x): the MSE objective with the l1_lambda penalty of
+    _calculate_loss (opt.py:372-396; c = l1_lambda * loss(bkg, y) / n_elements).  Solved exactly as a
+    Lawson-Hanson problem on the Cholesky factor of the Gram matrix (|L^T x - L^-1 (h - c/2)|^2 has the
+    same minimiser).  B: [E, C] float64."""
+    from scipy.optimize import nnls
+
+    r = np.asarray(spectrum, dtype=np.float64) - (0.0 if bkg is None else np.asarray(bkg, dtype=np.float64))
+    B = np.asarray(B, dtype=np.float64)
+    live = (B * B).sum(axis=1) > 0
+    x = np.zeros(B.shape[0])
+    Bl = B[live]
+    L = np.linalg.cholesky(Bl @ Bl.T)
+    rhs = np.linalg.solve(L, Bl @ r - 0.5 * c)
+    x[live] = nnls(L.T, rhs, maxiter=50 * L.shape[0])[0]
+    return x
+
+
+def fit_lad(spectrum, B, bkg=None, c=0.0):
+    """argmin_{x>=0} sum|x B - (y - bkg)| + c*sum(x): the loss="l1" objective (opt.py:232-233, 364-396),
+    as the exact linear programme  min sum(t) + c*sum(x)  s.t. -t <= x B - r <= t.  Returns (x, objective)."""
+    from scipy.optimize import linprog
+
+    r = np.asarray(spectrum, dtype=np.float64) - (0.0 if bkg is None else np.asarray(bkg, dtype=np.float64))
+    B = np.asarray(B, dtype=np.float64)
+    n_e, n_c = B.shape
+    cost = np.r_[np.full(n_e, float(c)), np.ones(n_c)]
+    eye = np.eye(n_c)
+    a_ub = np.block([[B.T, -eye], [-B.T, -eye]])
+    b_ub = np.r_[r, -r]
+    sol = linprog(cost, A_ub=a_ub, b_ub=b_ub, bounds=[(0, None)] * (n_e + n_c), method="highs")
+    if sol.status != 0:
+        raise RuntimeError(f"LAD programme did not solve: {sol.message}")
+    return sol.x[:n_e], float(sol.fun)
+
+
 def fit_map_composed(spectra, B, snip_args=None, er=None):
     """"Reference functions, best-case composition" (BASELINE.md section 4.2): batched snip_bkg,
     then (Y - bkg) @ pinv(B) in fp32 BLAS, then scipy NNLS only for the pixels whose unconstrained

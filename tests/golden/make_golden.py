@@ -11,6 +11,7 @@ Outputs (np.savez_compressed):
   snip_golden.npz   snip_bkg inputs+outputs and the per-pass gather indices
   fit_golden.npz    per-spectrum fit_spec(tune_params=False) runs (converged Adam) + loss traces
   host_golden.npz   init_elem_amps, get_peak_ranges, escape bins
+  objectives_golden.npz  fit_spec(tune_params=False) with loss="l1", l1_lambda > 0 and `indices` (--only objectives)
   override_golden.npz  override files written by the reference, what its parser and read_constants make of
                        them, and element spectra evaluated with the edited branching ratios
 The reference ships no tests or fixtures of its own, so these are the pins.
@@ -354,6 +355,40 @@ def gen_refine(out, n_iter=3000):
     out["j_model"] = m.detach().numpy()
 
 
+def gen_objectives(out, n_iter=6000):
+    """fit_spec(tune_params=False) under the other objectives: loss="l1", the l1_lambda penalty, and a channel
+    subset (`indices`).  Ten elements are in the spectrum, twenty are fitted, so the penalty has something to
+    switch off; two channels carry outliers so that L1 and MSE disagree."""
+    torch.set_num_threads(8)
+    rng = np.random.default_rng(11)
+    p = params_a()
+    er = (0, 2047)
+    spec, _ = synth_spectrum(p, er, ELEMS10, rng, 1.5, 3.0, flat=0.0)
+    spec = spec.copy()
+    spec[500] += 5000.0
+    spec[900] += 3000.0
+    idx = np.r_[100:480, 520:880, 920:1400]
+    runs = [("l1", dict(loss="l1"), ELEMS10, None), ("mse_pen", dict(loss="mse", l1_lambda=1.5e-6), ELEMS20, None),
+            ("l1_pen", dict(loss="l1", l1_lambda=1e-4), ELEMS20, None), ("mse_idx", dict(loss="mse"), ELEMS10, idx)]
+    out["runs"] = np.array([r[0] for r in runs])
+    out["spec"] = spec
+    out["er"] = np.array(er)
+    out["param_names"] = np.array(list(p.keys()))
+    out["param_vals"] = np.array([p[k] for k in p], dtype=np.float64)
+    for tag, kw, elems, indices in runs:
+        tensors, spec_fit, bkg, trace = ropt.fit_spec(
+            spec, er, elements_to_fit=list(elems), init_param_vals=p, tune_params=False, init_amp=True,
+            use_snip=False, optimizer="adam", n_iter=n_iter, progress_bar=False, indices=indices, **kw)
+        names = list(elems) + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+        out[f"{tag}_names"] = np.array(names)
+        out[f"{tag}_kwargs"] = np.array(repr(kw))
+        out[f"{tag}_indices"] = np.array([] if indices is None else indices, dtype=np.int64)
+        out[f"{tag}_logamps"] = np.array([tensors[n].item() for n in names], dtype=np.float64)
+        out[f"{tag}_spec_fit"] = spec_fit
+        out[f"{tag}_trace"] = np.array(trace, dtype=np.float64)
+        print(tag, "final loss", trace[-1], "min", min(trace), flush=True)
+
+
 OVERRIDE_ELEMS = ["Fe", "Gd_L", "Pt_L", "Sn_L", "I_L", "Si_Si"]
 OVERRIDE_EXTRA = ("BRANCHING_RATIO_ADJUSTMENT_K: Pb_L, 1., 0.5, 2.0, 1.\n"
                   "BRANCHING_FAMILY_ADJUSTMENT_L: Au_L, 0.5, 0.7, 1.1\n"
@@ -445,6 +480,12 @@ def main():
         fn(out)
         np.savez_compressed(HERE / f"{name}_golden.npz", **out)
         print("wrote", name, (HERE / f"{name}_golden.npz").stat().st_size, flush=True)
+    if args.only == "objectives":
+        out = {}
+        gen_objectives(out)
+        np.savez_compressed(HERE / "objectives_golden.npz", **out)
+        print("wrote objectives", (HERE / "objectives_golden.npz").stat().st_size, flush=True)
+        return
     if args.only == "refine":
         out = {}
         gen_refine(out)
