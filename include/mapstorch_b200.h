@@ -211,7 +211,8 @@ typedef struct MtRefineConfig {
 /* lines_host sorted by energy; chan_lines_host[c] = lo | hi << 16 is the range of line indices that can
  * contribute at channel c; comp_start_host/comp_lines_host list each component's lines;
  * line_window_host[l] = first | (last + 1) << 16 local channel of line l's window and line_off_host
- * [n_lines + 1] the prefix sums of the window lengths (slots of the cached line values); g0inv_dev = inverse
+ * [n_lines + 1] the prefix sums of the window lengths (validated, reserved: the kernel no longer caches
+ * line values); g0inv_dev = inverse
  * Gram matrix of the unit-amplitude basis at the global parameters, fp32 [n_comp][n_comp].
  * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
  * theta_dev [n_theta][ld_x], loss_dev [n_px], iters_dev [n_px] are optional outputs. */

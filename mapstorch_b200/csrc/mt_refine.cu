@@ -26,11 +26,12 @@
 
 namespace {
 
-constexpr int kRefThreads = 128;
+constexpr int kRefThreads = 128;  // 256 threads per pixel measured the same (70.1 ms) at equal warps per SM
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kMaxLines = 512;
 constexpr int kMaxComp = 64;
 constexpr int kMaxTheta = MT_MAX_THETA;
+constexpr int kRefDefaultMinBlocks = 6;  // measured on B200 (c4): 4 -> 77.0 ms, 5 -> 72.3, 6 -> 69.6, 7/8 -> 70.0
 
 struct RefParams {
     MtRefineConfig cfg;
@@ -39,7 +40,6 @@ struct RefParams {
     const int32_t *comp_start;      // [n_comp + 1] into comp_lines
     const int32_t *comp_lines;      // line indices grouped by component
     const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
-    const int32_t *line_off;        // [n_lines + 1]: offset of each line's window in the cached basis values
     const float *g0inv;             // [n_comp][n_comp]
     const float *bkg;
     long long ld_bkg;
@@ -66,20 +66,19 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename T, bool CACHE, int NT>
-__global__ void __launch_bounds__(kRefThreads)
+template <typename T, int MINB, int NT>
+__global__ void __launch_bounds__(kRefThreads, MINB)
 refine_kernel(const RefParams p) {
-    extern __shared__ float dyn[];  // r[n_ch], d[n_theta][n_ch], cached basis values of every line window
+    extern __shared__ float4 dyn4[];  // lc0[L], lc1[L], then r[n_ch], d[n_theta][n_ch]
     const MtRefineConfig &cfg = p.cfg;
     const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines;  // NT (free parameters) is a template argument
-    float *r_s = dyn;
-    float *d_s = dyn + n_ch;
-    float *b_s = dyn + (size_t)n_ch * (1 + NT);  // unit-amplitude line values, filled by B1, reused by B2
-
-    __shared__ float l_inv_sigma[kMaxLines], l_unit[kMaxLines], l_coef[kMaxLines], l_dfo[kMaxLines],
-        l_dfa[kMaxLines], l_energy[kMaxLines];
-    __shared__ uint32_t l_win[kMaxLines];
-    __shared__ int l_off[kMaxLines];
+    // per-line constants, packed so that one 128-bit load feeds the inner loops:
+    //   lc0 = {energy, a = -log2(e) / (2 sigma^2), amplitude * unit, window (first | last+1 << 16)}
+    //   lc1 = {1 / sigma^2, dsigma/dFWHM_OFFSET / sigma, dsigma/dFWHM_FANOPRIME / sigma, unit}
+    float4 *lc0 = dyn4;
+    float4 *lc1 = dyn4 + L;
+    float *r_s = reinterpret_cast<float *>(dyn4 + 2 * L);
+    float *d_s = r_s + n_ch;
     __shared__ float xs[kMaxComp], x_prev[kMaxComp], dx[kMaxComp], gx[kMaxComp], w_s[kMaxComp];
     __shared__ float hthx[kMaxTheta][kMaxComp], t1[kMaxComp][kMaxTheta];
     __shared__ float part[kRefWarps][1 + kMaxTheta + kMaxTheta * kMaxTheta];
@@ -105,11 +104,6 @@ refine_kernel(const RefParams p) {
         ctl[1] = 3.0e38f;  // loss_prev
         ctl[2] = 1.f;      // alpha
     }
-    for (int l = tid; l < L; l += kRefThreads) {
-        l_energy[l] = p.lines[l].energy;
-        l_win[l] = p.line_window[l];
-        l_off[l] = p.line_off[l];
-    }
     __syncthreads();
 
     int iter = 0;
@@ -131,11 +125,12 @@ refine_kernel(const RefParams p) {
             const float base = sqrtf(fmaxf(s0 * s0 + ln.e296 * fa, 1e-12f));
             const float sigma = base * ln.sigma_scale;
             const float unit = ln.factor * slope / (sigma * 2.5066282746310002f);
-            l_inv_sigma[l] = 1.f / sigma;
-            l_unit[l] = unit;
-            l_coef[l] = unit * xs[ln.comp];
-            l_dfo[l] = ln.sigma_scale * s0 / (2.3548f * base);  // d sigma / d FWHM_OFFSET
-            l_dfa[l] = ln.sigma_scale * ln.e296 / (2.f * base); // d sigma / d FWHM_FANOPRIME
+            const float is = 1.f / sigma, is2 = is * is;
+            const float dfo = ln.sigma_scale * s0 / (2.3548f * base);   // d sigma / d FWHM_OFFSET
+            const float dfa = ln.sigma_scale * ln.e296 / (2.f * base);  // d sigma / d FWHM_FANOPRIME
+            lc0[l] = make_float4(ln.energy, -0.72134752044448170f * is2, unit * xs[ln.comp],
+                                 __uint_as_float(__ldg(p.line_window + l)));
+            lc1[l] = make_float4(is2, dfo * is, dfa * is, unit);
         }
         __syncthreads();
 
@@ -149,18 +144,17 @@ refine_kernel(const RefParams p) {
             const uint32_t range = __ldg(p.chan_lines + c);
             float m = 0.f, d_ev = 0.f, d_fo = 0.f, d_fa = 0.f;
             for (int l = (int)(range & 0xffffu); l < (int)(range >> 16); ++l) {
-                const uint32_t win = l_win[l];
+                const float4 a0 = lc0[l];
+                const uint32_t win = __float_as_uint(a0.w);
                 if (c < (int)(win & 0xffffu) || c >= (int)(win >> 16)) continue;  // outside this line's window
-                const float is = l_inv_sigma[l];
-                const float u = (ev - l_energy[l]) * is;
-                const float g = __expf(-0.5f * u * u);
-                if (CACHE) b_s[l_off[l] + c - (int)(win & 0xffffu)] = l_unit[l] * g;
-                const float v = l_coef[l] * g;
+                const float4 a1 = lc1[l];
+                const float dl = ev - a0.x, dl2 = dl * dl;
+                const float v = a0.z * exp2f(a0.y * dl2);  // amplitude * unit * exp(-u^2 / 2), u = dl / sigma
                 m += v;
-                d_ev -= v * u * is;
-                const float dsg = v * (u * u - 1.f) * is;
-                d_fo += dsg * l_dfo[l];
-                d_fa += dsg * l_dfa[l];
+                d_ev = fmaf(-(v * dl), a1.x, d_ev);        // -v u / sigma
+                const float w = v * fmaf(dl2, a1.x, -1.f); // v (u^2 - 1); the 1 / sigma sits in a1.y, a1.z
+                d_fo = fmaf(w, a1.y, d_fo);
+                d_fa = fmaf(w, a1.z, d_fa);
             }
             float d[kMaxTheta] = {0.f, 0.f, 0.f, 0.f};
             if (k_off >= 0) d[k_off] = d_ev;
@@ -192,18 +186,13 @@ refine_kernel(const RefParams p) {
             float g = 0.f, h[kMaxTheta] = {0.f, 0.f, 0.f, 0.f};
             for (int j = p.comp_start[e]; j < p.comp_start[e + 1]; ++j) {
                 const int l = p.comp_lines[j];
-                const uint32_t win = l_win[l];
-                const float *bl = b_s + l_off[l] - (int)(win & 0xffffu);
-                const float is = l_inv_sigma[l], unit = l_unit[l], el = l_energy[l];
+                const float4 a0 = lc0[l];
+                const uint32_t win = __float_as_uint(a0.w);
+                const float unit = lc1[l].w;
                 for (int c = (int)(win & 0xffffu) + lane; c < (int)(win >> 16); c += 32) {
-                    float b;
-                    if (CACHE) {
-                        b = bl[c];
-                    } else {
-                        const float cg = (float)(cfg.ch0 + c);
-                        const float u = (off + slope * cg + cfg.energy_quad * (cg * cg) - el) * is;
-                        b = unit * __expf(-0.5f * u * u);
-                    }
+                    const float cg = (float)(cfg.ch0 + c);
+                    const float dl = fmaf(cfg.energy_quad, cg * cg, fmaf(slope, cg, off)) - a0.x;
+                    const float b = unit * exp2f(a0.y * (dl * dl));
                     g += b * r_s[c];
 #pragma unroll
                     for (int k = 0; k < kMaxTheta; ++k)
@@ -398,10 +387,10 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     // stage the small tables in one stream-ordered scratch allocation
     const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
-                 b_lw = sizeof(uint32_t) * cfg.n_lines, b_lo = sizeof(int32_t) * (cfg.n_lines + 1);
+                 b_lw = sizeof(uint32_t) * cfg.n_lines;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char *scratch = nullptr;
-    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_lo), stream));
+    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw), stream));
     char *q = scratch;
     RefParams p{};
     p.cfg = cfg;
@@ -416,7 +405,6 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.comp_start = static_cast<const int32_t *>(stage(comp_start_host, b_cs));
     p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
     p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
-    p.line_off = static_cast<const int32_t *>(stage(line_off_host, b_lo));
     MT_CUDA_TRY(cudaGetLastError());
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
@@ -429,34 +417,37 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.loss_out = loss_dev;
     p.iters_out = iters_dev;
     p.n_px = n_px;
-    const size_t smem_base = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta);
-    const size_t smem_cache = smem_base + sizeof(float) * (size_t)line_off_host[cfg.n_lines];
-    if (smem_base > 200 * 1024)
+    const size_t smem = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta) + 2 * sizeof(float4) * (size_t)cfg.n_lines;
+    if (smem > 200 * 1024)
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: %zu bytes of shared memory needed (channels x free parameters)",
-                        smem_base);
-    // caching the line values halves the exp count but costs occupancy; measured slower on B200 (c4), opt-in
-    const char *env = getenv("MT_REFINE_CACHE");
-    const bool cache = env && atoi(env) != 0 && smem_cache <= 200 * 1024;
-    const size_t smem = cache ? smem_cache : smem_base;
-#define MT_LAUNCH_REFINE_NT(T, C, N)                                                                                    \
+                        smem);
+    // resident CTAs per SM the compiler must leave room for (register cap 65536 / (128 * MINB))
+    const char *env = getenv("MT_REFINE_MINB");
+    const int minb = env ? atoi(env) : kRefDefaultMinBlocks;
+#define MT_LAUNCH_REFINE_NT(T, B, N)                                                                                    \
     do {                                                                                                                 \
-        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        refine_kernel<T, C, N><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                        \
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, B, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        refine_kernel<T, B, N><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                        \
     } while (0)
-#define MT_LAUNCH_REFINE(T, C)                                  \
+#define MT_LAUNCH_REFINE_B(T, B)                                \
     do {                                                        \
         switch (cfg.n_theta) {                                  \
-            case 0: MT_LAUNCH_REFINE_NT(T, C, 0); break;        \
-            case 1: MT_LAUNCH_REFINE_NT(T, C, 1); break;        \
-            case 2: MT_LAUNCH_REFINE_NT(T, C, 2); break;        \
-            case 3: MT_LAUNCH_REFINE_NT(T, C, 3); break;        \
-            default: MT_LAUNCH_REFINE_NT(T, C, 4); break;       \
+            case 0: MT_LAUNCH_REFINE_NT(T, B, 0); break;        \
+            case 1: MT_LAUNCH_REFINE_NT(T, B, 1); break;        \
+            case 2: MT_LAUNCH_REFINE_NT(T, B, 2); break;        \
+            case 3: MT_LAUNCH_REFINE_NT(T, B, 3); break;        \
+            default: MT_LAUNCH_REFINE_NT(T, B, 4); break;       \
         }                                                       \
     } while (0)
+#define MT_LAUNCH_REFINE(T)                                     \
+    do {                                                        \
+        if (minb <= 4) MT_LAUNCH_REFINE_B(T, 4);                \
+        else MT_LAUNCH_REFINE_B(T, 6);                          \
+    } while (0)
     if (dtype == MT_DTYPE_F32) {
-        if (cache) MT_LAUNCH_REFINE(float, true); else MT_LAUNCH_REFINE(float, false);
+        MT_LAUNCH_REFINE(float);
     } else if (dtype == MT_DTYPE_F16) {
-        if (cache) MT_LAUNCH_REFINE(__half, true); else MT_LAUNCH_REFINE(__half, false);
+        MT_LAUNCH_REFINE(__half);
     } else {
         cudaFreeAsync(scratch, stream);
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: dtype %d", dtype);
