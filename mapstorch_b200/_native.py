@@ -8,6 +8,7 @@ import os
 from pathlib import Path
 
 MT_OK = 0
+MT_ERR_INVALID, MT_ERR_CUDA, MT_ERR_UNSUPPORTED, MT_ERR_NO_DEVICE = -1, -2, -3, -4  # include/mapstorch_b200.h
 MT_DTYPE_F32, MT_DTYPE_F16 = 0, 1
 MT_TERM_GAUSS, MT_TERM_STEP, MT_TERM_TAIL = 0, 1, 2
 MT_SNIP_BACKGROUND, MT_SNIP_RESIDUAL, MT_SNIP_RESIDUAL_HILO = 0, 1, 2
@@ -134,7 +135,7 @@ def dtype_code(torch_dtype):
         return MT_DTYPE_F32
     if torch_dtype == torch.float16:
         return MT_DTYPE_F16
-    raise NativeError(-3, f"spectral volumes must be float32 or float16 on the device, got {torch_dtype}")
+    raise NativeError(MT_ERR_UNSUPPORTED, f"spectral volumes must be float32 or float16 on the device, got {torch_dtype}")
 
 
 def require_device():
