@@ -29,8 +29,57 @@ __device__ __forceinline__ float finite_or_zero(float v) {
     return (fabsf(v) <= 3.402823466e+38f) ? v : 0.f;
 }
 
+// log(1 + x) and exp(v) - 1 through the 1-ulp logf / expf.  The library's log1pf / expm1f keep RELATIVE accuracy
+// for |x| << 1, which costs ~40 instructions each (30 % of this kernel's instruction count in the ncu source
+// view); the parity bar of the background is relative to the row maximum, where the plain forms are as good:
+// the rounding of 1 + x and of exp(v) - 1 is an absolute error of 6e-8 (x (1 + bkg)), far below 1e-5 of any row
+// that holds at least one count.  Zero stays exactly zero.
+__device__ __forceinline__ float log_1p(float x) { return logf(__fadd_rn(1.f, x)); }
+__device__ __forceinline__ float exp_m1(float v) { return __fsub_rn(expf(v), 1.f); }
+
 __device__ __forceinline__ float clip(float a, float b, float c) {
     return fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), c);
+}
+
+// Packed fp32 arithmetic of sm_100 (FADD2 / FMUL2: two IEEE round-to-nearest operations per issue slot, bit-identical
+// to the scalar forms).  The kernel is issue / shared-memory bound, not FP32-pipe bound, so halving the slots of the
+// adds and multiplies of the 4-pixel records is a direct gain.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// cur <- min((a + b) / 2, cur) for the four pixels of a record
+__device__ __forceinline__ void clip4(const float4 &a, const float4 &b, float4 &cur) {
+    const unsigned long long half = pack2(0.5f, 0.5f);
+    float m0, m1, m2, m3;
+    unpack2(mul2(add2(pack2(a.x, a.y), pack2(b.x, b.y)), half), m0, m1);
+    unpack2(mul2(add2(pack2(a.z, a.w), pack2(b.z, b.w)), half), m2, m3);
+    cur.x = fminf(m0, cur.x);
+    cur.y = fminf(m1, cur.y);
+    cur.z = fminf(m2, cur.z);
+    cur.w = fminf(m3, cur.w);
+}
+
+// acc <- acc + v * w for the four pixels of a record (two roundings per element, like the reference's conv1d)
+__device__ __forceinline__ void axpy4(float4 &acc, const float4 &v, float w) {
+    const unsigned long long w2 = pack2(w, w);
+    unpack2(add2(pack2(acc.x, acc.y), mul2(pack2(v.x, v.y), w2)), acc.x, acc.y);
+    unpack2(add2(pack2(acc.z, acc.w), mul2(pack2(v.z, v.w), w2)), acc.z, acc.w);
 }
 
 // 128-bit shared-memory accesses with explicit 32-bit addresses (keeps the address arithmetic of the
@@ -86,11 +135,7 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
                 // the default window, away from the edges: five unconditional 128-bit loads
 #pragma unroll
                 for (int j = -2; j <= 2; ++j) {
-                    const float4 v = sb[i + j];
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, wgt));
-                    acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, wgt));
-                    acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, wgt));
-                    acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, wgt));
+                    axpy4(acc, sb[i + j], wgt);
                 }
             } else {
                 for (int j = -half; j <= half; ++j) {
@@ -104,10 +149,10 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
                     }
                 }
             }
-            acc.x = finite_or_zero(log1pf(acc.x));
-            acc.y = finite_or_zero(log1pf(acc.y));
-            acc.z = finite_or_zero(log1pf(acc.z));
-            acc.w = finite_or_zero(log1pf(acc.w));
+            acc.x = finite_or_zero(log_1p(acc.x));
+            acc.y = finite_or_zero(log_1p(acc.y));
+            acc.z = finite_or_zero(log_1p(acc.z));
+            acc.w = finite_or_zero(log_1p(acc.w));
         }
         cur[k] = acc;
     }
@@ -138,10 +183,7 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
             const float4 b = lds128(sb_base + ((tab[k] >> 12) & 0xffff0u));
             // this word is consumed: fetch the next pass's (from L2) behind the rest of the pass
             tab[k] = (more && i < n_ch) ? __ldg(next + i) : 0u;
-            cur[k].x = clip(a.x, b.x, cur[k].x);
-            cur[k].y = clip(a.y, b.y, cur[k].y);
-            cur[k].z = clip(a.z, b.z, cur[k].z);
-            cur[k].w = clip(a.w, b.w, cur[k].w);
+            clip4(a, b, cur[k]);
         }
         if (!more) break;  // the result of the last pass stays in registers
         __syncthreads();
@@ -155,8 +197,22 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
 
     // ---- back to counts (bkg.py:113-114) and output -----------------------------------------
 #pragma unroll
+    // the counts of channel k + 1 are fetched while channel k goes through expf and the stores
+    const bool need_y = out_mode != MT_SNIP_BACKGROUND;
+    float y_next[kSnipPix];
+    auto fetch = [&](int k) {
+        const int i = tid + k * kSnipThreads;
+#pragma unroll
+        for (int p = 0; p < kSnipPix; ++p) y_next[p] = (need_y && i < n_ch) ? load_count(rows[p] + i) : 0.f;
+    };
+    fetch(0);
+#pragma unroll
     for (int k = 0; k < KCH; ++k) {
         const int i = tid + k * kSnipThreads;
+        float y[kSnipPix];
+#pragma unroll
+        for (int p = 0; p < kSnipPix; ++p) y[p] = y_next[p];
+        if (k + 1 < KCH) fetch(k + 1);
         if (i >= n_ch) continue;
         const float vals[kSnipPix] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
 #pragma unroll
@@ -164,11 +220,11 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
             const long long px = px0 + p;
             if (px >= n_px) continue;
             float *orow = out + px * ld_out;
-            const float bkg = finite_or_zero(expm1f(vals[p]));
+            const float bkg = finite_or_zero(exp_m1(vals[p]));
             if (out_mode == MT_SNIP_BACKGROUND) {
                 orow[i] = bkg;
             } else {
-                const float r = __fsub_rn(load_count(rows[p] + i), bkg);
+                const float r = __fsub_rn(y[p], bkg);
                 if (out_mode == MT_SNIP_RESIDUAL) {
                     orow[i] = r;
                 } else {
