@@ -51,7 +51,7 @@ def gaussian_lines(params, names, e_consts=default_energy_consts, elem_info=defa
     return out
 
 
-def refine_tables(params, names, er, free, bounds=None, k_sigma=7.0, **kw):
+def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
     """Host tables of mt_refine for the components `names` over channels er[0]..er[1]."""
     bounds = dict(DEFAULT_BOUNDS, **(bounds or {}))
     lines = sorted(gaussian_lines(params, names, **kw), key=lambda t: float(t[0]))
