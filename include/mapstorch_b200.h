@@ -210,16 +210,16 @@ typedef struct MtRefineConfig {
 
 /* lines_host sorted by energy; chan_lines_host[c] = lo | hi << 16 is the range of line indices that can
  * contribute at channel c; comp_start_host/comp_lines_host list each component's lines;
- * line_window_host[l] = first | (last + 1) << 16 local channel of line l's window and line_off_host
- * [n_lines + 1] the prefix sums of the window lengths (validated, reserved: the kernel no longer caches
- * line values); g0inv_dev = inverse
+ * line_window_host[l] = first | (last + 1) << 16 local channel of line l's window; comp_order_host
+ * [n_comp] is a permutation of the components: warp w of the CTA's 4 takes entries w, w + 4, ... in the
+ * component-major pass, so the host orders them to balance the summed window lengths; g0inv_dev = inverse
  * Gram matrix of the unit-amplitude basis at the global parameters, fp32 [n_comp][n_comp].
  * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
  * theta_dev [n_theta][ld_x], loss_dev [n_px], iters_dev [n_px] are optional outputs. */
 int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
               int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
               const uint32_t *chan_lines_host, const int32_t *comp_start_host, const int32_t *comp_lines_host,
-              const uint32_t *line_window_host, const int32_t *line_off_host, const float *g0inv_dev,
+              const uint32_t *line_window_host, const int32_t *comp_order_host, const float *g0inv_dev,
               float *x_dev, int64_t ld_x,
               float *theta_dev, float *loss_dev, int32_t *iters_dev, void *stream);
 

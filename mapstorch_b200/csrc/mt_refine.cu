@@ -23,8 +23,18 @@
 #include <cstdlib>
 
 #include "mt_common.cuh"
+#include "mt_f32x2.cuh"
 
 namespace {
+
+using mt::add2;
+using mt::bcast2;
+using mt::f32x2;
+using mt::fma2;
+using mt::hsum2;
+using mt::mul2;
+using mt::pack2;
+using mt::unpack2;
 
 constexpr int kRefThreads = 128;  // 256 threads per pixel measured the same (70.1 ms) at equal warps per SM
 constexpr int kRefWarps = kRefThreads / 32;
@@ -40,6 +50,7 @@ struct RefParams {
     const int32_t *comp_start;      // [n_comp + 1] into comp_lines
     const int32_t *comp_lines;      // line indices grouped by component
     const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
+    const int32_t *comp_order;      // [n_comp]: permutation; warp w takes entries w, w + 4, ... (balanced by the host)
     const float *g0inv;             // [n_comp][n_comp]
     const float *bkg;
     long long ld_bkg;
@@ -84,8 +95,9 @@ refine_kernel(const RefParams p) {
     //   lc1 = {1 / sigma^2, dsigma/dFWHM_OFFSET / sigma, dsigma/dFWHM_FANOPRIME / sigma, unit}
     float4 *lc0 = dyn4;
     float4 *lc1 = dyn4 + L;
+    const int ld = (n_ch + 1) & ~1;  // even pitch: channel pairs are read and written with 64-bit accesses
     float *r_s = reinterpret_cast<float *>(dyn4 + 2 * L);
-    float *d_s = r_s + n_ch;
+    float *d_s = r_s + ld;  // d_s[k] = r_s + (k + 1) * ld
     __shared__ float xs[kMaxComp], x_prev[kMaxComp], dx[kMaxComp], gx[kMaxComp], w_s[kMaxComp];
     __shared__ float hthx[kMaxTheta][kMaxComp], t1[kMaxComp][kMaxTheta];
     __shared__ float part[kRefWarps][1 + kMaxTheta + kMaxTheta * kMaxTheta];
@@ -141,53 +153,76 @@ refine_kernel(const RefParams p) {
         __syncthreads();
 
         // ---- B1: channels -> model, theta derivatives, residual ---------------------------
-        // (chan_lines ranges are the union of the line windows; the ~1 % of pairs that lie in a range but outside
-        //  the line's own window contribute < e^-24 of the peak and are simply evaluated)
+        // Every thread takes PAIRS of adjacent channels through packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2:
+        // two channels per issue slot, the per-line constants enter as broadcast operands); the line range of a
+        // pair is the union of its channels' ranges.  chan_lines ranges are unions of line windows, so a few
+        // (line, channel) pairs outside the line's own window are evaluated too -- they are < e^-15 of the peak.
         constexpr int kAcc = 1 + NT + NT * NT;  // loss, D^T r, D^T D
-        float acc[kAcc > 0 ? kAcc : 1];
+        f32x2 acc[kAcc > 0 ? kAcc : 1];
 #pragma unroll
-        for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+        for (int i = 0; i < kAcc; ++i) acc[i] = 0ull;
         int id_k[NT > 0 ? NT : 1];
 #pragma unroll
         for (int k = 0; k < NT; ++k) id_k[k] = cfg.theta_id[k];
-        const float inv_slope = 1.f / slope;
-        for (int c = tid; c < n_ch; c += kRefThreads) {
-            const float cg = (float)(cfg.ch0 + c);
-            const float ev = fmaf(fmaf(cfg.energy_quad, cg, slope), cg, off);
-            const uint32_t range = __ldg(p.chan_lines + c);
-            float m = 0.f, d_ev = 0.f, d_fo = 0.f, d_fa = 0.f;
-            for (int l = (int)(range & 0xffffu); l < (int)(range >> 16); ++l) {
+        const f32x2 inv_slope2 = bcast2(1.f / slope), off2 = bcast2(off), slope2 = bcast2(slope),
+                    quad2 = bcast2(cfg.energy_quad), minus_one2 = bcast2(-1.f);
+        for (int q = tid; q < (ld >> 1); q += kRefThreads) {
+            const int c0 = 2 * q;
+            const bool has1 = c0 + 1 < n_ch;
+            const float cg0 = (float)(cfg.ch0 + c0);
+            const f32x2 cg = pack2(cg0, cg0 + 1.f);
+            const f32x2 ev = fma2(fma2(quad2, cg, slope2), cg, off2);
+            const uint32_t ra = __ldg(p.chan_lines + c0), rb = has1 ? __ldg(p.chan_lines + c0 + 1) : ra;
+            const int l_begin = min((int)(ra & 0xffffu), (int)(rb & 0xffffu));
+            const int l_end = max((int)(ra >> 16), (int)(rb >> 16));
+            f32x2 m = 0ull, d_ev = 0ull, d_fo = 0ull, d_fa = 0ull;
+            for (int l = l_begin; l < l_end; ++l) {
                 const float4 a0 = lc0[l];
                 const float4 a1 = lc1[l];
-                const float dl = ev - a0.x, dl2 = dl * dl;
-                const float v = a0.z * ex2_approx(a0.y * dl2);  // amplitude * unit * exp(-u^2 / 2), u = dl / sigma
-                m += v;
-                d_ev = fmaf(-(v * dl), a1.x, d_ev);             // -v u / sigma
-                const float w = v * fmaf(dl2, a1.x, -1.f);      // v (u^2 - 1); the 1 / sigma sits in a1.y, a1.z
-                d_fo = fmaf(w, a1.y, d_fo);
-                d_fa = fmaf(w, a1.z, d_fa);
+                const f32x2 dl = add2(ev, bcast2(-a0.x)), dl2 = mul2(dl, dl);
+                float e0, e1;
+                unpack2(mul2(dl2, bcast2(a0.y)), e0, e1);
+                const f32x2 v = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), bcast2(a0.z));  // amplitude * unit * exp(-u^2/2)
+                m = add2(m, v);
+                d_ev = fma2(mul2(v, dl), bcast2(-a1.x), d_ev);              // -v u / sigma
+                const f32x2 w = mul2(v, fma2(dl2, bcast2(a1.x), minus_one2));  // v (u^2 - 1); 1 / sigma sits in a1.y, a1.z
+                d_fo = fma2(w, bcast2(a1.y), d_fo);
+                d_fa = fma2(w, bcast2(a1.z), d_fa);
             }
-            const float d_slope = fmaf(d_ev, cg, m * inv_slope);
-            float d[NT > 0 ? NT : 1];
+            const f32x2 d_slope = fma2(d_ev, cg, mul2(m, inv_slope2));
+            f32x2 d[NT > 0 ? NT : 1];
 #pragma unroll
             for (int k = 0; k < NT; ++k)
                 d[k] = id_k[k] == MT_THETA_ENERGY_OFFSET ? d_ev
                        : id_k[k] == MT_THETA_ENERGY_SLOPE ? d_slope
                        : id_k[k] == MT_THETA_FWHM_OFFSET ? d_fo : d_fa;
-            const float res = m + (brow ? __ldg(brow + c) : 0.f) - ld_spec<T>(row + c);
-            r_s[c] = res;
-            acc[0] = fmaf(res, res, acc[0]);
+            const float y0 = ld_spec<T>(row + c0) - (brow ? __ldg(brow + c0) : 0.f);
+            const float y1 = has1 ? ld_spec<T>(row + c0 + 1) - (brow ? __ldg(brow + c0 + 1) : 0.f) : 0.f;
+            f32x2 res = add2(m, pack2(-y0, -y1));
+            if (!has1) {
+                // phantom channel of an odd window: contributes nothing anywhere
+                float lo, hi;
+                unpack2(res, lo, hi);
+                res = pack2(lo, 0.f);
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    unpack2(d[k], lo, hi);
+                    d[k] = pack2(lo, 0.f);
+                }
+            }
+            *reinterpret_cast<f32x2 *>(r_s + c0) = res;
+            acc[0] = fma2(res, res, acc[0]);
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                d_s[k * n_ch + c] = d[k];
-                acc[1 + k] = fmaf(d[k], res, acc[1 + k]);
+                *reinterpret_cast<f32x2 *>(d_s + k * ld + c0) = d[k];
+                acc[1 + k] = fma2(d[k], res, acc[1 + k]);
 #pragma unroll
-                for (int k2 = 0; k2 < NT; ++k2) acc[1 + NT + k * NT + k2] = fmaf(d[k], d[k2], acc[1 + NT + k * NT + k2]);
+                for (int k2 = 0; k2 < NT; ++k2) acc[1 + NT + k * NT + k2] = fma2(d[k], d[k2], acc[1 + NT + k * NT + k2]);
             }
         }
 #pragma unroll
         for (int i = 0; i < kAcc; ++i) {
-            const float v = warp_sum(acc[i]);
+            const float v = warp_sum(hsum2(acc[i]));
             if (lane == 0) {
                 // scatter into the fixed [1 + kMaxTheta + kMaxTheta^2] layout the solve reads
                 const int slot = i == 0 ? 0 : (i <= NT ? i : 1 + kMaxTheta + ((i - 1 - NT) / (NT > 0 ? NT : 1)) * kMaxTheta +
@@ -198,35 +233,42 @@ refine_kernel(const RefParams p) {
         __syncthreads();
 
         // ---- B2: components -> B^T r and D^T B over the line windows ------------------------
-        for (int e = warp; e < E; e += kRefWarps) {
-            float g = 0.f, h[NT > 0 ? NT : 1];
+        // window bounds are rounded outwards to even channels, so a lane owns the aligned pair (c, c + 1): 64-bit
+        // shared-memory loads of r and d, packed arithmetic; r and d of the phantom channel are zero
+        for (int slot = warp; slot < E; slot += kRefWarps) {
+            const int e = __ldg(p.comp_order + slot);
+            f32x2 g = 0ull, h[NT > 0 ? NT : 1];
 #pragma unroll
-            for (int k = 0; k < NT; ++k) h[k] = 0.f;
+            for (int k = 0; k < NT; ++k) h[k] = 0ull;
             const int j_end = __ldg(p.comp_start + e + 1);
             for (int j = __ldg(p.comp_start + e); j < j_end; ++j) {
                 const int l = __ldg(p.comp_lines + j);
                 const float4 a0 = lc0[l];
                 const uint32_t win = __float_as_uint(a0.w);
-                const float unit = lc1[l].w;
-                const int c_end = (int)(win >> 16);
-                int c = (int)(win & 0xffffu) + lane;
-                float cg = (float)(cfg.ch0 + c);
+                const f32x2 unit2 = bcast2(lc1[l].w), ay2 = bcast2(a0.y), me2 = bcast2(-a0.x);
+                const int c_end = min(((int)(win >> 16) + 1) & ~1, ld);
+                int c = ((int)(win & 0xffffu) & ~1) + 2 * lane;
+                const float cg0 = (float)(cfg.ch0 + c);
+                f32x2 cg = pack2(cg0, cg0 + 1.f);
                 const float *rp = r_s + c;
-                for (; c < c_end; c += 32, cg += 32.f, rp += 32) {
-                    const float dl = fmaf(fmaf(cfg.energy_quad, cg, slope), cg, off) - a0.x;
-                    const float b = unit * ex2_approx(a0.y * (dl * dl));
-                    g = fmaf(b, rp[0], g);
+                for (; c < c_end; c += 64, cg = add2(cg, bcast2(64.f)), rp += 64) {
+                    const f32x2 dl = add2(fma2(fma2(quad2, cg, slope2), cg, off2), me2);
+                    float e0, e1;
+                    unpack2(mul2(mul2(dl, dl), ay2), e0, e1);
+                    const f32x2 b = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), unit2);
+                    g = fma2(b, *reinterpret_cast<const f32x2 *>(rp), g);
 #pragma unroll
-                    for (int k = 0; k < NT; ++k) h[k] = fmaf(b, rp[(k + 1) * n_ch], h[k]);  // d_s follows r_s
+                    for (int k = 0; k < NT; ++k) h[k] = fma2(b, *reinterpret_cast<const f32x2 *>(rp + (k + 1) * ld), h[k]);
                 }
             }
-            g = warp_sum(g);
+            const float gs = warp_sum(hsum2(g));
+            float hs[NT > 0 ? NT : 1];
 #pragma unroll
-            for (int k = 0; k < NT; ++k) h[k] = warp_sum(h[k]);
+            for (int k = 0; k < NT; ++k) hs[k] = warp_sum(hsum2(h[k]));
             if (lane == 0) {
-                gx[e] = g;
+                gx[e] = gs;
 #pragma unroll
-                for (int k = 0; k < NT; ++k) hthx[k][e] = h[k];
+                for (int k = 0; k < NT; ++k) hthx[k][e] = hs[k];
             }
         }
         __syncthreads();
@@ -277,53 +319,71 @@ refine_kernel(const RefParams p) {
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            float S[kMaxTheta][kMaxTheta], rhs[kMaxTheta], sol[kMaxTheta];
+        // Schur complement of the theta block: the E-long dot products across warp 0, the NT x NT solve on lane 0
+        __shared__ float schur[kMaxTheta + kMaxTheta * kMaxTheta];
+        if (warp == 0) {
+#pragma unroll
             for (int k = 0; k < NT; ++k) {
                 float g = 0.f;
-                for (int w = 0; w < kRefWarps; ++w) g += part[w][1 + k];
-                for (int j = 0; j < E; ++j) g -= hthx[k][j] * w_s[j];
-                rhs[k] = -g;
+                for (int j = lane; j < E; j += 32) g = fmaf(hthx[k][j], w_s[j], g);
+                g = warp_sum(g);
+                if (lane == 0) schur[k] = g;
+#pragma unroll
                 for (int k2 = 0; k2 < NT; ++k2) {
                     float h = 0.f;
+                    for (int j = lane; j < E; j += 32) h = fmaf(hthx[k][j], t1[j][k2], h);
+                    h = warp_sum(h);
+                    if (lane == 0) schur[kMaxTheta + k * kMaxTheta + k2] = h;
+                }
+            }
+            __syncwarp();
+        }
+        if (tid == 0) {
+            float S[NT > 0 ? NT : 1][NT > 0 ? NT : 1], rhs[NT > 0 ? NT : 1], sol[NT > 0 ? NT : 1];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                float g = -schur[k];
+                for (int w = 0; w < kRefWarps; ++w) g += part[w][1 + k];
+                rhs[k] = -g;
+#pragma unroll
+                for (int k2 = 0; k2 < NT; ++k2) {
+                    float h = -schur[kMaxTheta + k * kMaxTheta + k2];
                     for (int w = 0; w < kRefWarps; ++w) h += part[w][1 + kMaxTheta + k * kMaxTheta + k2];
-                    for (int j = 0; j < E; ++j) h -= hthx[k][j] * t1[j][k2];
                     S[k][k2] = h;
                 }
             }
+#pragma unroll
             for (int k = 0; k < NT; ++k) S[k][k] = S[k][k] * 1.0001f + 1e-30f;
-            // Gaussian elimination with partial pivoting on the NT x NT system
-            int perm[kMaxTheta] = {0, 1, 2, 3};
+            // S is the Schur complement of a positive semi-definite Gauss-Newton matrix (plus the damping above):
+            // symmetric positive definite, so elimination needs no pivoting; fully unrolled, everything in registers
             bool ok = true;
-            for (int c = 0; c < NT && ok; ++c) {
-                int piv = c;
-                for (int q = c + 1; q < NT; ++q)
-                    if (fabsf(S[perm[q]][c]) > fabsf(S[perm[piv]][c])) piv = q;
-                const int tmp = perm[c];
-                perm[c] = perm[piv];
-                perm[piv] = tmp;
-                const float pv = S[perm[c]][c];
-                if (!(fabsf(pv) > 0.f)) { ok = false; break; }
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const float pv = S[c][c];
+                ok = ok && pv > 0.f && isfinite(pv);
+                const float inv = 1.f / pv;
+#pragma unroll
                 for (int q = c + 1; q < NT; ++q) {
-                    const float f = S[perm[q]][c] / pv;
-                    for (int cc = c; cc < NT; ++cc) S[perm[q]][cc] -= f * S[perm[c]][cc];
-                    rhs[perm[q]] -= f * rhs[perm[c]];
+                    const float f = S[q][c] * inv;
+#pragma unroll
+                    for (int cc = c; cc < NT; ++cc) S[q][cc] -= f * S[c][cc];
+                    rhs[q] -= f * rhs[c];
                 }
             }
+#pragma unroll
             for (int c = NT - 1; c >= 0; --c) {
-                float s = rhs[perm[c]];
-                for (int cc = c + 1; cc < NT; ++cc) s -= S[perm[c]][cc] * sol[cc];
-                sol[c] = ok ? s / S[perm[c]][c] : 0.f;
+                float acc_s = rhs[c];
+#pragma unroll
+                for (int cc = c + 1; cc < NT; ++cc) acc_s -= S[c][cc] * sol[cc];
+                sol[c] = ok ? acc_s / S[c][c] : 0.f;
             }
-            for (int k = 0; k < kMaxTheta; ++k) {
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
                 theta_prev[k] = theta[k];
-                float step = (k < NT && isfinite(sol[k])) ? sol[k] : 0.f;
-                if (k < NT) {
-                    const float nt = fminf(fmaxf(theta[k] + step, cfg.theta_lo[k]), cfg.theta_hi[k]);
-                    step = nt - theta[k];
-                    theta[k] = nt;
-                }
-                dtheta[k] = step;
+                const float step = isfinite(sol[k]) ? sol[k] : 0.f;
+                const float nt = fminf(fmaxf(theta[k] + step, cfg.theta_lo[k]), cfg.theta_hi[k]);
+                dtheta[k] = nt - theta[k];
+                theta[k] = nt;
             }
             ctl[1] = ctl[0];
             ctl[2] = 1.f;
@@ -389,12 +449,12 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
                          int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
                          const uint32_t *chan_lines_host, const int32_t *comp_start_host,
                          const int32_t *comp_lines_host, const uint32_t *line_window_host,
-                         const int32_t *line_off_host, const float *g0inv_dev,
+                         const int32_t *comp_order_host, const float *g0inv_dev,
                          float *x_dev, int64_t ld_x, float *theta_dev, float *loss_dev, int32_t *iters_dev,
                          void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && cfg_host && lines_host && chan_lines_host && comp_start_host && comp_lines_host &&
-                   line_window_host && line_off_host && g0inv_dev && x_dev,
+                   line_window_host && comp_order_host && g0inv_dev && x_dev,
                "mt_refine: null pointer");
     const MtRefineConfig &cfg = *cfg_host;
     MT_REQUIRE(cfg.n_ch > 0 && cfg.n_ch <= 8192 && cfg.ch0 >= 0 && ld_spec >= (int64_t)cfg.ch0 + cfg.n_ch,
@@ -405,16 +465,24 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     MT_REQUIRE(n_px >= 0 && ld_x >= n_px && (!bkg_dev || ld_bkg >= cfg.n_ch), "mt_refine: sizes");
     for (int l = 0; l < cfg.n_lines; ++l)
         MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp, "mt_refine: line %d component", l);
+    {
+        bool seen[kMaxComp] = {false};
+        for (int e = 0; e < cfg.n_comp; ++e) {
+            const int c = comp_order_host[e];
+            MT_REQUIRE(c >= 0 && c < cfg.n_comp && !seen[c], "mt_refine: comp_order is not a permutation (entry %d)", e);
+            seen[c] = true;
+        }
+    }
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
     // stage the small tables in one stream-ordered scratch allocation
     const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
-                 b_lw = sizeof(uint32_t) * cfg.n_lines;
+                 b_lw = sizeof(uint32_t) * cfg.n_lines, b_co = sizeof(int32_t) * cfg.n_comp;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char *scratch = nullptr;
-    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw), stream));
+    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co), stream));
     char *q = scratch;
     RefParams p{};
     p.cfg = cfg;
@@ -429,6 +497,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.comp_start = static_cast<const int32_t *>(stage(comp_start_host, b_cs));
     p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
     p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
+    p.comp_order = static_cast<const int32_t *>(stage(comp_order_host, b_co));
     MT_CUDA_TRY(cudaGetLastError());
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
@@ -441,7 +510,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.loss_out = loss_dev;
     p.iters_out = iters_dev;
     p.n_px = n_px;
-    const size_t smem = sizeof(float) * (size_t)cfg.n_ch * (1 + cfg.n_theta) + 2 * sizeof(float4) * (size_t)cfg.n_lines;
+    const size_t smem = sizeof(float) * (size_t)((cfg.n_ch + 1) & ~1) * (1 + cfg.n_theta) +
+                        2 * sizeof(float4) * (size_t)cfg.n_lines;
     if (smem > 200 * 1024)
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: %zu bytes of shared memory needed (channels x free parameters)",
                         smem);

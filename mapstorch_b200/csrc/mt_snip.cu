@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 
 #include "mt_common.cuh"
+#include "mt_f32x2.cuh"
 
 namespace {
 
@@ -41,27 +42,10 @@ __device__ __forceinline__ float clip(float a, float b, float c) {
     return fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), c);
 }
 
-// Packed fp32 arithmetic of sm_100 (FADD2 / FMUL2: two IEEE round-to-nearest operations per issue slot, bit-identical
-// to the scalar forms).  The kernel is issue / shared-memory bound, not FP32-pipe bound, so halving the slots of the
-// adds and multiplies of the 4-pixel records is a direct gain.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
+using mt::add2;
+using mt::mul2;
+using mt::pack2;
+using mt::unpack2;
 
 // cur <- min((a + b) / 2, cur) for the four pixels of a record
 __device__ __forceinline__ void clip4(const float4 &a, const float4 &b, float4 &cur) {

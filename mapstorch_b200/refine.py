@@ -17,6 +17,8 @@ from mapstorch_b200.default import default_energy_consts, default_elem_info, def
 
 f32 = np.float32
 
+REFINE_WARPS = 4  # warps per CTA of mt_refine (csrc/mt_refine.cu: kRefThreads / 32)
+
 DEFAULT_BOUNDS = {
     "ENERGY_OFFSET": ("abs", 0.03),       # +- keV around the global value
     "ENERGY_SLOPE": ("rel", 0.01),        # +- 1 %
@@ -100,10 +102,20 @@ def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
     counts = np.bincount([lines[i][2] for i in order], minlength=len(names))
     comp_start = np.zeros(len(names) + 1, dtype=np.int32)
     np.cumsum(counts, out=comp_start[1:])
+    # schedule of the component-major pass: the CTA's 4 warps take entries w, w + 4, ... of comp_order; deal the
+    # components out by decreasing cost (summed window lengths) in serpentine order so that the warps finish together
     lengths = (window >> 16).astype(np.int64) - (window & 0xFFFF).astype(np.int64)
-    line_off = np.zeros(len(lines) + 1, dtype=np.int32)
-    np.cumsum(lengths, out=line_off[1:])
-    return cfg, arr, chan_lines, comp_start, comp_lines, window, line_off
+    cost = np.zeros(len(names), dtype=np.int64)
+    for i, line in enumerate(lines):
+        cost[line[2]] += lengths[i] + 16  # + per-line overhead
+    ranked = sorted(range(len(names)), key=lambda c: (-int(cost[c]), c))
+    comp_order = np.zeros(len(names), dtype=np.int32)
+    for r0 in range(0, len(ranked), REFINE_WARPS):
+        chunk = ranked[r0: r0 + REFINE_WARPS]
+        if (r0 // REFINE_WARPS) % 2:
+            chunk = chunk[::-1] if len(chunk) == REFINE_WARPS else chunk
+        comp_order[r0: r0 + len(chunk)] = chunk
+    return cfg, arr, chan_lines, comp_start, comp_lines, window, comp_order
 
 
 def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=None, max_iter=12, tol=1e-6,
@@ -117,7 +129,7 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
     unknown = [f for f in free if f not in _native.THETA_IDS]
     if unknown or len(free) > 4:
         raise ValueError(f"free parameters must be a subset of {sorted(_native.THETA_IDS)}, got {free}")
-    cfg, lines, chan_lines, comp_start, comp_lines, window, line_off = refine_tables(plan.params, plan.names, plan.er,
+    cfg, lines, chan_lines, comp_start, comp_lines, window, comp_order = refine_tables(plan.params, plan.names, plan.er,
                                                                                   free, bounds)
     cfg.max_iter, cfg.tol = int(max_iter), float(tol)
     n_px = spec2d.shape[0]
@@ -132,7 +144,7 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
                  bkg.data_ptr() if bkg is not None else None, bkg.stride(0) if bkg is not None else 0,
                  ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p), chan_lines.ctypes.data_as(ctypes.c_void_p),
                  comp_start.ctypes.data_as(ctypes.c_void_p), comp_lines.ctypes.data_as(ctypes.c_void_p),
-                 window.ctypes.data_as(ctypes.c_void_p), line_off.ctypes.data_as(ctypes.c_void_p),
+                 window.ctypes.data_as(ctypes.c_void_p), comp_order.ctypes.data_as(ctypes.c_void_p),
                  plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
                  theta.data_ptr(), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
     return theta[: len(free)], loss, iters
