@@ -29,6 +29,22 @@ int require_sm100();
         if (!(cond)) return ::mt::fail(MT_ERR_INVALID, __VA_ARGS__);   \
     } while (0)
 
+// stream-ordered scratch allocation that is returned on every exit path of an entry point
+struct StreamScratch {
+    char *ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    StreamScratch() = default;
+    StreamScratch(const StreamScratch &) = delete;
+    StreamScratch &operator=(const StreamScratch &) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        stream = s;
+        return cudaMallocAsync(reinterpret_cast<void **>(&ptr), bytes, s);
+    }
+    ~StreamScratch() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+    }
+};
+
 inline int num_sms() {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);

@@ -89,8 +89,9 @@ extern "C" int mt_model_terms(const float *ev_dev, int32_t n_ch, const MtTerm *t
     const int n_terms = col_start_host[n_cols];
     const size_t term_bytes = sizeof(MtTerm) * (size_t)(n_terms > 0 ? n_terms : 1);
     const size_t idx_bytes = sizeof(int32_t) * (size_t)(n_cols + 1);
-    char *scratch = nullptr;
-    MT_CUDA_TRY(cudaMallocAsync(&scratch, term_bytes + idx_bytes, stream));
+    mt::StreamScratch holder;
+    MT_CUDA_TRY(holder.alloc(term_bytes + idx_bytes, stream));
+    char *scratch = holder.ptr;
     if (n_terms > 0)
         MT_CUDA_TRY(cudaMemcpyAsync(scratch, terms_host, sizeof(MtTerm) * (size_t)n_terms,
                                     cudaMemcpyHostToDevice, stream));
@@ -101,8 +102,7 @@ extern "C" int mt_model_terms(const float *ev_dev, int32_t n_ch, const MtTerm *t
                                                       reinterpret_cast<const int *>(scratch + term_bytes),
                                                       out_dev, ld_out);
     MT_CUDA_TRY(cudaGetLastError());
-    MT_CUDA_TRY(cudaFreeAsync(scratch, stream));
-    return MT_OK;
+    return MT_OK;  // the scratch goes back to the pool in stream order (StreamScratch)
 }
 
 extern "C" int mt_model_sum(const float *cols_dev, int64_t ld_cols, int32_t n_cols, int32_t n_ch,

@@ -21,6 +21,8 @@
 // path (map.py:152-208 with f_step = 0, elastic, Compton Gaussian); exp dominates (MUFU bound).
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "mt_common.cuh"
 #include "mt_f32x2.cuh"
@@ -476,20 +478,22 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-    // stage the small tables in one stream-ordered scratch allocation
+    // stage the small tables: packed on the host, ONE copy into one stream-ordered scratch allocation
     const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
                  b_lw = sizeof(uint32_t) * cfg.n_lines, b_co = sizeof(int32_t) * cfg.n_comp;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    char *scratch = nullptr;
-    MT_CUDA_TRY(cudaMallocAsync(&scratch, up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co), stream));
-    char *q = scratch;
+    const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co);
+    mt::StreamScratch holder;  // returned to the pool in stream order on every exit path
+    MT_CUDA_TRY(holder.alloc(total, stream));
+    std::vector<char> packed(total);
+    size_t cursor = 0;
     RefParams p{};
     p.cfg = cfg;
     auto stage = [&](const void *src, size_t bytes) -> const void * {
-        cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, stream);
-        const void *dst = q;
-        q += up(bytes);
+        memcpy(packed.data() + cursor, src, bytes);
+        const void *dst = holder.ptr + cursor;
+        cursor += up(bytes);
         return dst;
     };
     p.lines = static_cast<const MtRefineLine *>(stage(lines_host, b_lines));
@@ -498,6 +502,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
     p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
     p.comp_order = static_cast<const int32_t *>(stage(comp_order_host, b_co));
+    // pageable source: the runtime copies it out before returning, so `packed` may die with this frame
+    MT_CUDA_TRY(cudaMemcpyAsync(holder.ptr, packed.data(), total, cudaMemcpyHostToDevice, stream));
     MT_CUDA_TRY(cudaGetLastError());
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
@@ -543,10 +549,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     } else if (dtype == MT_DTYPE_F16) {
         MT_LAUNCH_REFINE(__half);
     } else {
-        cudaFreeAsync(scratch, stream);
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: dtype %d", dtype);
     }
     MT_CUDA_TRY(cudaGetLastError());
-    MT_CUDA_TRY(cudaFreeAsync(scratch, stream));
     return MT_OK;
 }

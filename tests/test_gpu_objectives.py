@@ -137,7 +137,7 @@ def test_fit_map_penalty_per_pixel(dtype, use_snip, with_idx):
     y = rng.poisson(amps @ Bt.astype(np.float64).T + (3.0 if use_snip else 0.0)).astype(np.float32)
     assert y.max() < 2048
     idx = np.r_[60:900, 950:1500] if with_idx else None
-    lam = 2e-6
+    lam = 2e-5
     vol = torch.from_numpy(y).to(dtype).cuda()
     maps, plan = opt.fit_map(vol, er, fitted, p, use_snip=use_snip, indices=idx, l1_lambda=lam, return_plan=True)
     B, names = mo.basis(p, er, fitted)
