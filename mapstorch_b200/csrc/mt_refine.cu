@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "mt_common.cuh"
@@ -445,6 +446,56 @@ refine_kernel(const RefParams p) {
     }
 }
 
+// ---- device-resident copies of the host tables, keyed by content -------------------------------------------
+struct TableEntry {
+    int device = -1;
+    uint64_t hash = 0;
+    std::vector<char> host;  // full comparison on a hash match
+    char *dev = nullptr;
+    uint64_t stamp = 0;
+};
+constexpr int kTableSlots = 16;
+TableEntry g_tables[kTableSlots];
+std::mutex g_tables_mutex;
+uint64_t g_tables_clock = 0;
+
+int cached_tables(const std::vector<char> &packed, const char **out) {
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over 8-byte words (the buffer is padded to 256-byte pieces)
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(packed.data());
+    for (size_t i = 0; i < packed.size() / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    int dev = 0;
+    MT_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    int victim = 0;
+    for (int i = 0; i < kTableSlots; ++i) {
+        TableEntry &t = g_tables[i];
+        if (t.dev && t.device == dev && t.hash == h && t.host == packed) {
+            t.stamp = ++g_tables_clock;
+            *out = t.dev;
+            return MT_OK;
+        }
+        if (g_tables[i].stamp < g_tables[victim].stamp) victim = i;
+    }
+    TableEntry &t = g_tables[victim];
+    if (t.dev) {
+        // a kernel of an earlier call may still be reading the evicted tables
+        int cur = dev;
+        if (t.device != cur) cudaSetDevice(t.device);
+        cudaDeviceSynchronize();
+        cudaFree(t.dev);
+        if (t.device != cur) cudaSetDevice(cur);
+        t.dev = nullptr;
+    }
+    MT_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&t.dev), packed.size()));
+    MT_CUDA_TRY(cudaMemcpy(t.dev, packed.data(), packed.size(), cudaMemcpyHostToDevice));  // synchronous: visible to every stream
+    t.device = dev;
+    t.hash = h;
+    t.host = packed;
+    t.stamp = ++g_tables_clock;
+    *out = t.dev;
+    return MT_OK;
+}
+
 }  // namespace
 
 extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
@@ -478,33 +529,41 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-    // stage the small tables: packed on the host, ONE copy into one stream-ordered scratch allocation
+    // the small tables, packed into one host buffer
     const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch,
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
                  b_lw = sizeof(uint32_t) * cfg.n_lines, b_co = sizeof(int32_t) * cfg.n_comp;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co);
-    mt::StreamScratch holder;  // returned to the pool in stream order on every exit path
-    MT_CUDA_TRY(holder.alloc(total, stream));
     std::vector<char> packed(total);
     size_t cursor = 0;
     RefParams p{};
     p.cfg = cfg;
-    auto stage = [&](const void *src, size_t bytes) -> const void * {
+    size_t o_lines, o_chan, o_cs, o_cl, o_lw, o_co;
+    auto stage = [&](const void *src, size_t bytes) -> size_t {
         memcpy(packed.data() + cursor, src, bytes);
-        const void *dst = holder.ptr + cursor;
+        const size_t at = cursor;
         cursor += up(bytes);
-        return dst;
+        return at;
     };
-    p.lines = static_cast<const MtRefineLine *>(stage(lines_host, b_lines));
-    p.chan_lines = static_cast<const uint32_t *>(stage(chan_lines_host, b_chan));
-    p.comp_start = static_cast<const int32_t *>(stage(comp_start_host, b_cs));
-    p.comp_lines = static_cast<const int32_t *>(stage(comp_lines_host, b_cl));
-    p.line_window = static_cast<const uint32_t *>(stage(line_window_host, b_lw));
-    p.comp_order = static_cast<const int32_t *>(stage(comp_order_host, b_co));
-    // pageable source: the runtime copies it out before returning, so `packed` may die with this frame
-    MT_CUDA_TRY(cudaMemcpyAsync(holder.ptr, packed.data(), total, cudaMemcpyHostToDevice, stream));
-    MT_CUDA_TRY(cudaGetLastError());
+    o_lines = stage(lines_host, b_lines);
+    o_chan = stage(chan_lines_host, b_chan);
+    o_cs = stage(comp_start_host, b_cs);
+    o_cl = stage(comp_lines_host, b_cl);
+    o_lw = stage(line_window_host, b_lw);
+    o_co = stage(comp_order_host, b_co);
+    // The tables are the same for every slab of a map.  Uploading them per call would put a host-to-device copy
+    // in front of every launch, and that copy queues on the DMA engine BEHIND the next slab of the volume that
+    // a streaming caller is already sending -- the kernel would wait for it.  So device copies are kept in a small
+    // content-addressed cache; a miss uploads synchronously (once per plan), a hit costs one hash of ~10 KB.
+    const char *tables = nullptr;
+    if (int rc = cached_tables(packed, &tables)) return rc;
+    p.lines = reinterpret_cast<const MtRefineLine *>(tables + o_lines);
+    p.chan_lines = reinterpret_cast<const uint32_t *>(tables + o_chan);
+    p.comp_start = reinterpret_cast<const int32_t *>(tables + o_cs);
+    p.comp_lines = reinterpret_cast<const int32_t *>(tables + o_cl);
+    p.line_window = reinterpret_cast<const uint32_t *>(tables + o_lw);
+    p.comp_order = reinterpret_cast<const int32_t *>(tables + o_co);
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
     p.ld_bkg = ld_bkg;

@@ -128,6 +128,7 @@ class MapFitPlan:
                             if k in default_param_vals})
         self.use_snip = bool(use_snip)
         self.boxcar_size = int(boxcar_size)
+        self.e_consts, self.elem_info = e_consts, elem_info  # the refinement builds its line tables from them
         elements = list(dict.fromkeys(list(elements_to_fit)))
         self.basis, self.names = _map.element_basis(self.params, self.er, elements, e_consts, elem_info,
                                                     detector_type, escape_factor)
@@ -429,10 +430,13 @@ class MapFitPlan:
         return out
 
 
-def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0):
+def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0, after_slab=None):
     """Stream a HOST volume [P, C] through the device in row slabs: slab k+1 is copied
     host->device on a second stream while slab k is being fitted (pinned host memory makes the
-    copies asynchronous).  Returns x [E, P] on the device."""
+    copies asynchronous).  Returns x [E, P] on the device.
+
+    after_slab(dev_slab, p0, n, x_slab), if given, runs on the compute stream right after the fit of each
+    slab while the slab is still resident (per-pixel refinement uses it), so the volume crosses PCIe once."""
     n_px, n_ch = host2d.shape
     out = torch.zeros((len(self.names), n_px), dtype=torch.float32, device="cuda")
     chunk = max(1, min(int(chunk_px), n_px))
@@ -459,6 +463,8 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
             too_big[i] = bufs[b][:n, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0
         self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
                  exact_counts=True if check else None, l1_lambda=l1_lambda)
+        if after_slab is not None:
+            after_slab(bufs[b][:n], p0, n, out[:, p0: p0 + n])
         consumed[b].record(compute)
     if check:
         for i in torch.nonzero(too_big).flatten().tolist():
@@ -467,6 +473,8 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
             bufs[0][:n].copy_(host2d[p0: p0 + n])
             self.fit(bufs[0][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine, exact_counts="split",
                      l1_lambda=l1_lambda)
+            if after_slab is not None:
+                after_slab(bufs[0][:n], p0, n, out[:, p0: p0 + n])
     for buf in bufs:
         buf.record_stream(compute)
     return out
@@ -566,32 +574,41 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         params.update(fixed_param_vals)
         plan = _cached_plan(energy_range, elements_to_fit, params, indices, use_snip, e_consts, elem_info,
                             detector_type, escape_factor)
-    if flat.device.type == "cuda":
-        x = plan.fit(flat, nonneg=nonneg, engine=engine, l1_lambda=l1_lambda)
-    else:
-        x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px, l1_lambda=l1_lambda)
     extra = {}
+    refine_slab = None
     if refine:
-        # per-pixel nonlinear refinement of peak-shape parameters + amplitudes (kernel K4)
+        # per-pixel nonlinear refinement of peak-shape parameters + amplitudes (kernel K4), slab by slab so that
+        # neither a host volume nor the SNIP background has to be resident as a whole
         from mapstorch_b200.refine import refine_map
 
-        # slab by slab, so that neither a host volume nor the SNIP background has to be resident as a whole
         n_px = flat.shape[0]
         theta = torch.empty((len(refine), n_px), dtype=torch.float32, device="cuda")
-        loss = torch.empty(n_px, dtype=torch.float32, device="cuda")
+        loss_px = torch.empty(n_px, dtype=torch.float32, device="cuda")
         iters = torch.empty(n_px, dtype=torch.int32, device="cuda")
-        p = plan.params
-        snip_args = [torch.tensor(float(p[k])) for k in (
-            "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")]
-        for p0 in range(0, n_px, SNIP_CHUNK_PX):
-            p1 = min(p0 + SNIP_CHUNK_PX, n_px)
-            dev = flat[p0:p1] if flat.device.type == "cuda" else flat[p0:p1].cuda()
-            bkg = _bkg.snip_bkg(dev[:, plan.er[0]: plan.er[1] + 1], plan.er, *snip_args, device="cuda") if plan.use_snip else None
-            t, l, it = refine_map(plan, dev, x[:, p0:p1], free=tuple(refine), bounds=refine_bounds,
-                                  max_iter=refine_iters, bkg=bkg)
-            theta[:, p0:p1], loss[p0:p1], iters[p0:p1] = t, l, it
+
+        def refine_slab(dev, p0, n, x_slab):
+            bkg = None
+            if plan.use_snip:  # same tables as the fit (plan._snip), one kernel, no host work per slab
+                bkg = torch.empty((n, plan.n_ch), dtype=torch.float32, device="cuda")
+                _bkg.snip_launch(dev, plan.er[0], plan.n_ch, plan._snip[0], plan._snip[1], plan.boxcar_size, bkg,
+                                 _native.MT_SNIP_BACKGROUND)
+            t, l, it = refine_map(plan, dev, x_slab, free=tuple(refine), bounds=refine_bounds, max_iter=refine_iters,
+                                  bkg=bkg)
+            theta[:, p0: p0 + n], loss_px[p0: p0 + n], iters[p0: p0 + n] = t, l, it
+
         extra = {name: theta[i] for i, name in enumerate(refine)}
-        extra["loss"], extra["iterations"] = loss, iters
+        extra["loss"], extra["iterations"] = loss_px, iters
+    if flat.device.type == "cuda":
+        x = plan.fit(flat, nonneg=nonneg, engine=engine, l1_lambda=l1_lambda)
+        if refine_slab is not None:
+            for p0 in range(0, flat.shape[0], SNIP_CHUNK_PX):
+                p1 = min(p0 + SNIP_CHUNK_PX, flat.shape[0])
+                refine_slab(flat[p0:p1], p0, p1 - p0, x[:, p0:p1])
+    else:
+        # the slab is fitted and refined while it is resident: the volume crosses PCIe once, and the next slab's
+        # copy overlaps both kernels
+        x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px, l1_lambda=l1_lambda,
+                          after_slab=refine_slab)
     if as_log10:
         x = torch.log10(x)
     if torch.device(device).type != "cuda":

@@ -129,8 +129,14 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
     unknown = [f for f in free if f not in _native.THETA_IDS]
     if unknown or len(free) > 4:
         raise ValueError(f"free parameters must be a subset of {sorted(_native.THETA_IDS)}, got {free}")
-    cfg, lines, chan_lines, comp_start, comp_lines, window, comp_order = refine_tables(plan.params, plan.names, plan.er,
-                                                                                  free, bounds)
+    # the host tables depend only on the plan and the free parameters: built once, reused for every slab
+    key = (tuple(free), tuple(sorted((bounds or {}).items())))
+    cache = plan.__dict__.setdefault("_refine_tables", {})
+    if key not in cache:
+        cache[key] = refine_tables(plan.params, plan.names, plan.er, free, bounds,
+                                   e_consts=getattr(plan, "e_consts", default_energy_consts),
+                                   elem_info=getattr(plan, "elem_info", default_elem_info))
+    cfg, lines, chan_lines, comp_start, comp_lines, window, comp_order = cache[key]
     cfg.max_iter, cfg.tol = int(max_iter), float(tol)
     n_px = spec2d.shape[0]
     if not hasattr(plan, "_g0inv32"):
