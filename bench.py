@@ -194,6 +194,29 @@ def run_reference(args, rank, world, emit):
     emit(line)
 
 
+def bind_near_gpu(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (same NUMA node / PCIe root), so
+    that the pinned staging buffers of the end-to-end leg are allocated next to the GPU they feed.  With 8 ranks
+    streaming 4.3 GB each, remote-socket pinned memory halves the per-GPU host-to-device rate.  Returns the
+    previous affinity (to restore) or None when NVML / sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        previous = os.sched_getaffinity(0)
+        cpus &= previous
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return previous
+    except Exception as exc:  # noqa: BLE001 - best effort, the run is valid without it
+        print(f"[bench] no NUMA binding: {exc}", file=sys.stderr)
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,6 +373,7 @@ def main():
     # ---- end to end through the public API, host buffers ------------------------------------------
     e2e = None
     if not args.no_e2e:
+        previous_affinity = bind_near_gpu(local_rank)
         host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
         host.copy_(flat)
         torch.cuda.synchronize()
@@ -364,8 +388,11 @@ def main():
         e2e = {"value": world * n_px / (ms * 1e-3), "unit": "px/s", "h2d_bytes_per_step": world * flat.numel() * es,
                "d2h_bytes_per_step": world * n_comp * n_px * 4, "ms_per_step": ms, "steps": args.e2e_steps,
                "api": "mapstorch_b200.opt.fit_map(pinned host volume) -> host maps; plan build, chunked H2D "
-                      "overlapped with the fit, D2H of the maps all inside the timed region"}
+                      "overlapped with the fit, D2H of the maps all inside the timed region",
+               "numa_bound": previous_affinity is not None}
         del host
+        if previous_affinity is not None:
+            os.sched_setaffinity(0, previous_affinity)  # the CPU baseline below uses every core again
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
