@@ -152,13 +152,20 @@ def cpu_baseline_refine(w, params, er, elems, budget_s=12.0):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rng = np.random.default_rng(0)
     B, _ = mo.basis(params, er, elems)
-    n = max(cores, int(cores * max(1.0, budget_s / 0.6)))  # ~0.3 s per pixel and core
-    amps = 10.0 ** rng.uniform(1.5, 3.0, size=(n, B.shape[1]))
-    y = rng.poisson(amps @ B.astype(np.float64).T + w["flat"]).astype(np.float32)
-    jobs = [(y[i], params, er, list(elems), tuple(w["refine"])) for i in range(n)]
+
+    def sample(n):
+        amps = 10.0 ** rng.uniform(1.5, 3.0, size=(n, B.shape[1]))
+        y = rng.poisson(amps @ B.astype(np.float64).T + w["flat"]).astype(np.float32)
+        return [(y[i], params, er, list(elems), tuple(w["refine"])) for i in range(n)]
+
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_refine_worker, jobs[:cores])  # start the workers, import scipy
+        pool.map(_refine_worker, sample(cores))  # start the workers, import scipy
+        t0 = time.perf_counter()
+        pool.map(_refine_worker, sample(2 * cores), chunksize=1)
+        per_round = (time.perf_counter() - t0) / 2  # seconds for one pixel on every core
+        n = cores * max(2, int(budget_s / max(per_round, 1e-3)))
+        jobs = sample(n)
         t0 = time.perf_counter()
         pool.map(_refine_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
