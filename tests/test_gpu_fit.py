@@ -293,3 +293,43 @@ def test_all_default_components_at_high_incident_energy():
     r_mine = ((y - xn @ B.T.astype(np.float64)) ** 2).sum(axis=1)
     r_ref = ((y - refn @ B[:, live].T.astype(np.float64)) ** 2).sum(axis=1)
     assert np.all(r_mine <= r_ref * (1 + 1e-4))
+
+
+def test_fit_map_with_override_file_constants(tmp_path):
+    """e_consts edited by a MAPS override file (Fe K-beta x1.2, Ge absorption column, ...) reach the basis,
+    the Gram matrix and the per-pixel refinement tables: fit a volume generated WITH those constants and
+    compare with float64 NNLS on the oracle's basis for the same constants; the default constants must fit
+    the same volume visibly worse."""
+    from mapstorch_b200 import constant, io as mio, opt
+    from mapstorch_b200.default import default_elem_info
+    from oracle import maps_oracle as mo
+
+    path = tmp_path / "maps_fit_parameters_override.txt"
+    mio.write_override_params_file(str(path), {"COHERENT_SCT_ENERGY": 12.0}, ["Fe", "Cu", "Zn", "Gd_L", "Pt_L"], "Ge", 0.0)
+    consts = constant.read_constants(str(path), default_elem_info)
+    cfg = mio.parse_override_params_file(str(path))
+    p = params12()
+    elems, er = cfg["elements_to_fit"], (0, 2047)
+    assert cfg["detector_material"] == "Ge" and elems == ["Fe", "Cu", "Zn", "Gd_L", "Pt_L"]
+    B, names = mo.basis(p, er, elems, e_consts=consts, elem_info=default_elem_info)
+    rng = np.random.default_rng(8)
+    amps = 10.0 ** rng.uniform(2.0, 3.0, size=(96, B.shape[1]))
+    y = rng.poisson(amps @ B.astype(np.float64).T).astype(np.float32)
+    maps, plan = opt.fit_map(torch.from_numpy(y).cuda(), er, elems, p, use_snip=False, e_consts=consts,
+                             return_plan=True)
+    assert plan.e_consts is consts
+    got = np.stack([maps[n].cpu().numpy() for n in names], axis=1)
+    ref = mo.fit_nnls(y, B)
+    check_against(got, ref)
+    plain = opt.fit_map(torch.from_numpy(y).cuda(), er, elems, p, use_snip=False)
+    worse = np.stack([plain[n].cpu().numpy() for n in names], axis=1)
+    resid = lambda a: float((((a.astype(np.float64) @ B.astype(np.float64).T) - y) ** 2).sum())  # noqa: E731
+    assert resid(worse) > 1.05 * resid(got)
+    # refinement builds its line tables from the plan's constants too (with ~1e3 counts per pixel the calibration
+    # itself is statistically loose, so the check is on the objective and the bounds)
+    fine = opt.fit_map(torch.from_numpy(y[:16]).cuda(), er, elems, p, use_snip=False, e_consts=consts,
+                       refine=("ENERGY_OFFSET", "FWHM_OFFSET"))
+    assert float((fine["ENERGY_OFFSET"] - p["ENERGY_OFFSET"]).abs().max()) <= 0.03 + 1e-6
+    assert float((fine["FWHM_OFFSET"] / p["FWHM_OFFSET"] - 1).abs().max()) <= 0.30 + 1e-6
+    sse = (((got[:16].astype(np.float64) @ B.astype(np.float64).T) - y[:16]) ** 2).sum(axis=1)
+    assert np.all(fine["loss"].cpu().numpy() <= sse * (1 + 1e-5))  # refining can only lower the objective
