@@ -117,6 +117,19 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
             int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar, float *out_dev,
             int64_t ld_out, int32_t out_mode, void *stream);
 
+/* The same kernel driven by a pre-scaled gather table: scaled_dev = (n_pass + 1) rows of ld_scaled words,
+ * word = (lo * 16) | (hi * 16) << 16 (shared-memory byte offsets of the 4-pixel records), entries past n_ch and
+ * the extra last row are 0 -- the clipping passes then need no index arithmetic and no bounds tests.
+ * mt_snip_scaled_pitch(n_ch) gives the row pitch (n_ch rounded up to the kernel's thread grid; 0 when n_ch > 4096,
+ * where byte offsets no longer fit 16 bits and mt_snip must be used); mt_snip_scale_tables converts lohi_dev
+ * (once per calibration, one tiny launch). */
+int mt_snip_scaled_pitch(int32_t n_ch);
+int mt_snip_scale_tables(const uint32_t *lohi_dev, int32_t n_pass, int32_t n_ch, uint32_t *scaled_dev,
+                         int32_t ld_scaled, void *stream);
+int mt_snip_scaled(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0, int32_t n_ch,
+                   const uint32_t *scaled_dev, int32_t ld_scaled, int32_t n_pass, int32_t boxcar, float *out_dev,
+                   int64_t ld_out, int32_t out_mode, void *stream);
+
 /* K3 -- the per-pixel amplitude solve: replaces the Adam loop of fit_spec (opt.py:249-317)
  * for fixed global parameters, where the model is linear in the amplitudes.
  *   x[e][p] = colscale[e] * sum_d plane_ratio^d * ( sum_k spec[p][k] * wpack[d*e_pad + e][k] )

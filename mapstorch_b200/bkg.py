@@ -14,12 +14,27 @@ from mapstorch_b200.constant import M_SQRT2  # noqa: F401
 
 
 def snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+    """(gather table [n_pass, n_ch] int32 on the device, n_pass).  For windows of up to 4096 channels the table
+    also carries its pre-scaled form (mt_snip_scale_tables) as attribute ``_mt_scaled``; snip_launch picks it up."""
     tab = tables.snip_tables(n_ch, er[0], e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
-    return torch.from_numpy(tab.view(np.int32)).to("cuda"), tab.shape[0]
+    lohi = torch.from_numpy(tab.view(np.int32)).to("cuda")
+    pitch = _native.load().mt_snip_scaled_pitch(int(n_ch))
+    if pitch > 0 and tab.shape[0] > 0:
+        scaled = torch.empty((tab.shape[0] + 1, pitch), dtype=torch.int32, device="cuda")
+        _native.call("mt_snip_scale_tables", lohi.data_ptr(), tab.shape[0], int(n_ch), scaled.data_ptr(), pitch,
+                     _native.stream_ptr())
+        lohi._mt_scaled = scaled
+    return lohi, tab.shape[0]
 
 
 def snip_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode, stream=None):
     """spec2d: CUDA [P, ld] fp32/fp16 (row-contiguous); out: CUDA fp32 [P, ld_out]."""
+    scaled = getattr(lohi_dev, "_mt_scaled", None)
+    if scaled is not None and scaled.shape[0] == int(n_pass) + 1:
+        _native.call("mt_snip_scaled", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.shape[0],
+                     spec2d.stride(0), int(ch0), int(n_ch), scaled.data_ptr(), scaled.stride(0), int(n_pass),
+                     int(boxcar_size), out.data_ptr(), out.stride(0), int(out_mode), _native.stream_ptr(stream))
+        return out
     _native.call("mt_snip", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.shape[0], spec2d.stride(0),
                  int(ch0), int(n_ch), lohi_dev.data_ptr(), int(n_pass), int(boxcar_size), out.data_ptr(),
                  out.stride(0), int(out_mode), _native.stream_ptr(stream))

@@ -78,10 +78,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4 &v) {
 }
 
 // KCH channels per thread (n_ch <= kSnipThreads * KCH); 4 pixels per CTA.
-template <typename T, int KCH>
+// SCALED: the gather table holds shared-memory BYTE offsets (lo * 16 | hi * 16 << 16, mt_snip_scale_tables), its rows
+// are padded to the thread grid and followed by a zero row, so the pass loop needs no shifts and no bounds tests.
+template <typename T, int KCH, bool SCALED>
 __global__ void __launch_bounds__(kSnipThreads, (KCH <= 4 ? 3 : (KCH <= 8 ? 2 : 1)))
 snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int ch0, int n_ch,
-            const uint32_t *__restrict__ lohi, int n_pass, int boxcar, float *__restrict__ out,
+            const uint32_t *__restrict__ lohi, int ld_tab, int n_pass, int boxcar, float *__restrict__ out,
             long long ld_out, int out_mode) {
     extern __shared__ float4 sb[];  // [n_ch] x (4 pixels)
     const int tid = threadIdx.x;
@@ -152,19 +154,22 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
 #pragma unroll
     for (int k = 0; k < KCH; ++k) {
         const int i = tid + k * kSnipThreads;
-        tab[k] = (n_pass > 0 && i < n_ch) ? __ldg(lohi + i) : 0u;
+        if (SCALED)
+            tab[k] = __ldg(lohi + i);
+        else
+            tab[k] = (n_pass > 0 && i < n_ch) ? __ldg(lohi + i) : 0u;
     }
     __syncthreads();
     const uint32_t sb_base = static_cast<uint32_t>(__cvta_generic_to_shared(sb));
     for (int pass = 0; pass < n_pass; ++pass) {
-        const uint32_t *next = lohi + (long long)(pass + 1) * n_ch;
+        const uint32_t *next = lohi + (long long)(pass + 1) * ld_tab;
         const bool more = pass + 1 < n_pass;
         // channels past n_ch carry index word 0: they read channel 0 and their result is never stored
 #pragma unroll
         for (int k = 0; k < KCH; ++k) {
             const int i = tid + k * kSnipThreads;
-            const float4 a = lds128(sb_base + ((tab[k] & 0xffffu) << 4));
-            const float4 b = lds128(sb_base + ((tab[k] >> 12) & 0xffff0u));
+            const float4 a = lds128(sb_base + (SCALED ? (tab[k] & 0xffffu) : ((tab[k] & 0xffffu) << 4)));
+            const float4 b = lds128(sb_base + (SCALED ? (tab[k] >> 16) : ((tab[k] >> 12) & 0xffff0u)));
             // this word is consumed: fetch the next pass's (from L2) behind the rest of the pass
             tab[k] = (more && i < n_ch) ? __ldg(next + i) : 0u;
             clip4(a, b, cur[k]);
@@ -180,7 +185,6 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
     }
 
     // ---- back to counts (bkg.py:113-114) and output -----------------------------------------
-#pragma unroll
     // the counts of channel k + 1 are fetched while channel k goes through expf and the stores
     const bool need_y = out_mode != MT_SNIP_BACKGROUND;
     float y_next[kSnipPix];
@@ -221,10 +225,10 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
     }
 }
 
-template <typename T, int KCH>
-int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi,
+template <typename T, int KCH, bool SCALED>
+int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi, int ld_tab,
                 int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
-    auto kern = snip_kernel<T, KCH>;
+    auto kern = snip_kernel<T, KCH, SCALED>;
     const size_t smem = sizeof(float4) * (size_t)n_ch;
     static int smem_set[16] = {0};
     int dev = 0;
@@ -235,33 +239,57 @@ int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_
     }
     const long long n_cta = (n_px + kSnipPix - 1) / kSnipPix;
     kern<<<(unsigned)n_cta, kSnipThreads, smem, stream>>>(static_cast<const T *>(spec), n_px, ld_spec, ch0, n_ch, lohi,
-                                                          n_pass, boxcar, out, ld_out, out_mode);
+                                                          ld_tab, n_pass, boxcar, out, ld_out, out_mode);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
 
+// rows of a scaled table: n_ch rounded up to the thread grid of the kernel variant that handles it
+int scaled_pitch(int n_ch) {
+    for (int k = 2; k <= 8; k *= 2)
+        if (n_ch <= kSnipThreads * k) return kSnipThreads * k;
+    return 0;  // wider windows keep plain indices (their byte offsets do not fit 16 bits)
+}
+
 template <typename T>
-int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi,
-                  int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
-#define MT_SNIP_CASE(K)                                                                                    \
-    if (n_ch <= kSnipThreads * K)                                                                          \
-        return launch_snip<T, K>(spec, n_px, ld_spec, ch0, n_ch, lohi, n_pass, boxcar, out, ld_out, out_mode, stream);
+int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi, int ld_tab,
+                  bool scaled, int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
+#define MT_SNIP_CASE(K)                                                                                             \
+    if (n_ch <= kSnipThreads * K) {                                                                                 \
+        if (scaled)                                                                                                 \
+            return launch_snip<T, K, true>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, \
+                                           out_mode, stream);                                                       \
+        return launch_snip<T, K, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out,   \
+                                        out_mode, stream);                                                          \
+    }
     MT_SNIP_CASE(2)
     MT_SNIP_CASE(4)
     MT_SNIP_CASE(8)
-    MT_SNIP_CASE(16)
 #undef MT_SNIP_CASE
+    if (n_ch <= kSnipThreads * 16 && !scaled)
+        return launch_snip<T, 16, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, out_mode,
+                                         stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: n_ch=%d exceeds the on-chip limit of %d channels", n_ch,
-                    kSnipThreads * 16);
+                    kSnipThreads * (scaled ? 8 : 16));
 }
 
-}  // namespace
+__global__ void snip_scale_tables_kernel(const uint32_t *__restrict__ lohi, int n_pass, int n_ch, uint32_t *__restrict__ out,
+                                         int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, pass = blockIdx.y;
+    if (i >= ld) return;
+    uint32_t w = 0u;
+    if (pass < n_pass && i < n_ch) {
+        const uint32_t v = lohi[(long long)pass * n_ch + i];
+        w = ((v & 0xffffu) << 4) | ((v >> 16) << 20);
+    }
+    out[(long long)pass * ld + i] = w;
+}
 
-extern "C" int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
-                       int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar,
-                       float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {
+int snip_common(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0, int32_t n_ch,
+                const uint32_t *tab_dev, int ld_tab, bool scaled, int32_t n_pass, int32_t boxcar, float *out_dev,
+                int64_t ld_out, int32_t out_mode, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
-    MT_REQUIRE(spec_dev && lohi_dev && out_dev, "mt_snip: null pointer");
+    MT_REQUIRE(spec_dev && tab_dev && out_dev, "mt_snip: null pointer");
     MT_REQUIRE(n_px >= 0 && n_ch > 0 && ch0 >= 0 && ld_spec >= (int64_t)ch0 + n_ch,
                "mt_snip: bad sizes n_px=%lld n_ch=%d ch0=%d ld=%lld", (long long)n_px, n_ch, ch0,
                (long long)ld_spec);
@@ -275,10 +303,45 @@ extern "C" int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (dtype == MT_DTYPE_F32)
-        return dispatch_snip<float>(spec_dev, n_px, ld_spec, ch0, n_ch, lohi_dev, n_pass, boxcar, out_dev,
+        return dispatch_snip<float>(spec_dev, n_px, ld_spec, ch0, n_ch, tab_dev, ld_tab, scaled, n_pass, boxcar, out_dev,
                                     ld_out, out_mode, stream);
     if (dtype == MT_DTYPE_F16)
-        return dispatch_snip<__half>(spec_dev, n_px, ld_spec, ch0, n_ch, lohi_dev, n_pass, boxcar, out_dev,
+        return dispatch_snip<__half>(spec_dev, n_px, ld_spec, ch0, n_ch, tab_dev, ld_tab, scaled, n_pass, boxcar, out_dev,
                                      ld_out, out_mode, stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: dtype %d", dtype);
+}
+
+}  // namespace
+
+extern "C" int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
+                       int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar,
+                       float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {
+    return snip_common(spec_dev, dtype, n_px, ld_spec, ch0, n_ch, lohi_dev, n_ch, false, n_pass, boxcar, out_dev, ld_out,
+                       out_mode, stream_);
+}
+
+extern "C" int mt_snip_scaled_pitch(int32_t n_ch) { return scaled_pitch(n_ch); }
+
+extern "C" int mt_snip_scale_tables(const uint32_t *lohi_dev, int32_t n_pass, int32_t n_ch, uint32_t *scaled_dev,
+                                    int32_t ld_scaled, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(lohi_dev && scaled_dev, "mt_snip_scale_tables: null pointer");
+    MT_REQUIRE(n_pass >= 0 && n_ch > 0, "mt_snip_scale_tables: bad sizes");
+    MT_REQUIRE(scaled_pitch(n_ch) > 0 && ld_scaled == scaled_pitch(n_ch),
+               "mt_snip_scale_tables: n_ch=%d needs a row pitch of %d words (0 = not available), got %d", n_ch,
+               scaled_pitch(n_ch), ld_scaled);
+    dim3 grid((ld_scaled + 255) / 256, n_pass + 1);  // one zero row after the last pass
+    snip_scale_tables_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(lohi_dev, n_pass, n_ch, scaled_dev,
+                                                                                   ld_scaled);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
+
+extern "C" int mt_snip_scaled(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
+                              int32_t n_ch, const uint32_t *scaled_dev, int32_t ld_scaled, int32_t n_pass, int32_t boxcar,
+                              float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {
+    MT_REQUIRE(scaled_pitch(n_ch) > 0 && ld_scaled == scaled_pitch(n_ch), "mt_snip_scaled: table pitch %d for n_ch=%d",
+               ld_scaled, n_ch);
+    return snip_common(spec_dev, dtype, n_px, ld_spec, ch0, n_ch, scaled_dev, ld_scaled, true, n_pass, boxcar, out_dev,
+                       ld_out, out_mode, stream_);
 }
