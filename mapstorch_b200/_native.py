@@ -71,6 +71,7 @@ SIGNATURES = {
     "mt_fit_contract_simt": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp],
     "mt_nnls_fixup": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mt_penalty_shift": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "mt_split_hilo": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                   _vp],
 }
@@ -113,7 +114,7 @@ def check(status):
 # kernels launched per successful call of each entry point (bench.py reports the total)
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 1, "mt_refine": 1,
-                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1}
+                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1}
 launch_count = 0
 
 

@@ -86,3 +86,41 @@ extern "C" int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
+
+// ---- exact operand split for fp32 volumes whose counts exceed 11 significant bits ------------------------------
+// out[p][0 .. n_ch)      = y with the low 13 mantissa bits cleared (exactly representable as a tf32 operand)
+// out[p][n_ch .. 2 n_ch) = y - hi (exact in fp32; its own top 11 bits carry the result to 22 bits)
+// One read of the window, two writes: the layout K3 contracts with `repeat = 2`, as the SNIP kernel emits it.
+namespace {
+
+__global__ void __launch_bounds__(256)
+split_hilo_kernel(const float *__restrict__ spec, long long n_px, long long ld_spec, int col0, int n_ch,
+                  float *__restrict__ out, long long ld_out) {
+    const long long total = n_px * (long long)n_ch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / n_ch;
+        const int c = (int)(i - p * n_ch);
+        const float y = __ldg(spec + p * ld_spec + col0 + c);
+        const float hi = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+        out[p * ld_out + c] = hi;
+        out[p * ld_out + n_ch + c] = __fsub_rn(y, hi);
+    }
+}
+
+}  // namespace
+
+extern "C" int mt_split_hilo(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch,
+                             float *out_dev, int64_t ld_out, void *stream) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(spec_dev && out_dev, "mt_split_hilo: null pointer");
+    MT_REQUIRE(n_px >= 0 && n_ch > 0 && col0 >= 0 && ld_spec >= (int64_t)col0 + n_ch && ld_out >= 2 * (int64_t)n_ch,
+               "mt_split_hilo: bad sizes");
+    if (n_px == 0) return MT_OK;
+    const long long total = n_px * (long long)n_ch;
+    const long long want = (total + 255) / 256, cap = (long long)mt::num_sms() * 32;
+    split_hilo_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        spec_dev, n_px, ld_spec, col0, n_ch, out_dev, ld_out);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}

@@ -298,10 +298,8 @@ class MapFitPlan:
             scratch = torch.empty((chunk, pitch), dtype=torch.float32, device="cuda")[:, :width]
             for p0 in range(0, n_px, chunk):
                 n = min(chunk, n_px - p0)
-                y = spec2d[p0: p0 + n, self.er[0]: self.er[1] + 1]
-                hi = (y.view(torch.int32) & -8192).view(torch.float32)
-                scratch[:n, : self.n_ch] = hi
-                scratch[:n, self.n_ch:] = y - hi
+                _native.call("mt_split_hilo", spec2d[p0: p0 + n].data_ptr(), n, spec2d.stride(0), self.er[0], self.n_ch,
+                             scratch.data_ptr(), scratch.stride(0), _native.stream_ptr(stream))
                 self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2, 0, width, engine, stream, neg, p0,
                                _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
                 if coef is not None:
