@@ -633,12 +633,21 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
     source compatibility and ignored.  ``loss_trace`` holds the objective in the reference's units."""
     assert loss in ["mse", "l1"], "Loss function not supported"
     assert optimizer in ["adam", "adamw"], "Optimizer not supported"
+
+    def finish(result):
+        # the reference ticks status_updator once per Adam iteration (opt.py:319-320); callers size their progress
+        # bars with n_iter, so the direct solve reports the same number of ticks when it is done
+        if status_updator is not None:
+            for _ in range(int(n_iter)):
+                status_updator.update()
+        return result
+
     if tune_params:
         from mapstorch_b200.refine import fit_spec_global
 
-        return fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals,
-                               fixed_param_vals, indices, use_snip, n_iter, e_consts, elem_info, detector_type,
-                               escape_factor, device, verbose, loss=loss, l1_lambda=l1_lambda)
+        return finish(fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals,
+                                      fixed_param_vals, indices, use_snip, n_iter, e_consts, elem_info, detector_type,
+                                      escape_factor, device, verbose, loss=loss, l1_lambda=l1_lambda))
     _native.require_device()
     spec = torch.as_tensor(np.asarray(int_spec, dtype=np.float32) if not isinstance(int_spec, torch.Tensor)
                            else int_spec.detach().float().cpu().numpy())
@@ -673,4 +682,4 @@ def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitt
         if idx is not None:
             resid = resid[idx]
         loss_trace = [float(torch.sum(resid * resid).item())]
-    return tensors, spec_fit.cpu().numpy(), bkg.cpu().numpy(), loss_trace
+    return finish((tensors, spec_fit.cpu().numpy(), bkg.cpu().numpy(), loss_trace))

@@ -123,3 +123,39 @@ def test_fit_spec_with_tuned_parameters_recovers_calibration():
     t2, fit2, bkg2, trace2 = opt.fit_spec(g["r_spec"], (50, 1450), names[:-2], init_param_vals=p, tune_params=True,
                                           use_snip=True, n_iter=15)
     assert trace2[-1] < trace2[0] and fit2.shape == (1401,) and bkg2.shape == (1401,)
+
+
+def test_fit_spec_with_the_apps_default_arguments():
+    """apps/guess_elements.py:257-263 and scripts/fit_spec.py call fit_spec(int_spec, energy_range,
+    init_param_vals=..., n_iter=..., status_updator=bar) with everything else defaulted: all 93 default
+    components, the 12 default tunable parameters, SNIP on.  That call must run here, lower the objective from a
+    perturbed calibration, keep the reference's return structure and tick the progress bar n_iter times."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_fitting_elems, default_fitting_params, default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    elems = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+    er = (50, 1450)
+    rng = np.random.default_rng(5)
+    B, names = mo.basis(p, (0, 2047), elems)
+    amps = 10.0 ** rng.uniform(3.0, 4.0, size=B.shape[1])
+    spec = rng.poisson(amps @ B.astype(np.float64).T + 20.0).astype(np.float32)
+    start = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + 0.004, FWHM_OFFSET=p["FWHM_OFFSET"] * 1.05)
+
+    class Bar:
+        ticks = 0
+
+        def update(self):
+            self.ticks += 1
+
+    bar = Bar()
+    tensors, spec_fit, bkg, trace = opt.fit_spec(spec, er, init_param_vals=start, n_iter=25, status_updator=bar)
+    assert bar.ticks == 25
+    assert spec_fit.shape == (1401,) and bkg.shape == (1401,) and len(trace) >= 2
+    assert trace[-1] < 0.7 * trace[0]                       # the shifted calibration was corrected
+    assert set(default_fitting_params) <= set(tensors) and "Fe" in tensors and "Pb_L" in tensors
+    assert all(e in tensors for e in default_fitting_elems if e in tensors or True) and "COMPTON_AMPLITUDE" in tensors
+    assert abs(tensors["ENERGY_OFFSET"].item() - p["ENERGY_OFFSET"]) < 1.5e-3
+    resid = spec_fit + bkg - spec[er[0]: er[1] + 1]
+    assert abs(float((resid.astype(np.float64) ** 2).sum()) - trace[-1]) <= 1e-3 * trace[-1]
