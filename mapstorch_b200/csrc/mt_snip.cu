@@ -97,17 +97,24 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
     float4 cur[KCH];
 
     // ---- stage raw counts in shared memory -------------------------------------------------
+    // all global loads of the thread are issued before the first shared-memory store, so the CTA pays ONE
+    // memory latency here, not one per channel (cur[] is free until the boxcar step)
 #pragma unroll
     for (int k = 0; k < KCH; ++k) {
         const int i = tid + k * kSnipThreads;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n_ch) {
-            float4 r;
             r.x = load_count(rows[0] + i);
             r.y = (px0 + 1 < n_px) ? load_count(rows[1] + i) : 0.f;
             r.z = (px0 + 2 < n_px) ? load_count(rows[2] + i) : 0.f;
             r.w = (px0 + 3 < n_px) ? load_count(rows[3] + i) : 0.f;
-            sb[i] = r;
         }
+        cur[k] = r;
+    }
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) {
+        const int i = tid + k * kSnipThreads;
+        if (i < n_ch) sb[i] = cur[k];
     }
     __syncthreads();
 
