@@ -38,10 +38,6 @@ __device__ __forceinline__ float finite_or_zero(float v) {
 __device__ __forceinline__ float log_1p(float x) { return logf(__fadd_rn(1.f, x)); }
 __device__ __forceinline__ float exp_m1(float v) { return __fsub_rn(expf(v), 1.f); }
 
-__device__ __forceinline__ float clip(float a, float b, float c) {
-    return fminf(__fmul_rn(__fadd_rn(a, b), 0.5f), c);
-}
-
 using mt::add2;
 using mt::mul2;
 using mt::pack2;
