@@ -169,7 +169,7 @@ def cpu_baseline_refine(w, params, er, elems, budget_s=12.0):
         t0 = time.perf_counter()
         pool.map(_refine_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "px/s", "cores": cores, "kind": "port",
+    return {"value": n / dt, "unit": "px/s", "cores": cores, "kind": "port", "seconds": dt,
             "sample": f"{n} synthetic pixels of the same workload: oracle.refine_spectrum per pixel (free = "
                       f"{', '.join(w['refine'])}; amplitudes by non-negative least squares inside scipy least_squares), "
                       f"one process per core, {dt:.1f} s"}
@@ -207,7 +207,7 @@ def cpu_baseline(w, params, er, elems, budget_s=12.0, threads=None):
     for i in range(4):
         mo.fit_spec_adam(y[i] if not w["snip"] else y[i], B, None, np.full(B.shape[1], 2.0, np.float32), n_iter=500)
     adam = 4 / (time.perf_counter() - t1)
-    return {"value": n_big / dt, "unit": "px/s", "cores": cores, "kind": "port",
+    return {"value": n_big / dt, "unit": "px/s", "cores": cores, "kind": "port", "seconds": dt,
             "sample": f"{n_big} synthetic pixels of the same workload: oracle composition of the reference functions "
                       f"({'snip_bkg + ' if w['snip'] else ''}fp32 BLAS contraction with pinv(B) + scipy NNLS on negative "
                       f"pixels), {dt:.1f} s",
@@ -232,7 +232,9 @@ def run_reference(args, rank, world, emit):
     value = float(np.mean([c["value"] for c in vals]))
     cb = dict(vals[-1], value=value)
     line = {"impl": "reference", "metric": "pixels/sec", "value": value, "unit": "px/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean([c["seconds"] for c in vals])) * 1e3,  # one step = one bounded CPU sample
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload},
             "cpu_baseline": cb,
