@@ -277,18 +277,15 @@ refine_kernel(const RefParams p) {
         __syncthreads();
 
         // ---- accept / reject the previous step -----------------------------------------------
-        if (tid == 0) {
-            float loss = 0.f;
-            for (int w = 0; w < kRefWarps; ++w) loss += part[w][0];
-            ctl[0] = loss;
-            // a step is rejected only when the loss rises by more than its evaluation noise (2-ulp exponentials,
-            // fp32 sums: ~1e-6 relative); smaller rises are what the last Newton steps look like in fp32 and
-            // rejecting them costs ten futile step halvings per pixel
-            const bool worse = loss > ctl[1] * (1.f + 2e-5f) && iter > 0;
-            ctl[3] = worse ? 1.f : 0.f;
-        }
-        __syncthreads();
-        const bool rejected = ctl[3] != 0.f;
+        // every thread forms the same decision from the same shared values: no hand-off, no barrier
+        float loss = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRefWarps; ++w) loss += part[w][0];
+        // a step is rejected only when the loss rises by more than its evaluation noise (2-ulp exponentials,
+        // fp32 sums: ~1e-6 relative); smaller rises are what the last Newton steps look like in fp32 and
+        // rejecting them costs ten futile step halvings per pixel
+        const bool rejected = loss > ctl[1] * (1.f + 2e-5f) && iter > 0;
+        if (tid == 0) ctl[0] = loss;
         if (rejected) {
             // go back and retry with half the step (costs one evaluation)
             const float alpha = ctl[2] * 0.5f;
