@@ -235,13 +235,13 @@ typedef struct MtRefineConfig {
  * component-major pass, so the host orders them to balance the summed window lengths; g0inv_dev = inverse
  * Gram matrix of the unit-amplitude basis at the global parameters, fp32 [n_comp][n_comp].
  * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
- * theta_dev [n_theta][ld_x], loss_dev [n_px], iters_dev [n_px] are optional outputs. */
+ * theta_dev [n_theta][ld_theta], loss_dev [n_px], iters_dev [n_px] are optional outputs. */
 int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
               int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
               const uint32_t *chan_lines_host, const int32_t *comp_start_host, const int32_t *comp_lines_host,
               const uint32_t *line_window_host, const int32_t *comp_order_host, const float *g0inv_dev,
               float *x_dev, int64_t ld_x,
-              float *theta_dev, float *loss_dev, int32_t *iters_dev, void *stream);
+              float *theta_dev, int64_t ld_theta, float *loss_dev, int32_t *iters_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -72,8 +72,8 @@ SIGNATURES = {
     "mt_nnls_fixup": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mt_penalty_shift": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "mt_split_hilo": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
-    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
-                  _vp],
+    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
+                  _vp, _vp],
 }
 
 

@@ -62,6 +62,7 @@ struct RefParams {
     float *x;
     long long ld_x;
     float *theta_out;
+    long long ld_theta;
     float *loss_out;
     int *iters_out;
     long long n_px;
@@ -436,7 +437,7 @@ refine_kernel(const RefParams p) {
     }
 
     for (int e = tid; e < E; e += kRefThreads) p.x[(long long)e * p.ld_x + px] = xs[e];
-    if (tid < NT && p.theta_out) p.theta_out[(long long)tid * p.ld_x + px] = theta[tid];
+    if (tid < NT && p.theta_out) p.theta_out[(long long)tid * p.ld_theta + px] = theta[tid];
     if (tid == 0) {
         if (p.loss_out) p.loss_out[px] = ctl[0];
         if (p.iters_out) p.iters_out[px] = iter;
@@ -500,7 +501,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
                          const uint32_t *chan_lines_host, const int32_t *comp_start_host,
                          const int32_t *comp_lines_host, const uint32_t *line_window_host,
                          const int32_t *comp_order_host, const float *g0inv_dev,
-                         float *x_dev, int64_t ld_x, float *theta_dev, float *loss_dev, int32_t *iters_dev,
+                         float *x_dev, int64_t ld_x, float *theta_dev, int64_t ld_theta, float *loss_dev, int32_t *iters_dev,
                          void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && cfg_host && lines_host && chan_lines_host && comp_start_host && comp_lines_host &&
@@ -513,6 +514,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     MT_REQUIRE(cfg.n_lines >= 1 && cfg.n_lines <= kMaxLines, "mt_refine: n_lines=%d (max %d)", cfg.n_lines, kMaxLines);
     MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= kMaxTheta, "mt_refine: n_theta=%d", cfg.n_theta);
     MT_REQUIRE(n_px >= 0 && ld_x >= n_px && (!bkg_dev || ld_bkg >= cfg.n_ch), "mt_refine: sizes");
+    MT_REQUIRE(!theta_dev || cfg.n_theta == 0 || ld_theta >= n_px, "mt_refine: ld_theta=%lld < n_px", (long long)ld_theta);
     for (int l = 0; l < cfg.n_lines; ++l)
         MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp, "mt_refine: line %d component", l);
     {
@@ -569,6 +571,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.x = x_dev;
     p.ld_x = ld_x;
     p.theta_out = theta_dev;
+    p.ld_theta = ld_theta;
     p.loss_out = loss_dev;
     p.iters_out = iters_dev;
     p.n_px = n_px;

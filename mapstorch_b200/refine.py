@@ -152,7 +152,7 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
                  comp_start.ctypes.data_as(ctypes.c_void_p), comp_lines.ctypes.data_as(ctypes.c_void_p),
                  window.ctypes.data_as(ctypes.c_void_p), comp_order.ctypes.data_as(ctypes.c_void_p),
                  plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),
-                 theta.data_ptr(), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
+                 theta.data_ptr(), theta.stride(0), loss.data_ptr(), iters.data_ptr(), _native.stream_ptr(stream))
     return theta[: len(free)], loss, iters
 
 

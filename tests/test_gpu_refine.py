@@ -159,3 +159,30 @@ def test_fit_spec_with_the_apps_default_arguments():
     assert abs(tensors["ENERGY_OFFSET"].item() - p["ENERGY_OFFSET"]) < 1.5e-3
     resid = spec_fit + bkg - spec[er[0]: er[1] + 1]
     assert abs(float((resid.astype(np.float64) ** 2).sum()) - trace[-1]) <= 1e-3 * trace[-1]
+
+
+def test_host_volume_is_refined_slab_by_slab_with_the_same_result():
+    """fit_map on a HOST volume streams it in slabs and refines each slab while it is resident (one PCIe
+    crossing); pixels are independent and the reductions deterministic, so the maps must equal the
+    device-resident call bit for bit, whatever the slab size, with and without SNIP."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    elems = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+    er = (0, 2047)
+    rng = np.random.default_rng(77)
+    B, _ = mo.basis(p, er, elems)
+    amps = 10.0 ** rng.uniform(2.0, 3.0, size=(300, B.shape[1]))
+    y = rng.poisson(amps @ B.astype(np.float64).T + 2.0).astype(np.float32)
+    for use_snip in (False, True):
+        kw = dict(init_param_vals=p, use_snip=use_snip, refine=("ENERGY_OFFSET", "FWHM_OFFSET"), refine_iters=10)
+        on_device = opt.fit_map(torch.from_numpy(y).cuda(), er, elems, **kw)
+        from_host = opt.fit_map(torch.from_numpy(y), er, elems, chunk_px=128, **kw)
+        pinned = opt.fit_map(torch.from_numpy(y).pin_memory().reshape(20, 15, 2048), er, elems, chunk_px=77, **kw)
+        assert set(on_device) == set(from_host) == set(pinned)
+        for k in on_device:
+            assert torch.equal(on_device[k], from_host[k]), (use_snip, k)
+            assert torch.equal(on_device[k], pinned[k].reshape(-1)), (use_snip, k)
+        assert pinned["Fe"].shape == (20, 15) and pinned["iterations"].dtype == torch.int32
