@@ -333,3 +333,35 @@ def test_fit_map_with_override_file_constants(tmp_path):
     assert float((fine["FWHM_OFFSET"] / p["FWHM_OFFSET"] - 1).abs().max()) <= 0.30 + 1e-6
     sse = (((got[:16].astype(np.float64) @ B.astype(np.float64).T) - y[:16]) ** 2).sum(axis=1)
     assert np.all(fine["loss"].cpu().numpy() <= sse * (1 + 1e-5))  # refining can only lower the objective
+
+
+@pytest.mark.parametrize("case", ["snip", "snip_penalty", "wide", "refine", "host_penalty"])
+def test_chunked_paths_equal_the_single_chunk_result(monkeypatch, case):
+    """Volumes larger than one scratch slab are processed slab by slab (SNIP residual, exact operand split,
+    penalty shift, refinement, host streaming).  Pixels are independent, so forcing tiny slabs must reproduce
+    the single-slab maps bit for bit -- this is what catches a pitch or offset mixed up between a slab and
+    the whole map."""
+    from mapstorch_b200 import opt
+
+    p = params12()
+    er = (0, 2047)
+    bright = case == "wide"
+    y, names = synth(p, er, ELEMS10, 101, seed=13, lo=4.2 if bright else 1.5, hi=5.0 if bright else 3.0,
+                     flat=0.0 if bright else 3.0)
+    dev = torch.from_numpy(y).cuda()
+    kw = dict(init_param_vals=p, use_snip=case.startswith("snip"))
+    if case.endswith("penalty"):
+        kw["l1_lambda"] = 2e-5
+    if case == "refine":
+        kw.update(refine=("ENERGY_OFFSET", "FWHM_OFFSET"), refine_iters=8)
+    whole = opt.fit_map(dev, er, ELEMS10, **kw)
+    monkeypatch.setattr(opt, "SNIP_CHUNK_PX", 24)
+    if case == "host_penalty":
+        parts = opt.fit_map(torch.from_numpy(y), er, ELEMS10, chunk_px=24, **kw)
+    else:
+        parts = opt.fit_map(dev, er, ELEMS10, **kw)
+    assert set(whole) == set(parts)
+    for k in whole:
+        assert torch.equal(whole[k], parts[k]), (case, k)
+    if bright:
+        assert y.max() >= 2048  # the exact-split path was the one exercised
