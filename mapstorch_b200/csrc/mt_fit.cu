@@ -522,6 +522,17 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// L2 promotion of the TMA loads: 256 B by default; MT_FIT_L2PROMO=0|1|2|3 selects none / 64 / 128 / 256 B (tuning knob)
+CUtensorMapL2promotion l2_promotion() {
+    const char *env = getenv("MT_FIT_L2PROMO");
+    switch (env ? atoi(env) : 3) {
+        case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        case 1: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
+}
+
 // 2-D row-major tensor [rows][cols] with a row pitch, boxes of [box_rows][128 bytes], swizzle 128B
 int make_tile_map(CUtensorMap *map, const void *base, int dtype, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
                   uint32_t box_rows) {
@@ -534,7 +545,7 @@ int make_tile_map(CUtensorMap *map, const void *base, int dtype, uint64_t cols, 
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, dtype == MT_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                      2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return mt::fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return MT_OK;
