@@ -184,7 +184,7 @@ int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_t n_px, int
                      int64_t ld_x, int32_t x_layout, int32_t n_comp, void *stream);
 
 /* Exact operand split for fp32 volumes whose values need more than the 11 significant bits of a tf32 operand
- * (integer counts >= 2048): out[p][0..n_ch) = spec[p][col0 + c] with the low 13 mantissa bits cleared,
+ * (integer counts >= 2048): out[p][0..n_ch) = spec[p][col0 + c] rounded to nearest to 11 significant bits,
  * out[p][n_ch..2 n_ch) = the remainder (exact).  mt_fit_contract then runs over the 2 n_ch columns with the
  * operand pack repeated twice -- the layout MT_SNIP_RESIDUAL_HILO produces for the SNIP path. */
 int mt_split_hilo(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch, float *out_dev,

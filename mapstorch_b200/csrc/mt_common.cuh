@@ -45,6 +45,18 @@ struct StreamScratch {
     }
 };
 
+#ifdef __CUDACC__
+// High part of an exact two-operand split: the value rounded TO NEAREST to the 11 significant bits of a tf32
+// operand (low 13 mantissa bits zero).  The remainder v - hi is exact in fp32 and at most 2^-12 |v|, so what the
+// tensor core drops when it truncates the remainder is below 2^-23 |v| (masking the low bits instead would leave
+// a remainder twice as large, and a one-sided error).
+__device__ __forceinline__ float tf32_round(float v) {
+    uint32_t b;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+    return __uint_as_float(b);
+}
+#endif
+
 inline int num_sms() {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);

@@ -88,7 +88,7 @@ extern "C" int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_
 }
 
 // ---- exact operand split for fp32 volumes whose counts exceed 11 significant bits ------------------------------
-// out[p][0 .. n_ch)      = y with the low 13 mantissa bits cleared (exactly representable as a tf32 operand)
+// out[p][0 .. n_ch)      = y rounded to nearest to 11 significant bits (exactly representable as a tf32 operand)
 // out[p][n_ch .. 2 n_ch) = y - hi (exact in fp32; its own top 11 bits carry the result to 22 bits)
 // One read of the window, two writes: the layout K3 contracts with `repeat = 2`, as the SNIP kernel emits it.
 namespace {
@@ -102,7 +102,7 @@ split_hilo_kernel(const float *__restrict__ spec, long long n_px, long long ld_s
         const long long p = i / n_ch;
         const int c = (int)(i - p * n_ch);
         const float y = __ldg(spec + p * ld_spec + col0 + c);
-        const float hi = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+        const float hi = mt::tf32_round(y);
         out[p * ld_out + c] = hi;
         out[p * ld_out + n_ch + c] = __fsub_rn(y, hi);
     }

@@ -219,7 +219,7 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
                 if (out_mode == MT_SNIP_RESIDUAL) {
                     orow[i] = r;
                 } else {
-                    const float hi = __uint_as_float(__float_as_uint(r) & 0xffffe000u);
+                    const float hi = mt::tf32_round(r);
                     orow[i] = hi;
                     orow[n_ch + i] = __fsub_rn(r, hi);
                 }
