@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the per-pixel XRF map fit (BASELINE.json metric: pixels/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4] [--impl ours|reference]
 
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A step is one fit of
-the rank's resident row shard (plus, for N > 1, the all-gather of the element maps).  Rank 0
-prints ONE JSON line.  `--impl reference` times the CPU baseline (the oracle's composition of the
-reference functions) on the host cores instead.
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A step is one fit of the rank's
+resident row shard plus, for N > 1, the exchange of the element maps (fused into the fit kernels as NVLink peer
+stores, dist.ShardedMapFit).  Rank 0 prints ONE JSON line: the headline workload (default c5) at the top level
+and, in "workloads", short runs of the other BASELINE configurations (c2, c3, c4 and config 1's fit_spec), each
+with the roofline of ITS dominant kernel.  `--impl reference` times the reference's own CPU code
+(baseline/_ref, installed by tools/install_reference.py) on the host cores instead.
 """
 import argparse
 import json
@@ -15,6 +17,7 @@ import subprocess
 import sys
 import tempfile
 import time
+import warnings
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -42,6 +45,10 @@ WORKLOADS = {
                desc="BASELINE config 4: 512x512x2048 fp32, 20 elements + 2 scatter peaks, per-pixel Gauss-Newton "
                     "refinement of ENERGY_OFFSET and FWHM_OFFSET + amplitudes (<= 12 iterations)"),
 }
+SNIP_KEYS = ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")
+C1_DESC = ("BASELINE config 1: opt.fit_spec on one synthetic 2048-channel integrated spectrum, 10 K-line elements + 2 "
+           "scatter peaks, 12 keV, the CLI's arguments (energy_range=[50,1450], tune_params=True, init_amp=True, "
+           "use_snip=True, loss='mse', optimizer='adamw', n_iter=500)")
 
 
 def dist_env():
@@ -131,6 +138,63 @@ def build_workload(name, rank, world, device):
     return w, elems, params, er, plan, truth, vol
 
 
+# ---- CPU baselines ------------------------------------------------------------------------------------------------
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def reference_modules():
+    """The unmodified reference, imported from baseline/_ref (tools/install_reference.py); None if absent."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "mapstorch" / "opt.py").exists():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    warnings.filterwarnings("ignore")
+    try:
+        import mapstorch.bkg as rbkg
+        import mapstorch.map as rmap
+        import mapstorch.opt as ropt
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] reference in baseline/_ref does not import: {exc}", file=sys.stderr)
+        return None
+    return ropt, rmap, rbkg
+
+
+def reference_basis(rmap, params, er, elems):
+    """B [E, C] from the reference's own model functions at unit amplitude (what model_spec sums, map.py:282-304)."""
+    t = {k: torch.tensor(float(v)) for k, v in params.items()}
+    for e in list(elems) + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]:
+        t[e] = torch.tensor(0.0)
+    ch = torch.arange(er[0], er[1] + 1, dtype=torch.float32)
+    ev = t["ENERGY_OFFSET"] + t["ENERGY_SLOPE"] * ch + t["ENERGY_QUADRATIC"] * (ch ** 2)
+    cols = [rmap.model_elem_spec(t, e, ev, True, False) for e in elems]
+    cols.append(rmap.elastic_peak(t, ev, t["ENERGY_SLOPE"]))  # component order of MapFitPlan.names / oracle.basis
+    cols.append(rmap.compton_peak(t, ev, t["ENERGY_SLOPE"], True, False))
+    return torch.stack(cols)
+
+
+def reference_composed(mods, y, params, er, elems, snip):
+    """The reference's functions composed into a map fit, best case: its batched snip_bkg (bkg.py:69-114), its basis,
+    one fp32 contraction with pinv(B) in torch and NNLS (scipy) for the pixels whose solution has a negative
+    component -- what its 10**a parametrisation converges to.  The reference itself ships no per-pixel fitter."""
+    from scipy.optimize import nnls
+
+    ropt, rmap, rbkg = mods
+    yt = torch.from_numpy(y)
+    if snip:
+        yt = yt - rbkg.snip_bkg(yt, er, *(torch.tensor(float(params[k])) for k in SNIP_KEYS))
+    B = reference_basis(rmap, params, er, elems)
+    B64 = B.double()
+    pinv = torch.linalg.solve(B64 @ B64.T, B64).float()
+    x = (yt @ pinv.T).numpy()
+    bad = np.nonzero((x < 0).any(axis=1))[0]
+    b_np, y_np = B64.numpy().T, yt.double().numpy()
+    for i in bad:
+        x[i] = nnls(b_np, y_np[i], maxiter=50 * b_np.shape[1])[0]
+    return x
+
+
 def _refine_worker(job):
     """one pixel of the CPU refinement baseline (runs in a forked worker; numpy / scipy only)"""
     from oracle import maps_oracle as mo
@@ -149,7 +213,7 @@ def cpu_baseline_refine(w, params, er, elems, budget_s=12.0):
 
     from oracle import maps_oracle as mo
 
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     rng = np.random.default_rng(0)
     B, _ = mo.basis(params, er, elems)
 
@@ -176,42 +240,124 @@ def cpu_baseline_refine(w, params, er, elems, budget_s=12.0):
 
 
 def cpu_baseline(w, params, er, elems, budget_s=12.0, threads=None):
-    """Oracle composition of the reference functions on the host cores, on a bounded sample."""
+    """The map fit on the host cores, on a bounded sample: the REFERENCE's own functions composed (kind
+    "reference") when baseline/_ref is installed, otherwise the oracle's restatement of the same composition
+    (kind "port")."""
     from oracle import maps_oracle as mo
 
     if w.get("refine"):
         return cpu_baseline_refine(w, params, er, elems, budget_s)
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_cores()
     torch.set_num_threads(cores)
     rng = np.random.default_rng(0)
     B, names = mo.basis(params, er, elems)
-    snip_args = [params[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET",
-                                     "FWHM_FANOPRIME")] if w["snip"] else None
+    snip_args = [params[k] for k in SNIP_KEYS] if w["snip"] else None
+    mods = reference_modules()
 
     def sample(n):
         amps = 10.0 ** rng.uniform(1.5, 3.0, size=(n, B.shape[1]))
         return rng.poisson(amps @ B.astype(np.float64).T + w["flat"]).astype(np.float32)
 
+    def run(y):
+        if mods is not None:
+            return reference_composed(mods, y, params, er, elems, w["snip"])
+        return mo.fit_map_composed(y, B, snip_args, er)
+
     n = 512
     y = sample(n)
     t0 = time.perf_counter()
-    mo.fit_map_composed(y, B, snip_args, er)
+    run(y)
     dt = time.perf_counter() - t0
     n_big = int(min(max(n, n * budget_s / max(dt, 1e-6)), 1 << 18))
     y = sample(n_big)
     t0 = time.perf_counter()
-    mo.fit_map_composed(y, B, snip_args, er)
+    x = run(y)
     dt = time.perf_counter() - t0
-    # the reference's own per-spectrum fit: Adam, 500 iterations (restated with analytic gradients)
-    t1 = time.perf_counter()
-    for i in range(4):
-        mo.fit_spec_adam(y[i] if not w["snip"] else y[i], B, None, np.full(B.shape[1], 2.0, np.float32), n_iter=500)
-    adam = 4 / (time.perf_counter() - t1)
-    return {"value": n_big / dt, "unit": "px/s", "cores": cores, "kind": "port", "seconds": dt,
-            "sample": f"{n_big} synthetic pixels of the same workload: oracle composition of the reference functions "
-                      f"({'snip_bkg + ' if w['snip'] else ''}fp32 BLAS contraction with pinv(B) + scipy NNLS on negative "
-                      f"pixels), {dt:.1f} s",
-            "reference_adam_500it_px_s": adam}
+    out = {"value": n_big / dt, "unit": "px/s", "cores": cores, "kind": "reference" if mods is not None else "port",
+           "seconds": dt}
+    if mods is not None:
+        # the composition is only a baseline if it computes the same maps: compare a few pixels with the oracle
+        ref = mo.fit_nnls(y[:32], B, mo.snip_bkg(y[:32], er, *snip_args) if w["snip"] else None)
+        scale = ref.max(axis=1, keepdims=True)
+        out["max_abs_diff_vs_oracle_over_pixel_max"] = float((np.abs(x[:32] - ref) / scale).max())
+        out["sample"] = (f"{n_big} synthetic pixels of the same workload through the reference's own functions from "
+                         f"baseline/_ref ({'mapstorch.bkg.snip_bkg batched + ' if w['snip'] else ''}mapstorch.map basis + "
+                         f"one fp32 torch contraction with pinv(B) + scipy NNLS on negative pixels), {dt:.1f} s")
+    else:
+        out["sample"] = (f"{n_big} synthetic pixels of the same workload: oracle composition of the reference functions "
+                         f"({'snip_bkg + ' if w['snip'] else ''}fp32 BLAS contraction with pinv(B) + scipy NNLS on negative "
+                         f"pixels), {dt:.1f} s")
+    return out
+
+
+def _reference_fit_worker(job):
+    """The reference's actual per-spectrum fit, one pixel: fit_spec(tune_params=False) with Adam (opt.py:165-327)."""
+    spec, er, elems, params, n_iter, use_snip = job
+    torch.set_num_threads(1)
+    ropt, _, _ = reference_modules()
+    t0 = time.perf_counter()
+    ropt.fit_spec(spec, er, elements_to_fit=list(elems), init_param_vals=params, tune_params=False, init_amp=True,
+                  use_snip=use_snip, loss="mse", optimizer="adam", n_iter=n_iter, progress_bar=False)
+    return time.perf_counter() - t0
+
+
+def reference_fit_spec_rate(w, params, er, elems, budget_s=25.0):
+    """px/s of the reference's own fit_spec(tune_params=False, n_iter=500) per pixel, one process per core.  The
+    per-iteration cost is constant, so the iterations actually timed are sized to the budget and the 500-iteration
+    rate follows from the measured seconds per iteration (both reported)."""
+    import multiprocessing as mp
+
+    from oracle import maps_oracle as mo
+
+    cores = min(host_cores(), 64)
+    rng = np.random.default_rng(7)
+    B, _ = mo.basis(params, er, elems)
+    amps = 10.0 ** rng.uniform(1.5, 3.0, size=(cores, B.shape[1]))
+    y = rng.poisson(amps @ B.astype(np.float64).T + w["flat"]).astype(np.float32)
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_reference_fit_worker, [(y[i], er, elems, params, 2, w["snip"]) for i in range(cores)], chunksize=1)  # imports
+        warm = pool.map(_reference_fit_worker, [(y[i], er, elems, params, 8, w["snip"]) for i in range(cores)], chunksize=1)
+        per_it = float(np.mean(warm)) / 8
+        n_iter = int(min(500, max(16, budget_s / max(per_it, 1e-4))))
+        t0 = time.perf_counter()
+        secs = pool.map(_reference_fit_worker, [(y[i], er, elems, params, n_iter, w["snip"]) for i in range(cores)], chunksize=1)
+        wall = time.perf_counter() - t0
+    s_per_it = float(np.mean(secs)) / n_iter
+    return {"px_s_at_500_iterations": cores / (500 * s_per_it), "pixels": cores,
+            "processes": cores, "iterations_timed": n_iter, "seconds_per_iteration": s_per_it, "wall_seconds": wall,
+            "call": "mapstorch.opt.fit_spec(pixel, energy_range, elements, init_param_vals, tune_params=False, "
+                    "init_amp=True, use_snip=%s, optimizer='adam', n_iter=...)" % w["snip"]}
+
+
+def config1_spectrum():
+    """Synthetic integrated spectrum of BASELINE config 1 (2048 channels, 10 K-line elements, 12 keV)."""
+    from oracle import maps_oracle as mo
+
+    from mapstorch_b200 import synth
+
+    params = synth.benchmark_params(2048)
+    rng = np.random.default_rng(11)
+    B, names = mo.basis(params, (0, 2047), synth.ELEMS10)
+    amps = 10.0 ** rng.uniform(3.0, 4.5, size=B.shape[1])
+    amps[-1] *= 30.0  # a dominant elastic peak, as in measured spectra (SURVEY.md 8d on the scatter-peak heuristic)
+    spec = rng.poisson(B.astype(np.float64) @ amps + 40.0).astype(np.float32)
+    return spec, params, list(synth.ELEMS10)
+
+
+def reference_config1():
+    """Wall time of the reference's fit_spec with the CLI's arguments on config 1's spectrum (scripts/fit_spec.py)."""
+    mods = reference_modules()
+    if mods is None:
+        return None
+    spec, params, elems = config1_spectrum()
+    torch.set_num_threads(host_cores())
+    t0 = time.perf_counter()
+    tensors, spec_fit, bkg, trace = mods[0].fit_spec(spec, [50, 1450], elements_to_fit=elems, init_param_vals=params,
+                                                     tune_params=True, init_amp=True, use_snip=True, loss="mse",
+                                                     optimizer="adamw", n_iter=500, progress_bar=False, device="cpu")
+    return {"seconds": time.perf_counter() - t0, "final_loss": float(trace[-1]), "threads": torch.get_num_threads(),
+            "workload": C1_DESC}
 
 
 def run_reference(args, rank, world, emit):
@@ -223,6 +369,12 @@ def run_reference(args, rank, world, emit):
     elems = getattr(synth, w["elems"])
     params = synth.benchmark_params(w["n_ch"])
     er = (0, w["n_ch"] - 1)
+    extra = {}
+    if reference_modules() is not None and not args.no_extra:
+        # forked workers first (before this process spins up its own thread pools)
+        if not w.get("refine"):
+            extra["reference_fit_spec"] = reference_fit_spec_rate(w, params, er, elems)
+        extra["reference_config1"] = reference_config1()
     vals = []
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
@@ -239,6 +391,7 @@ def run_reference(args, rank, world, emit):
             "config": {"workload": w["desc"], "name": args.workload},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra)
     emit(line)
 
 
@@ -265,121 +418,15 @@ def bind_near_gpu(index):
         return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--nccl-gather", action="store_true", help="gather the maps with NCCL instead of peer-memory stores")
-    ap.add_argument("--gather", default="owner", choices=["owner", "gather", "allgather"],
-                    help="peer-memory exchange of the element maps: every component assembled on its owner GPU "
-                         "(balanced all-to-all, default), everything on rank 0, or everything everywhere")
-    args = ap.parse_args()
-    rank, local_rank, world = dist_env()
-    # libraries (NCCL's version banner) write to fd 1; keep stdout for the ONE JSON line
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-
-    def emit(line):
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
-
-    if args.impl == "reference":
-        run_reference(args, rank, world, emit)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-
-    import torch.distributed as dist
-    from mapstorch_b200 import _native, opt
-    from mapstorch_b200.dist import gather_maps
-
-    early_cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and WORKLOADS[args.workload].get("refine"):
-        # this baseline forks one worker per core: run it before the CUDA context exists
-        from mapstorch_b200 import synth as _synth
-
-        _w = WORKLOADS[args.workload]
-        early_cb = cpu_baseline(_w, _synth.benchmark_params(_w["n_ch"]), (0, _w["n_ch"] - 1), getattr(_synth, _w["elems"]))
-
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    w, elems, params, er, plan, truth, vol = build_workload(args.workload, rank, world, device)
-    flat = vol.reshape(-1, vol.shape[-1])
+# ---- one workload on the GPU(s) --------------------------------------------------------------------------------------
+def accuracy_check(plan, flat, got, params, er, w, device):
+    """Amplitudes of what is being timed against a float64 solve of a pixel sample."""
     n_px = flat.shape[0]
-    n_comp = len(plan.names)
-    out = torch.zeros((n_comp, n_px), dtype=torch.float32, device=device)
-    total_rows = world * w["rows"]
-
-    peer_maps = None
-    if world > 1 and not w["snip"] and not args.nccl_gather:
-        try:
-            from mapstorch_b200.dist import PeerMaps
-            peer_maps = PeerMaps(n_comp, total_rows, w["width"], mode=args.gather)
-        except Exception as exc:  # pragma: no cover - needs symmetric memory support
-            print(f"bench: peer-memory maps unavailable ({exc}); gathering with NCCL", file=sys.stderr)
-    graph = None
-    if not args.no_graph and world == 1:
-        try:
-            graph = plan.make_graph(flat, out)
-        except Exception as exc:  # pragma: no cover - depends on the driver
-            print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
-
-    refine_state = {}
-
-    def step(gather=True, eager=False):
-        if peer_maps is not None and gather:
-            # fused: the fit kernels store the amplitudes into the destination GPUs' map buffers over NVLink
-            plan.fit(flat, out=peer_maps.local, peers=peer_maps.peers)
-            peer_maps.barrier()
-            return peer_maps.full
-        if graph is not None and not eager:
-            graph.replay()
-        else:
-            plan.fit(flat, out=out)
-        if w.get("refine"):
-            from mapstorch_b200.refine import refine_map
-            refine_state["out"] = refine_map(plan, flat, out, free=w["refine"], max_iter=w["refine_iters"])
-        if world > 1 and gather:
-            return gather_maps(out, total_rows, w["width"])
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    for _ in range(args.warmup):
-        step()
-    # accuracy of what is being timed: amplitudes against the ground truth (Poisson-limited) and
-    # against a float64 solve of a pixel sample
-    got = plan.fit(flat, out=out).clone()
     sample = torch.arange(0, n_px, max(1, n_px // 512), device=device)[:512]
     y64 = flat[sample].double()
     if w["snip"]:
         from mapstorch_b200 import bkg as _bkg
-        pr = [torch.tensor(float(params[k])) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH",
-                                                       "FWHM_OFFSET", "FWHM_FANOPRIME")]
+        pr = [torch.tensor(float(params[k])) for k in SNIP_KEYS]
         y64 = y64 - _bkg.snip_bkg(flat[sample].float(), er, *pr, device="cuda").double()
     ref = torch.linalg.lstsq(plan.basis.double().T, y64.T).solution.T  # [n, E]
     mine = got[:, sample].T.double()
@@ -403,60 +450,204 @@ def main():
         check.update({"nnls_pixels": len(sub),
                       "nnls_max_abs_err_over_pixel_max": float((np.abs(got_nn - ref_nn) / top).max()),
                       "nnls_max_rel_err_interior": float((np.abs(got_nn - ref_nn) / np.maximum(ref_nn, 1e-30))[inner].max())})
+    return check
+
+
+def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e_steps, with_cpu_baseline):
+    """Build, check, time one workload; returns the record of its measurements (rank 0's view)."""
+    import torch.distributed as dist
+    from mapstorch_b200 import _native, opt
+    from mapstorch_b200.dist import ShardedMapFit, gather_maps
+
+    w, elems, params, er, plan, truth, vol = build_workload(name, rank, world, device)
+    del truth
+    flat = vol.reshape(-1, vol.shape[-1])
+    n_px = flat.shape[0]
+    n_comp = len(plan.names)
+    out = torch.zeros((n_comp, n_px), dtype=torch.float32, device=device)
+    total_rows = world * w["rows"]
+    use_graph = not args.no_graph and not w.get("refine")
+
+    sharded = None
+    if world > 1:
+        sharded = ShardedMapFit(plan, total_rows, w["width"], gather=args.gather, buffers=2,
+                                use_peers=not args.nccl_gather)
+        if not sharded.fused:
+            print(f"bench: maps gathered with NCCL ({sharded.why_not})", file=sys.stderr)
+    graph = None
+    if use_graph and world == 1:
+        try:
+            graph = plan.make_graph(flat, out)
+        except Exception as exc:  # pragma: no cover - depends on the driver
+            print(f"bench: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+
+    refine_state = {}
+
+    def refine():
+        from mapstorch_b200.refine import refine_map
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        refine_state["out"] = refine_map(plan, flat, out, free=w["refine"], max_iter=w["refine_iters"])
+        t1.record()
+        refine_state.setdefault("events", []).append((t0, t1))
+
+    def step(gather=True, eager=False):
+        if sharded is not None and gather:
+            # fused: the fit kernels store the amplitudes into the destination GPUs' map buffers over NVLink; the
+            # completion of step k is awaited at the start of step k+1 (other buffer) and once more after the loop
+            sharded.step(flat, graph=use_graph and sharded.fused and not eager)
+            return
+        if graph is not None and not eager:
+            graph.replay()
+        else:
+            plan.fit(flat, out=out)
+        if w.get("refine"):
+            refine()
+
+    def finish():
+        if sharded is not None:
+            sharded.finish()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, after=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        if after is not None:
+            after()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(warmup):
+        step()
+    finish()
+    got = plan.fit(flat, out=out).clone()
+    check = accuracy_check(plan, flat, got, params, er, w, device)
 
     # ---- device-resident timing (value) ---------------------------------------------------------
     sampler = ClockSampler(device)
     time.sleep(0.6)  # let nvidia-smi finish its NVML start-up before the timed region
     for _ in range(2):
         step()
-    ms_total = timed(step, args.steps)
-    # same steps launched eagerly with CUDA events around the dominant kernel (roofline numerator)
-    plan.timers = []
+    finish()
     launches0 = _native.launch_count
-    ms_eager = timed(lambda: step(gather=False, eager=True), args.steps)
+    ms_total = timed(step, steps, after=finish)
+    launches_graph = _native.launch_count - launches0
+    # same steps launched eagerly with CUDA events around the kernels (roofline numerators)
+    plan.timers = []
+    refine_state.pop("events", None)
+    launches0 = _native.launch_count
+    ms_eager = timed(lambda: step(gather=False, eager=True), steps)
     launches = _native.launch_count - launches0
     clocks = sampler.stop()
     timers, plan.timers = plan.timers, None
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in timers]))
-    kernel_px = float(np.mean([n for _, _, n in timers]))
-    ms_fit_only = timed(lambda: step(gather=False), args.steps) if world > 1 else ms_total
-    ms_per_step = ms_total / args.steps
+    ms_fit_only = timed(lambda: step(gather=False), steps) if world > 1 else ms_total
+    ms_per_step = ms_total / steps
     value = world * n_px / (ms_per_step * 1e-3)
 
+    def kernel_stats(kind):
+        sel = [(a.elapsed_time(b), n) for k, a, b, n in timers if k == kind]
+        if not sel:
+            return None
+        per_step_ms = sum(t for t, _ in sel) / steps
+        return {"ms_per_step": per_step_ms, "launches_per_step": len(sel) / steps,
+                "ms_per_launch": float(np.mean([t for t, _ in sel])), "px_per_launch": float(np.mean([n for _, n in sel]))}
+
     es = flat.element_size()
-    in_row_bytes = w["n_ch"] * es * (1 if not w["snip"] else 1)
-    bytes_per_px = w["n_ch"] * (es if not w["snip"] else 4 * 2) + n_comp * 4  # what the contraction kernel streams
     peak, peak_src = measured_peak()
-    achieved = bytes_per_px * kernel_px / (kernel_ms * 1e-3) / 1e9
+    alg_bytes_px = w["n_ch"] * es + n_comp * 4  # SURVEY 8d: read the spectrum once, write the amplitudes once
+    job_frac = alg_bytes_px * n_px / (ms_fit_only / steps * 1e-3) / 1e9 / peak
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(args.workload)
+            traffic = json.loads(tf.read_text()).get(name)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fit_contract_kernel (tcgen05 + TMA)", "bytes_per_px": bytes_per_px,
-                "px_per_launch": kernel_px, "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "job_frac": (w["n_ch"] * es + n_comp * 4) * n_px / (ms_fit_only / args.steps * 1e-3) / 1e9 / peak}
+    k3 = kernel_stats("contract")
+    k2 = kernel_stats("snip")
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+    eager_ms = ms_eager / steps
+    contract_bytes_px = w["n_ch"] * (es if not w["snip"] else 4 * 2) + n_comp * 4  # what K3 streams (hi/lo residual planes)
+    k3_roof = None
+    if k3:
+        achieved = contract_bytes_px * k3["px_per_launch"] / (k3["ms_per_launch"] * 1e-3) / 1e9
+        k3_roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   "traffic": traffic, "kernel": "fit_contract_kernel (tcgen05 + TMA)", "bytes_per_px": contract_bytes_px,
+                   "px_per_launch": k3["px_per_launch"], "kernel_ms": k3["ms_per_launch"], "peak_source": peak_src,
+                   "share_of_step": k3["ms_per_step"] / eager_ms}
+    if w["snip"] and k2:
+        # K2 is bound by shared-memory bandwidth, not HBM (SURVEY 8d): passes * C * (2 fetches + 1 store) * 4 B per pixel
+        n_pass = int(plan._snip[1])
+        smem_bytes_px = n_pass * w["n_ch"] * 12
+        achieved = smem_bytes_px * k2["px_per_launch"] / (k2["ms_per_launch"] * 1e-3) / 1e9
+        smem_peak = n_sm * 128 * sm_mhz * 1e6 / 1e9
+        roofline = {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+                    "traffic": traffic, "kernel": "snip_kernel (K2)", "bytes_per_px": smem_bytes_px, "passes": n_pass,
+                    "px_per_launch": k2["px_per_launch"], "kernel_ms": k2["ms_per_launch"],
+                    "peak_source": f"{n_sm} SMs x 128 B/clk x {sm_mhz:.0f} MHz (SM clock sampled during the run)",
+                    "share_of_step": k2["ms_per_step"] / eager_ms, "contraction": k3_roof}
+    elif w.get("refine") and refine_state.get("events"):
+        ev_ms = float(np.mean([a.elapsed_time(b) for a, b in refine_state["events"]]))
+        cfg, _, _, _, _, window, _ = next(iter(plan._refine_tables.values()))
+        pairs = int(((window >> 16).astype(np.int64) - (window & 0xFFFF).astype(np.int64)).sum())
+        evals = float(refine_state["out"][2].float().mean()) + 1.0  # model evaluations per pixel (iterations + the first)
+        achieved = pairs * evals * n_px / (ev_ms * 1e-3) / 1e9
+        sfu_peak = n_sm * 16 * sm_mhz * 1e6 / 1e9
+        roofline = {"bound": "sfu", "achieved": achieved, "peak": sfu_peak, "unit": "Gexp/s", "frac": achieved / sfu_peak,
+                    "traffic": traffic, "kernel": "refine_kernel (K4)", "exp_per_px": pairs * evals,
+                    "line_channel_pairs": pairs, "evaluations_per_px": evals, "px_per_launch": n_px, "kernel_ms": ev_ms,
+                    "peak_source": f"{n_sm} SMs x 16 MUFU.EX2/clk x {sm_mhz:.0f} MHz; algorithmic count = one exp per (line, "
+                                   "channel) pair inside the 5.5 sigma windows and model evaluation",
+                    "share_of_step": ev_ms / eager_ms, "contraction": k3_roof}
+    else:
+        roofline = k3_roof
+    roofline["job_frac"] = job_frac  # the complete step against the HBM streaming roofline (C*sizeof(in) + E*4 per pixel)
+
+    # ---- multi-GPU: what the timed step assembled must be what NCCL would have gathered, bit for bit ----
+    peer_check = None
+    if sharded is not None and sharded.fused:
+        b = sharded.step(flat, graph=use_graph)
+        sharded.finish()
+        torch.cuda.synchronize()
+        sharded.peer_maps.check()
+        ref_full = gather_maps(plan.fit(flat, out=out), total_rows, w["width"])
+        res = sharded.result(b)
+        owned = sharded.owned()
+        same = all(torch.equal(res[j] if sharded.gather == "owner" else res[e], ref_full[e]) for j, e in enumerate(owned))
+        flag = torch.tensor([1 if same else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        peer_check = {"bit_identical": bool(int(flag)), "mode": sharded.gather, "graph": bool(use_graph),
+                      "components_checked_on_rank0": len(owned), "against": "NCCL all-gather of the same fit"}
+        del ref_full
 
     # ---- end to end through the public API, host buffers ------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if e2e_steps > 0:
         previous_affinity = bind_near_gpu(local_rank)
         host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
         host.copy_(flat)
         torch.cuda.synchronize()
 
         def e2e_step():
-            maps = opt.fit_map(host.reshape(vol.shape), er, elems, init_param_vals=params, use_snip=w["snip"],
+            return opt.fit_map(host.reshape(vol.shape), er, elems, init_param_vals=params, use_snip=w["snip"],
                                device="cpu", refine=w.get("refine"), refine_iters=w.get("refine_iters", 12))
-            return maps
 
         e2e_step()
-        ms = timed(e2e_step, args.e2e_steps) / args.e2e_steps
+        ms = timed(e2e_step, e2e_steps) / e2e_steps
         e2e = {"value": world * n_px / (ms * 1e-3), "unit": "px/s", "h2d_bytes_per_step": world * flat.numel() * es,
-               "d2h_bytes_per_step": world * n_comp * n_px * 4, "ms_per_step": ms, "steps": args.e2e_steps,
+               "d2h_bytes_per_step": world * n_comp * n_px * 4, "ms_per_step": ms, "steps": e2e_steps,
                "api": "mapstorch_b200.opt.fit_map(pinned host volume) -> host maps; plan build, chunked H2D "
                       "overlapped with the fit, D2H of the maps all inside the timed region",
                "numa_bound": previous_affinity is not None}
@@ -464,33 +655,148 @@ def main():
         if previous_affinity is not None:
             os.sched_setaffinity(0, previous_affinity)  # the CPU baseline below uses every core again
 
-    cb = early_cb
-    if cb is None and rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cb = None
+    if with_cpu_baseline and rank == 0 and world == 1 and not w.get("refine"):
         cb = cpu_baseline(w, params, er, elems)
 
+    if sharded is None:
+        step_desc = "fit of the resident shard (contraction + non-negative fix-up)"
+    elif sharded.fused:
+        step_desc = ("fit of the resident shard + element maps assembled over NVLink by the fit kernels' own peer stores "
+                     + {"owner": "(every component's full map on its owner GPU: balanced all-to-all)",
+                        "root": "(all maps on rank 0)", "all": "(all maps on every GPU)"}[sharded.gather]
+                     + "; completion signalled per step (mt_peer_signal), awaited before the next use of the same "
+                       "double-buffered destination and after the last step (mt_peer_wait)")
+    else:
+        step_desc = "fit of the resident shard + NCCL all-gather of the element maps"
+    rec = {"value": value, "unit": "px/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+           "dtype": "f16 x f16 -> f32 (tcgen05)" if w["dtype"] == "f16" else "tf32 x tf32 -> f32 (tcgen05)",
+           "config": {"workload": w["desc"], "name": name, "pixels_per_gpu": n_px, "channels": w["n_ch"],
+                      "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
+                      "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
+                      "step": step_desc},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+           "cuda_graph": (graph is not None) or bool(sharded is not None and sharded.fused and use_graph),
+           "gpu_launches_in_graphed_region": launches_graph,
+           "ms_per_step_eager_launch": eager_ms, "roofline": roofline, "cpu_baseline": cb,
+           "fit_only_px_s": world * n_px / (ms_fit_only / steps * 1e-3),
+           "refine": ({"free": list(w["refine"]), "mean_iterations": float(refine_state["out"][2].float().mean()),
+                       "mean_loss": float(refine_state["out"][1].mean())} if w.get("refine") else None),
+           "check_vs_float64_lstsq": check, "peer_check": peer_check}
+    del sharded, graph, vol, flat, out, got
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_config1(device, repeats=3):
+    """BASELINE config 1 through opt.fit_spec (global calibration fit of one integrated spectrum, on the GPU)."""
+    from mapstorch_b200 import opt
+
+    spec, params, elems = config1_spectrum()
+    kw = dict(elements_to_fit=elems, init_param_vals=params, tune_params=True, init_amp=True, use_snip=True, loss="mse",
+              optimizer="adamw", n_iter=500, progress_bar=False, device="cuda")
+    opt.fit_spec(spec, [50, 1450], **kw)  # warm (tables, kernels)
+    torch.cuda.synchronize()
+    secs, trace = [], None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        tensors, spec_fit, bkg, trace = opt.fit_spec(spec, [50, 1450], **kw)
+        torch.cuda.synchronize()
+        secs.append(time.perf_counter() - t0)
+    return {"seconds": float(np.median(secs)), "unit": "s per fit_spec call", "repeats": repeats, "final_loss": float(trace[-1]),
+            "first_loss": float(trace[0]), "workload": C1_DESC,
+            "fitted": {k: float(tensors[k]) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "COMPTON_ANGLE")
+                       if k in tensors}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="only the headline workload (no c2/c3/c4/config-1 sub-records)")
+    ap.add_argument("--nccl-gather", action="store_true", help="gather the maps with NCCL instead of peer-memory stores")
+    ap.add_argument("--gather", default="owner", choices=["owner", "root", "all"],
+                    help="peer-memory exchange of the element maps: every component assembled on its owner GPU "
+                         "(balanced all-to-all, default), everything on rank 0, or everything everywhere")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    # libraries (NCCL's version banner) write to fd 1; keep stdout for the ONE JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+    if args.impl == "reference":
+        run_reference(args, rank, world, emit)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+
+    early_cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and WORKLOADS[args.workload].get("refine"):
+        # this baseline forks one worker per core: run it before the CUDA context exists
+        from mapstorch_b200 import synth as _synth
+
+        _w = WORKLOADS[args.workload]
+        early_cb = cpu_baseline(_w, _synth.benchmark_params(_w["n_ch"]), (0, _w["n_ch"] - 1), getattr(_synth, _w["elems"]))
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    head = run_workload(args.workload, args, rank, local_rank, world, device, args.steps, args.warmup,
+                        0 if args.no_e2e else args.e2e_steps, not args.no_cpu_baseline)
+    if early_cb is not None:
+        head["cpu_baseline"] = early_cb
+
+    # ---- the other BASELINE configurations, short runs (same process, same box) ----
+    extra = {}
+    if not args.no_extra and args.workload == "c5":
+        others = ["c2", "c3", "c4"] if world == 1 else ["c3"]
+        for name in others:
+            try:
+                rec = run_workload(name, args, rank, local_rank, world, device, steps=min(args.steps, 6), warmup=3,
+                                   e2e_steps=0 if args.no_e2e else 2, with_cpu_baseline=False)
+                extra[name] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config", "e2e",
+                                                  "roofline", "cuda_graph", "ms_per_step_eager_launch", "fit_only_px_s",
+                                                  "refine", "check_vs_float64_lstsq", "peer_check", "gpu_launches")}
+            except Exception as exc:  # noqa: BLE001 - a sub-record must not cost the headline line
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                print(f"bench: workload {name} failed: {exc}", file=sys.stderr)
+        if world == 1:
+            try:
+                extra["c1"] = run_config1(device)
+            except Exception as exc:  # noqa: BLE001
+                extra["c1"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    failed = False
     if rank == 0:
-        line = {"metric": "pixels/sec", "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05)" if w["dtype"] == "f16" else "tf32 x tf32 -> f32 (tcgen05)",
-                "data": "synthetic",
-                "config": {"workload": w["desc"], "name": args.workload, "pixels_per_gpu": n_px, "channels": w["n_ch"],
-                           "components": n_comp, "storage": w["dtype"], "snip": w["snip"],
-                           "l2": f"inputs larger than L2 ({flat.numel() * es / 1e6:.0f} MB per GPU per step), no flush",
-                           "step": "fit of the resident shard (contraction + non-negative fix-up)" +
-                                   ("" if world == 1 else " + element maps assembled over NVLink by the fit kernels' own peer stores "
-                                    + {"owner": "(every component's full map on its owner GPU: balanced all-to-all)",
-                                       "gather": "(all maps on rank 0)", "allgather": "(all maps on every GPU)"}[peer_maps.mode]
-                                    + " + barrier" if peer_maps is not None
-                                    else " + NCCL all-gather of the element maps")},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cuda_graph": graph is not None,
-                "ms_per_step_eager_launch": ms_eager / args.steps, "roofline": roofline, "cpu_baseline": cb,
-                "fit_only_px_s": world * n_px / (ms_fit_only / args.steps * 1e-3),
-                "refine": ({"free": list(w["refine"]), "mean_iterations": float(refine_state["out"][2].float().mean()),
-                            "mean_loss": float(refine_state["out"][1].mean())} if w.get("refine") else None),
-                "check_vs_float64_lstsq": check}
+        line = {"metric": "pixels/sec", "value": head["value"], "unit": "px/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic", "config": head["config"]}
+        for k in ("clocks", "e2e", "gpu_launches", "cuda_graph", "gpu_launches_in_graphed_region", "ms_per_step_eager_launch",
+                  "roofline", "cpu_baseline", "fit_only_px_s", "refine", "check_vs_float64_lstsq", "peer_check"):
+            line[k] = head[k]
+        if extra:
+            line["workloads"] = extra
         emit(line)
+    checks = [head.get("peer_check")] + [v.get("peer_check") for v in extra.values() if isinstance(v, dict)]
+    failed = any(c is not None and not c["bit_identical"] for c in checks)
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        print("bench: peer-store maps differ from the NCCL gather", file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

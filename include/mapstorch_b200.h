@@ -81,6 +81,14 @@ typedef struct MtPeers {
     float *owner_row[MT_MAX_OWNED];
 } MtPeers;
 
+/* Completion flags of the fused exchange: flags[r] addresses rank r's flag array (uint32 [n_ranks], zero
+ * initialised, symmetric memory); rank q's signal of step k stores k to flags[r][q] on every r. */
+typedef struct MtPeerSync {
+    int32_t n_ranks;
+    int32_t rank;
+    uint32_t *flags[MT_MAX_PEERS];
+} MtPeerSync;
+
 int mt_abi_version(void);
 const char *mt_last_error(void);
 
@@ -190,6 +198,17 @@ int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_t n_px, int
 int mt_split_hilo(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch, float *out_dev,
                   int64_t ld_out, void *stream);
 
+/* Operand-exactness test for fp32 volumes on the tensor-core path: *flag_dev |= 1 (int32, zeroed by the caller)
+ * when any value of spec[p][col0 .. col0+n_ch) needs more than the 11 significant bits of a tf32 operand (or is
+ * not finite).  The reference accepts arbitrary float spectra (opt.py:344-375); volumes that fail the test are
+ * routed through mt_split_hilo. */
+int mt_operand_inexact(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch,
+                       int32_t *flag_dev, void *stream);
+
+/* Number of pixels, since the last reset, whose non-negative pivot system was numerically singular (near-collinear
+ * components); such pixels receive the clamped unconstrained solution.  Synchronises the device. */
+int mt_nnls_singular_count(uint64_t *count_host, int32_t reset);
+
 /* Same solve, driven by the pixel list mt_fit_contract compacted (no scan of x, every lane busy):
  * list_dev[i] for i < *count_dev are pixel numbers p (x_dev[e*ld_x + p]).  short_list != 0 selects
  * the warp-per-pixel variant (n_comp <= 32, element-major), which minimises the latency of a solve
@@ -198,6 +217,15 @@ int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *li
                  int32_t short_list,
                  int32_t n_comp, const double *g_dev, const double *hinv_dev,
                  const MtPeers *peers_host /* optional */, void *stream);
+
+/* The collective that is left of the map gather once the stores are fused into the fit:
+ * mt_peer_signal increments *epoch_dev and publishes it to every rank's flag array after everything queued on
+ * `stream` so far (the fit kernels' peer stores) has completed; mt_peer_wait blocks the stream until every rank
+ * has published an epoch >= *epoch_dev into this rank's array, i.e. until this rank holds every peer's share of
+ * the maps of that step.  Separate calls so that the wait of step k can overlap the fit of step k+1.  The wait
+ * is bounded (~10 s): on expiry *timed_out_dev (optional int32) is set to 1 + the silent rank. */
+int mt_peer_signal(const MtPeerSync *sync_host, uint32_t *epoch_dev, void *stream);
+int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t *timed_out_dev, void *stream);
 
 /* ---- K4: batched per-pixel nonlinear refinement (BASELINE config 4) ----------------------------
  * Replaces fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:165-327) applied per pixel:

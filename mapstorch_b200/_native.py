@@ -51,6 +51,10 @@ class MtPeers(ctypes.Structure):
                 ("multicast", ctypes.c_void_p), ("owner_row", ctypes.c_void_p * 32)]
 
 
+class MtPeerSync(ctypes.Structure):
+    _fields_ = [("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("flags", ctypes.c_void_p * 8)]
+
+
 THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3}
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
@@ -72,6 +76,10 @@ SIGNATURES = {
     "mt_nnls_fixup": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mt_penalty_shift": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "mt_split_hilo": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
+    "mt_operand_inexact": [_vp, _i64, _i64, _i32, _i32, _vp, _vp],
+    "mt_nnls_singular_count": [_vp, _i32],
+    "mt_peer_signal": [_vp, _vp, _vp],
+    "mt_peer_wait": [_vp, _vp, _vp, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
                   _vp, _vp],
 }
@@ -114,7 +122,8 @@ def check(status):
 # kernels launched per successful call of each entry point (bench.py reports the total)
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 1, "mt_refine": 1,
-                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1}
+                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1,
+                    "mt_peer_wait": 1}
 launch_count = 0
 
 

@@ -16,6 +16,10 @@ namespace {
 
 constexpr int kNnlsThreads = 128;
 
+// pixels whose pivot system turned out numerically singular (near-collinear components): they receive the clamped
+// unconstrained solution and are counted here; the host reads the total with mt_nnls_singular_count()
+__device__ unsigned long long g_singular_pixels = 0ull;
+
 // Packed lower-triangular Cholesky of M[idx, idx] (M: shared, row-major ld), then solve into v.
 // Returns false if a pivot is not positive (numerically singular subset).
 template <int HALF>
@@ -101,6 +105,7 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major
     for (int e = 0; e < E; ++e) {
         free_[e] = xu[e] > 0.0;
         n_free += free_[e];
+        xs[e] = xu[e];
     }
     double gmax = 0.0;
     for (int e = 0; e < E; ++e) gmax = fmax(gmax, G[e * E + e]);
@@ -163,7 +168,16 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major
                 }
             }
         }
-        if (!ok) break;
+        if (!ok) {
+            // singular subset (strongly overlapping components): fall back to the clamped unconstrained solution
+            // rather than pairing stale values with a half-updated index set, and tell the host
+            for (int e = 0; e < E; ++e) {
+                free_[e] = xu[e] > 0.0;
+                xs[e] = xu[e];
+            }
+            atomicAdd(&g_singular_pixels, 1ull);
+            break;
+        }
         int n_bad = 0, last_bad = -1;
         for (int e = 0; e < E; ++e) {
             const bool bad = free_[e] ? (xs[e] < -tol_x) : (xs[e] < -tol_y);
@@ -213,6 +227,7 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major
         const float out = (float)(free_[e] ? fmax(xs[e], 0.0) : 0.0);
         const long long at = base + e * se;
         x[at] = out;
+        if (peers.n_owned > 0 && e < MT_MAX_OWNED && peers.owner_row[e]) peers.owner_row[e][px] = out;
         for (int k = 0; k < peers.n_peers; ++k) peers.peer[k][at] = out;  // keep the peers' copies in step
         if (peers.multicast)
             asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.multicast + at), "f"(out) : "memory");
@@ -363,6 +378,19 @@ int dispatch_nnls(float *x, int64_t ld_x, int x_layout, int64_t n_px, int E, con
 }
 
 }  // namespace
+
+extern "C" int mt_nnls_singular_count(uint64_t *count_host, int32_t reset) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(count_host, "mt_nnls_singular_count: null pointer");
+    unsigned long long v = 0ull;
+    MT_CUDA_TRY(cudaMemcpyFromSymbol(&v, g_singular_pixels, sizeof(v)));
+    if (reset) {
+        const unsigned long long zero = 0ull;
+        MT_CUDA_TRY(cudaMemcpyToSymbol(g_singular_pixels, &zero, sizeof(zero)));
+    }
+    *count_host = v;
+    return MT_OK;
+}
 
 extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64_t n_px, int32_t n_comp,
                              const double *g_dev,

@@ -108,7 +108,38 @@ split_hilo_kernel(const float *__restrict__ spec, long long n_px, long long ld_s
     }
 }
 
+// flag[0] |= 1 when any value of the window is not exactly representable as a tf32 operand (low 13 mantissa bits set;
+// NaN / Inf included): integer counts >= 2048, but also normalised or dead-time corrected data.  One read of the window.
+__global__ void __launch_bounds__(256)
+operand_inexact_kernel(const float *__restrict__ spec, long long n_px, long long ld_spec, int col0, int n_ch,
+                       int *__restrict__ flag) {
+    const long long total = n_px * (long long)n_ch;
+    unsigned bad = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / n_ch;
+        const int c = (int)(i - p * n_ch);
+        const unsigned b = __float_as_uint(__ldg(spec + p * ld_spec + col0 + c));
+        bad |= (b & 0x1fffu) | (((b >> 23) & 0xffu) == 0xffu ? 1u : 0u);
+    }
+    if (__any_sync(0xffffffffu, bad != 0u) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 }  // namespace
+
+extern "C" int mt_operand_inexact(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch,
+                                  int32_t *flag_dev, void *stream) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(spec_dev && flag_dev, "mt_operand_inexact: null pointer");
+    MT_REQUIRE(n_px >= 0 && n_ch > 0 && col0 >= 0 && ld_spec >= (int64_t)col0 + n_ch, "mt_operand_inexact: bad sizes");
+    if (n_px == 0) return MT_OK;
+    const long long total = n_px * (long long)n_ch;
+    const long long want = (total + 255) / 256, cap = (long long)mt::num_sms() * 32;
+    operand_inexact_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        spec_dev, n_px, ld_spec, col0, n_ch, flag_dev);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
 
 extern "C" int mt_split_hilo(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch,
                              float *out_dev, int64_t ld_out, void *stream) {

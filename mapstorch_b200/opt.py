@@ -128,6 +128,7 @@ class MapFitPlan:
                             if k in default_param_vals})
         self.use_snip = bool(use_snip)
         self.boxcar_size = int(boxcar_size)
+        self.detector_type, self.escape_factor = detector_type, float(escape_factor)
         self.e_consts, self.elem_info = e_consts, elem_info  # the refinement builds its line tables from them
         elements = list(dict.fromkeys(list(elements_to_fit)))
         self.basis, self.names = _map.element_basis(self.params, self.er, elements, e_consts, elem_info,
@@ -158,7 +159,6 @@ class MapFitPlan:
         self.hinv_dev = torch.from_numpy(hinv).cuda()
         self._packs = {}
         self._snip = None
-        self._host_out = {}
         self._neg = None
         self._last_engine = None
         self._last_wide = False
@@ -167,7 +167,7 @@ class MapFitPlan:
         self.epilogue_fixup = True  # K3 epilogue fixes pixels whose zero set has <= 2 components itself
         self._h32 = None
         self._pixel_major = False
-        self.timers = None  # set to a list to collect (start, end, n_px) CUDA events around the contraction
+        self.timers = None  # set to a list to collect (kind, start, end, n_px) CUDA events around K2 / K3 launches
         if self.use_snip:
             p = self.params
             self._snip = _bkg.snip_tables_device(
@@ -220,17 +220,22 @@ class MapFitPlan:
     def _x_chunk(self, x, p0, n):
         return x[p0: p0 + n] if self._pixel_major else x[:, p0: p0 + n]
 
+    def _timed(self, kind, n_px, stream, fn):
+        """Run fn(); with self.timers set, bracket it with CUDA events on the launching stream."""
+        if self.timers is None:
+            return fn()
+        s = stream if stream is not None else torch.cuda.current_stream()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(s)
+        fn()
+        t1.record(s)
+        self.timers.append((kind, t0, t1, n_px))
+
     def _contract(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0, peers=None):
         """x[e, p] = sum_k spec2d[p, k] * pinv-pack[e, k] for the live components."""
-        if self.timers is not None:
-            s = stream if stream is not None else torch.cuda.current_stream()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record(s)
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset, peers)
-            t1.record(s)
-            self.timers.append((t0, t1, spec2d.shape[0]))
-        else:
-            self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg, px_offset, peers)
+        self._timed("contract", spec2d.shape[0], stream,
+                    lambda: self._contract_untimed(spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg,
+                                                   px_offset, peers))
 
     def _contract_untimed(self, spec2d, x, col0, repeat, k_begin, k_end, engine, stream, neg=None, px_offset=0,
                           peers=None):
@@ -267,6 +272,12 @@ class MapFitPlan:
         else:
             raise ValueError(f"unknown engine {engine!r}")
 
+    def _operand_inexact(self, spec2d, flag, stream=None):
+        """flag (int32 [1], device) |= 1 if the fitted window of an fp32 volume holds values a tf32 operand
+        cannot carry exactly (more than 11 significant bits: counts >= 2048, normalised / corrected data)."""
+        _native.call("mt_operand_inexact", spec2d.data_ptr(), spec2d.shape[0], spec2d.stride(0), self.er[0], self.n_ch,
+                     flag.data_ptr(), _native.stream_ptr(stream))
+
     def _penalty_coef(self, l1_lambda):
         """coef[e] of mt_penalty_shift: l1_lambda / (2 n_elements) * (G^-1 1)[e] for the live components;
         n_elements counts every fitted name like the reference's len(elements) (opt.py:377-381)."""
@@ -288,7 +299,12 @@ class MapFitPlan:
             neg[1].zero_()
         wide = False
         if not self.use_snip and engine == "tensor" and spec2d.dtype == torch.float32 and exact_counts is not True:
-            wide = exact_counts == "split" or bool(spec2d[:, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0)
+            if exact_counts == "split":
+                wide = True
+            else:
+                flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+                self._operand_inexact(spec2d, flag, stream)
+                wide = bool(flag.item())
         self._last_wide = wide
         if wide:
             # exact for any magnitude: stream the volume as a tf32-exact high part plus remainder
@@ -318,8 +334,9 @@ class MapFitPlan:
             mode = _native.MT_SNIP_RESIDUAL_HILO if hilo else _native.MT_SNIP_RESIDUAL
             for p0 in range(0, n_px, chunk):
                 n = min(chunk, n_px - p0)
-                _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass, self.boxcar_size,
-                                 scratch[:n], mode, stream)
+                self._timed("snip", n, stream,
+                            lambda: _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass,
+                                                     self.boxcar_size, scratch[:n], mode, stream))
                 self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
                                _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
                 if coef is not None:
@@ -377,9 +394,11 @@ class MapFitPlan:
 
         exact_counts: the tensor-core operands (fp16 / tf32) hold 11 significant bits, i.e. integer
         counts below 2048 exactly.  fp16 volumes satisfy that by construction and the SNIP path
-        splits its residual exactly; for fp32 volumes without SNIP, None (default) checks the
-        maximum on the device (one extra read of the volume and a host sync) and routes volumes
-        with larger values through an exact hi/lo split; True skips the check.
+        splits its residual exactly; for fp32 volumes without SNIP, None (default) tests every value of
+        the window for tf32 representability on the device (mt_operand_inexact: one extra read of the
+        volume and a host sync) and routes volumes that fail -- large counts, but also normalised or
+        dead-time corrected data -- through an exact hi/lo split; True asserts that the volume holds
+        integer counts below 2048 and skips the test (other data would be truncated to 11 bits).
 
         peers: optional _native.MtPeers whose pointers address, on the other GPUs of the box, the
         element of their map buffers that corresponds to out[0, 0]; the kernels then store every
@@ -424,6 +443,7 @@ class MapFitPlan:
             self._fit_serial(spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers,
                              self._penalty_coef(l1_lambda) if l1_lambda > 0 else None)
         if not dense:
+            out.zero_()  # components without an open line (caller-provided buffers included)
             out[torch.as_tensor(self.live, device="cuda")] = x
         return out
 
@@ -448,7 +468,7 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
     # out to hold larger counts are redone through the exact split path after ONE synchronisation at the end
     check = host2d.dtype == torch.float32 and not self.use_snip and engine == "tensor"
     starts = list(range(0, n_px, chunk))
-    too_big = torch.zeros(len(starts), dtype=torch.bool, device="cuda") if check else None
+    too_big = torch.zeros(len(starts), dtype=torch.int32, device="cuda") if check else None
     for i, p0 in enumerate(starts):
         b, n = i & 1, min(chunk, n_px - p0)
         with torch.cuda.stream(copier):
@@ -458,7 +478,7 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
             copied[b].record(copier)
         compute.wait_event(copied[b])
         if check:
-            too_big[i] = bufs[b][:n, self.er[0]: self.er[1] + 1].abs().amax() >= 2048.0
+            self._operand_inexact(bufs[b][:n], too_big[i: i + 1])
         self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
                  exact_counts=True if check else None, l1_lambda=l1_lambda)
         if after_slab is not None:
@@ -494,11 +514,10 @@ def _make_graph(self, spec2d, out, nonneg=True, engine="tensor"):
 
 
 def _to_host(self, x):
-    """Device -> pinned host copy of a result (the pinned buffer is cached per shape)."""
-    key = (tuple(x.shape), x.dtype)
-    if key not in self._host_out:
-        self._host_out[key] = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
-    host = self._host_out[key]
+    """Device -> pinned host copy of a result.  Every call returns a tensor the caller owns (plans are cached and
+    reused across fit_map calls, so a shared staging buffer would let the next fit overwrite earlier results);
+    torch's caching host allocator recycles the pinned block once the caller drops it."""
+    host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
     host.copy_(x, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host
@@ -538,7 +557,7 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
             device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384, refine=None,
-            refine_iters=12, refine_bounds=None, loss="mse", l1_lambda=0.0):
+            refine_iters=12, refine_bounds=None, loss="mse", l1_lambda=0.0, group=None, gather="all"):
     """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
 
     Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
@@ -547,15 +566,37 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     log10 like the reference's tensors if as_log10) on `device`; the two scatter components are
     always fitted, as in fit_spec (opt.py:194-200).
 
+    Any float spectra are accepted, like the reference.  Integer counts below 2048 (every fp16 volume) run the
+    single-pass tensor-core contraction with exact accumulation; fp32 volumes holding anything else (larger counts,
+    normalised or corrected data) are detected on the device and contracted as an exact two-operand split.
+
     refine: optional tuple of calibration parameters (subset of ENERGY_OFFSET, ENERGY_SLOPE, FWHM_OFFSET,
     FWHM_FANOPRIME) to free PER PIXEL together with the amplitudes, like fit_spec(fitting_params=refine,
     tune_params=True) per pixel; their maps, the final "loss" and "iterations" are added to the result.
 
     l1_lambda: the reference's sparsity penalty on the amplitudes (opt.py:372-396), per pixel.  loss="l1" is
-    available for single spectra (fit_spec); per-pixel L1 maps are not built."""
+    available for single spectra (fit_spec); per-pixel L1 maps are not built.
+
+    group: a torch.distributed process group (one rank per GPU).  spec_vol is then THIS rank's block of rows of a
+    row-sharded grid (dist.shard_rows) and the returned maps cover the whole grid: every component on every rank
+    (gather="all"), each rank's own components ("owner": component e on rank e % world) or everything on rank 0
+    ("root").  The exchange is fused into the fit kernels (peer stores over NVLink), see dist.ShardedMapFit."""
     if loss != "mse":
         raise NotImplementedError('fit_map minimises the MSE objective; loss="l1" exists for fit_spec only')
     _native.require_device()
+    if group is not None:
+        # multi-GPU form: spec_vol is this rank's block of rows; maps of the whole grid come back (dist.py)
+        if refine or as_log10 or plan is not None or return_plan or engine != "tensor":
+            raise NotImplementedError("fit_map(group=...) supports the plain map fit (no refine / as_log10 / plan / engine)")
+        from mapstorch_b200.dist import fit_map_sharded
+
+        if not isinstance(spec_vol, torch.Tensor):
+            spec_vol = torch.from_numpy(np.asarray(spec_vol))
+        maps = fit_map_sharded(spec_vol, energy_range, elements_to_fit, group=group, gather=gather,
+                               init_param_vals=init_param_vals, fixed_param_vals=fixed_param_vals, indices=indices,
+                               use_snip=use_snip, e_consts=e_consts, elem_info=elem_info, detector_type=detector_type,
+                               escape_factor=escape_factor, nonneg=nonneg, l1_lambda=l1_lambda)
+        return maps if torch.device(device).type == "cuda" else {k: v.cpu() for k, v in maps.items()}
     if not isinstance(spec_vol, torch.Tensor):
         arr = np.asarray(spec_vol)
         if arr.dtype not in (np.float32, np.float16):

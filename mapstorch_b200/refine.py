@@ -125,6 +125,13 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
     Returns (theta [len(free), P], loss [P], iterations [P]) on the device."""
     if plan.n_live != len(plan.names):
         raise NotImplementedError("refinement with components that have no open line")
+    # mt_refine minimises over every channel of the window with Gaussian lines only; the plan's G^-1 (its fixed
+    # amplitude curvature) was built from the masked / escape-augmented basis, so these options would silently
+    # answer a different problem than the linear fit and the reference's fit_spec(indices=..., escape_factor=...)
+    if plan.chan_mask is not None:
+        raise NotImplementedError("per-pixel refinement with a channel mask (indices=...)")
+    if getattr(plan, "escape_factor", 0.0) > 0:
+        raise NotImplementedError("per-pixel refinement with escape peaks (escape_factor > 0)")
     free = list(free)
     unknown = [f for f in free if f not in _native.THETA_IDS]
     if unknown or len(free) > 4:

@@ -10,6 +10,7 @@ Outputs (np.savez_compressed):
   model_golden.npz  model_elem_spec / compton_peak / elastic_peak / model_spec outputs
   snip_golden.npz   snip_bkg inputs+outputs and the per-pass gather indices
   fit_golden.npz    per-spectrum fit_spec(tune_params=False) runs (converged Adam) + loss traces
+  fit_c3_golden.npz the same at BASELINE config 3's shape: 4096 channels, 30 elements, SNIP (--only fit_c3)
   host_golden.npz   init_elem_amps, get_peak_ranges, escape bins
   objectives_golden.npz  fit_spec(tune_params=False) with loss="l1", l1_lambda > 0 and `indices` (--only objectives)
   override_golden.npz  override files written by the reference, what its parser and read_constants make of
@@ -250,6 +251,36 @@ def gen_fit(out, quick):
         print(tag, "final loss", trace[-1], flush=True)
 
 
+def gen_fit_c3(out):
+    """BASELINE config 3's shape: 4096 channels, 30 elements + 2 scatter peaks, SNIP background -- two pixels
+    (high- and low-count) through the reference's own fit_spec(tune_params=False, use_snip=True), Adam, 4000 steps."""
+    torch.set_num_threads(8)
+    rng = np.random.default_rng(33)
+    p4 = params_4096()
+    runs = []
+    for i, (lo, hi, flat) in enumerate(((1.5, 3.0, 3.0), (0.3, 1.6, 1.0))):
+        spec, amps = synth_spectrum(p4, (0, 4095), ELEMS30, rng, lo, hi, flat=flat)
+        runs.append((f"e30_snip_px{i}", p4, (0, 4095), ELEMS30, spec, True, 4000))
+    out["fit_runs"] = np.array([r[0] for r in runs])
+    for tag, pp, er, elems, spec, use_snip, n_iter in runs:
+        tensors, spec_fit, bkg, trace = ropt.fit_spec(
+            spec, er, elements_to_fit=list(elems), init_param_vals=pp, tune_params=False, init_amp=True,
+            use_snip=use_snip, loss="mse", optimizer="adam", n_iter=n_iter, progress_bar=False)
+        names = list(elems) + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+        out[f"{tag}_spec"] = spec
+        out[f"{tag}_er"] = np.array(er)
+        out[f"{tag}_names"] = np.array(names)
+        out[f"{tag}_param_names"] = np.array(list(pp.keys()))
+        out[f"{tag}_param_vals"] = np.array([pp[k] for k in pp], dtype=np.float64)
+        out[f"{tag}_logamps"] = np.array([tensors[n].item() for n in names], dtype=np.float64)
+        out[f"{tag}_spec_fit"] = spec_fit
+        out[f"{tag}_bkg"] = bkg
+        out[f"{tag}_trace"] = np.array(trace[::10] + trace[-1:], dtype=np.float64)
+        out[f"{tag}_use_snip"] = np.array(use_snip)
+        out[f"{tag}_n_iter"] = np.array(n_iter)
+        print(tag, "final loss", trace[-1], flush=True)
+
+
 def gen_random_tables(out, n_sets=40):
     """Index arithmetic under randomly perturbed calibrations: CRC32 of every SNIP gather table, pass
     counts, escape bins, amplitude-guess windows and peak ranges, all computed by the reference's own
@@ -485,6 +516,12 @@ def main():
         gen_objectives(out)
         np.savez_compressed(HERE / "objectives_golden.npz", **out)
         print("wrote objectives", (HERE / "objectives_golden.npz").stat().st_size, flush=True)
+        return
+    if args.only == "fit_c3":
+        out = {}
+        gen_fit_c3(out)
+        np.savez_compressed(HERE / "fit_c3_golden.npz", **out)
+        print("wrote fit_c3", (HERE / "fit_c3_golden.npz").stat().st_size, flush=True)
         return
     if args.only == "refine":
         out = {}

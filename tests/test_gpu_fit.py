@@ -365,3 +365,90 @@ def test_chunked_paths_equal_the_single_chunk_result(monkeypatch, case):
         assert torch.equal(whole[k], parts[k]), (case, k)
     if bright:
         assert y.max() >= 2048  # the exact-split path was the one exercised
+
+
+def test_bright_fp16_volume_accuracy():
+    """Counts near the top of fp16's exact-integer range (2047) in many channels: sum_k y_k |digit_k| exceeds 2^24,
+    so the tensor-core accumulation is no longer exact integer arithmetic and rounds like ordinary fp32
+    (csrc/mt_fit.cu header).  The result must still sit well inside the 1e-4 bar."""
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12(4096)
+    er = (0, 4095)
+    B, names = mo.basis(p, er, ELEMS30)
+    rng = np.random.default_rng(404)
+    amps = 10.0 ** rng.uniform(2.0, 3.0, size=(384, B.shape[1]))
+    lam = amps @ B.astype(np.float64).T
+    lam *= 1900.0 / lam.max(axis=1, keepdims=True)  # brightest channel of every pixel near 1900 counts
+    y = np.minimum(rng.poisson(lam + 600.0), 2047).astype(np.float32)  # + a bright flat floor: every channel is large
+    assert (y > 512).mean() > 0.9 and y.max() == 2047
+    ref = mo.fit_lstsq(y, B)
+    plan = opt.MapFitPlan(er, ELEMS30, p, use_snip=False)
+    x = plan.fit(torch.from_numpy(y).half().cuda(), nonneg=False).cpu().numpy().T
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    err = (np.abs(x - ref) / scale).max()
+    interior = np.abs(ref) > 1e-3 * scale
+    rel = (np.abs(x - ref)[interior] / np.abs(ref)[interior]).max()
+    print(f"bright fp16: max error {err:.3g} of the pixel maximum, {rel:.3g} relative on interior components")
+    assert err <= 2e-5 and rel <= 1e-4
+
+
+def test_non_integer_fp32_volume_is_not_truncated():
+    """Normalised / dead-time corrected data are not integer counts: values with more than 11 significant bits are
+    detected on the device (mt_operand_inexact) and take the exact split path, whatever their magnitude."""
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12()
+    er = (0, 2047)
+    y, names = synth(p, er, ELEMS10, 300, seed=41, lo=1.5, hi=3.0)
+    y = (y * np.float32(0.3712)).astype(np.float32)  # all values < 2048, almost none tf32-exact
+    assert y.max() < 2048
+    B, _ = mo.basis(p, er, ELEMS10)
+    ref = mo.fit_lstsq(y, B)
+    plan = opt.MapFitPlan(er, ELEMS10, p, use_snip=False)
+    dev = torch.from_numpy(y).cuda()
+    x = plan.fit(dev, nonneg=False).cpu().numpy().T
+    assert plan._last_wide
+    assert (np.abs(x - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() <= 2e-6
+    # integer counts below 2048 keep the single-pass path
+    plan.fit(torch.from_numpy(np.rint(y)).cuda(), nonneg=False)
+    assert not plan._last_wide
+    # streamed host volumes: only the inexact slabs are redone
+    mixed = np.concatenate([np.rint(y[:128]), y[:60]])
+    xh = plan.fit_host(torch.from_numpy(mixed), nonneg=False, chunk_px=64).cpu().numpy().T
+    refm = mo.fit_lstsq(mixed, B)
+    assert (np.abs(xh - refm) / np.abs(refm).max(axis=1, keepdims=True)).max() <= 2e-6
+
+
+def test_host_results_of_consecutive_calls_are_independent():
+    """fit_map(device="cpu") returns tensors the caller owns: plans (and their buffers) are cached across calls, so a
+    second fit with the same calibration and shape must not overwrite the first result."""
+    from mapstorch_b200 import opt
+
+    p = params12()
+    er = (0, 2047)
+    y1, names = synth(p, er, ELEMS10, 64, seed=51)
+    y2, _ = synth(p, er, ELEMS10, 64, seed=52)
+    kw = dict(init_param_vals=p, use_snip=False, device="cpu")
+    first = opt.fit_map(torch.from_numpy(y1).reshape(8, 8, -1), er, ELEMS10, **kw)
+    keep = {k: v.clone() for k, v in first.items()}
+    second = opt.fit_map(torch.from_numpy(y2).reshape(8, 8, -1), er, ELEMS10, **kw)
+    for k in keep:
+        assert torch.equal(first[k], keep[k]), k
+        assert not torch.equal(first[k], second[k]), k
+        assert first[k].data_ptr() != second[k].data_ptr()
+
+
+def test_caller_buffer_rows_of_dead_components_are_zeroed():
+    from mapstorch_b200 import opt
+
+    p = params12()
+    er = (0, 2047)
+    elems = ELEMS10 + ["Pb_L"]  # no open Pb L line at 12 keV
+    y, _ = synth(p, er, ELEMS10, 32, seed=61)
+    plan = opt.MapFitPlan(er, elems, p, use_snip=False)
+    out = torch.full((len(plan.names), 32), 7.0, device="cuda")
+    plan.fit(torch.from_numpy(y).cuda(), out=out)
+    assert float(out[plan.names.index("Pb_L")].abs().max()) == 0.0

@@ -193,3 +193,32 @@ def test_variable_projection_oracle_beats_the_reference_adam_run():
     for n in names:
         if ref_amp[n] > 1e-3 * big:
             assert abs(mine[n] / ref_amp[n] - 1) < 1e-4, n
+
+
+def test_oracle_matches_reference_fit_at_config3_shape():
+    """fit_c3_golden: the reference's fit_spec(tune_params=False, use_snip=True, adam, 4000 it) at 4096 channels, 30
+    elements + 2 -- the oracle's SNIP background and float64 NNLS on it reproduce the converged reference fit."""
+    from conftest import GOLDEN, conditional_optimum
+
+    g = np.load(GOLDEN / "fit_c3_golden.npz", allow_pickle=False)
+    for tag in [str(t) for t in g["fit_runs"]]:
+        p = golden_params(g, tag)
+        er = tuple(int(v) for v in g[f"{tag}_er"])
+        names = [str(n) for n in g[f"{tag}_names"]]
+        spec = g[f"{tag}_spec"]
+        B, bnames = mo.basis(p, er, names[:-2])
+        pr = [p[k] for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")]
+        bkg = mo.snip_bkg(spec, er, *pr)
+        assert np.abs(bkg - g[f"{tag}_bkg"]).max() <= 1e-5 * g[f"{tag}_bkg"].max()
+        ref_log = dict(zip(names, g[f"{tag}_logamps"]))
+        ref_amp = np.array([10.0 ** ref_log[n] for n in bnames])
+        x = mo.fit_nnls(spec, B, bkg)[0]
+        # the reference's loss is still creeping down (clamped components decay like 10**a): never below the optimum
+        b64 = B.astype(np.float64)
+        assert ((b64 @ x + bkg - spec) ** 2).sum() <= g[f"{tag}_trace"][-1] * (1 + 1e-6)
+        cond = conditional_optimum(x, b64.T @ b64, ref_amp)
+        interior = x > 1e-3 * x.max()
+        rel = np.abs(ref_amp[interior] / cond[interior] - 1)
+        print(tag, "reference Adam vs oracle NNLS conditioned on the reference's leftover clamped amplitudes:", rel.max())
+        assert rel.max() < 1e-4, (tag, rel.max())
+        assert np.all(ref_amp[x == 0] <= 2e-3 * x.max())  # what the reference still carries on the clamped components
