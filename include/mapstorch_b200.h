@@ -221,11 +221,13 @@ int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *li
 /* The collective that is left of the map gather once the stores are fused into the fit:
  * mt_peer_signal increments *epoch_dev and publishes it to every rank's flag array after everything queued on
  * `stream` so far (the fit kernels' peer stores) has completed; mt_peer_wait blocks the stream until every rank
- * has published an epoch >= *epoch_dev into this rank's array, i.e. until this rank holds every peer's share of
- * the maps of that step.  Separate calls so that the wait of step k can overlap the fit of step k+1.  The wait
+ * has published an epoch >= *epoch_dev - lag into this rank's array, i.e. until this rank holds every peer's share
+ * of the maps of that step.  lag = 1 after the signal of step k waits for everybody's step k-1: with double-buffered
+ * maps the ranks then run with one step of slack and the barrier of step k overlaps step k+1.  The wait
  * is bounded (~10 s): on expiry *timed_out_dev (optional int32) is set to 1 + the silent rank. */
 int mt_peer_signal(const MtPeerSync *sync_host, uint32_t *epoch_dev, void *stream);
-int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t *timed_out_dev, void *stream);
+int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t lag, int32_t *timed_out_dev,
+                 void *stream);
 
 /* ---- K4: batched per-pixel nonlinear refinement (BASELINE config 4) ----------------------------
  * Replaces fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:165-327) applied per pixel:

@@ -79,7 +79,7 @@ SIGNATURES = {
     "mt_operand_inexact": [_vp, _i64, _i64, _i32, _i32, _vp, _vp],
     "mt_nnls_singular_count": [_vp, _i32],
     "mt_peer_signal": [_vp, _vp, _vp],
-    "mt_peer_wait": [_vp, _vp, _vp, _vp],
+    "mt_peer_wait": [_vp, _vp, _i32, _vp, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
                   _vp, _vp],
 }

@@ -6,10 +6,11 @@
 //   mt_peer_signal : ++epoch (device counter), then epoch -> flags[r][my rank] on every rank r.  Stream order puts
 //                    it after the fit kernels; kernel completion makes their peer stores visible system-wide, the
 //                    flag stores are release stores at system scope on top of that.
-//   mt_peer_wait   : spin (acquire loads, bounded) until every rank's slot in MY flag array has reached my epoch.
+//   mt_peer_wait   : spin (acquire loads, bounded) until every rank's slot in MY flag array has reached my epoch - lag.
 // Both read the epoch from device memory, so a CUDA graph holding them replays correctly.  Because signal and wait
-// are separate, the wait of step k can be issued after step k+1's fit has been launched (double-buffered maps): the
-// barrier latency then hides behind the next step's streaming instead of ending every step.
+// are separate and the wait takes a lag, step k can end with "wait for everybody's step k-1" (double-buffered maps):
+// the ranks then synchronise with one step of slack instead of in lock-step, and the barrier latency hides behind
+// the next step's streaming.
 #include "mt_common.cuh"
 
 namespace {
@@ -28,9 +29,9 @@ __global__ void peer_signal_kernel(MtPeerSync sync, uint32_t *epoch) {
     }
 }
 
-__global__ void peer_wait_kernel(MtPeerSync sync, const uint32_t *epoch, int *timed_out) {
+__global__ void peer_wait_kernel(MtPeerSync sync, const uint32_t *epoch, uint32_t lag, int *timed_out) {
     if ((int)threadIdx.x < sync.n_ranks) {
-        const uint32_t want = *epoch;
+        const uint32_t want = *epoch - lag;
         const uint32_t *slot = sync.flags[sync.rank] + threadIdx.x;
         long long t0 = 0;
         for (uint32_t spin = 0;; ++spin) {
@@ -69,11 +70,12 @@ extern "C" int mt_peer_signal(const MtPeerSync *sync_host, uint32_t *epoch_dev, 
     return MT_OK;
 }
 
-extern "C" int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t *timed_out_dev, void *stream) {
+extern "C" int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t lag, int32_t *timed_out_dev,
+                            void *stream) {
     if (int rc = mt::require_sm100()) return rc;
     if (int rc = check_sync(sync_host, "mt_peer_wait")) return rc;
-    MT_REQUIRE(epoch_dev, "mt_peer_wait: null epoch");
-    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*sync_host, epoch_dev, timed_out_dev);
+    MT_REQUIRE(epoch_dev && lag >= 0, "mt_peer_wait: null epoch or negative lag");
+    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*sync_host, epoch_dev, (uint32_t)lag, timed_out_dev);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }

@@ -202,14 +202,14 @@ class PeerMaps:
 
         _native.call("mt_peer_signal", ctypes.byref(self.sync), self._epoch.data_ptr(), _native.stream_ptr(stream))
 
-    def wait(self, stream=None):
-        """Block `stream` until every rank has signalled as many times as this rank has."""
+    def wait(self, lag=0, stream=None):
+        """Block `stream` until every rank has signalled (this rank's count - lag) times."""
         import ctypes
 
         from mapstorch_b200 import _native
 
-        _native.call("mt_peer_wait", ctypes.byref(self.sync), self._epoch.data_ptr(), self._timed_out.data_ptr(),
-                     _native.stream_ptr(stream))
+        _native.call("mt_peer_wait", ctypes.byref(self.sync), self._epoch.data_ptr(), int(lag),
+                     self._timed_out.data_ptr(), _native.stream_ptr(stream))
 
     def check(self):
         """Raise if a wait expired (a peer never signalled).  Synchronises."""
@@ -272,9 +272,10 @@ class ShardedMapFit:
     gather: "owner" (component e's full map on rank e % world: the balanced exchange), "all" (every map on every
     rank) or "root" (every map on rank 0).
 
-    step(shard2d) launches fit + signal into the current buffer and flips to the other one; finish() waits until
-    this rank holds every peer's share of all steps launched so far.  With two buffers step k+1 may be launched
-    before finish() of step k: its completion latency then hides behind the next fit."""
+    step(shard2d) launches fit + signal into the current buffer (with two buffers followed by a wait for everybody's
+    PREVIOUS step) and flips to the other buffer; finish() waits until this rank holds every peer's share of all
+    steps launched so far.  With two buffers the ranks therefore run with one step of slack: the completion latency
+    of step k hides behind the fit of step k+1."""
 
     MODES = {"owner": "owner", "all": "allgather", "root": "gather"}
 
@@ -327,12 +328,9 @@ class ShardedMapFit:
                 self._graphs[key] = self._capture(shard2d, fit_kw)
             self._graphs[key].replay()
         else:
-            # every peer has finished the PREVIOUS step (its stores into the other buffer have landed, and whatever
-            # it queued before that step -- e.g. reading this buffer's older maps -- is done) before this rank
-            # overwrites the peers' copy of this buffer
-            pm.wait()
             self.plan.fit(shard2d, out=pm.local, peers=pm.peers, **fit_kw)
             pm.signal()
+            self._trailing_wait()
         self._last = b
         pm.flip()
         return b
@@ -342,20 +340,28 @@ class ShardedMapFit:
         saved, plan.timers = plan.timers, None
         # warm run outside the capture (operand packs, tables, the count-range check of fp32 volumes); its signal
         # keeps every rank's epoch in step with the eager path
-        pm.wait()
         plan.fit(shard2d, out=pm.local, peers=pm.peers, **fit_kw)
         pm.signal()
+        self._trailing_wait()
         torch.cuda.synchronize()
         kw = dict(fit_kw)
         if shard2d.dtype == torch.float32 and not plan.use_snip and "exact_counts" not in kw:
             kw["exact_counts"] = "split" if plan._last_wide else True  # no host sync inside the capture
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            pm.wait()
             plan.fit(shard2d, out=pm.local, peers=pm.peers, **kw)
             pm.signal()
+            self._trailing_wait()
         plan.timers = saved
         return g
+
+    def _trailing_wait(self):
+        """With two buffers a step ends by waiting for everybody's PREVIOUS step: the maps of step k-1 (other buffer)
+        are then complete on this rank, and nobody can still be storing into the buffer that step k+1 reuses -- the
+        ranks run with one step of slack instead of in lock-step.  A rank that reads maps(b) between steps on the same
+        stream is ordered before its next signal, hence before any peer overwrites that buffer two steps later."""
+        if self.peer_maps.buffers >= 2:
+            self.peer_maps.wait(lag=1)
 
     def finish(self):
         """Block the current stream until the maps of every step launched so far are complete on this rank."""
