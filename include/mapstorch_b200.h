@@ -121,6 +121,7 @@ int mt_model_sum(const float *cols_dev, int64_t ld_cols, int32_t n_cols, int32_t
 #define MT_SNIP_BACKGROUND 0
 #define MT_SNIP_RESIDUAL 1
 #define MT_SNIP_RESIDUAL_HILO 2
+#define MT_SNIP_RESIDUAL_HILO_F16 3 /* mt_snip_residual_f16 only */
 int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
             int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar, float *out_dev,
             int64_t ld_out, int32_t out_mode, void *stream);
@@ -197,6 +198,16 @@ int mt_penalty_shift(const void *spec_dev, int32_t spec_dtype, int64_t n_px, int
  * operand pack repeated twice -- the layout MT_SNIP_RESIDUAL_HILO produces for the SNIP path. */
 int mt_split_hilo(const float *spec_dev, int64_t n_px, int64_t ld_spec, int32_t col0, int32_t n_ch, float *out_dev,
                   int64_t ld_out, void *stream);
+
+/* K2 writing the residual as TWO FP16 PLANES for the fp16 tensor-core path of mt_fit_contract: out_half_dev =
+ * fp16 [n_px][ld_out] (ld_out in fp16 elements, >= 2*n_ch): [0,n_ch) = spectrum - background rounded to fp16,
+ * [n_ch,2n_ch) = the remainder (22 significant bits together, like MT_SNIP_RESIDUAL_HILO, at half the bytes: the
+ * residual crosses HBM as 4 bytes per channel instead of 8).  *overflow_dev |= 1 (int32, zeroed by the caller) when a
+ * residual exceeds the fp16 range (|r| > 65504); the caller then repeats that slab with MT_SNIP_RESIDUAL_HILO.
+ * tab_dev / ld_tab: the gather table of mt_snip (scaled = 0, ld_tab ignored) or of mt_snip_scaled (scaled = 1). */
+int mt_snip_residual_f16(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0, int32_t n_ch,
+                         const uint32_t *tab_dev, int32_t ld_tab, int32_t scaled, int32_t n_pass, int32_t boxcar,
+                         void *out_half_dev, int64_t ld_out, int32_t *overflow_dev, void *stream);
 
 /* Operand-exactness test for fp32 volumes on the tensor-core path: *flag_dev |= 1 (int32, zeroed by the caller)
  * when any value of spec[p][col0 .. col0+n_ch) needs more than the 11 significant bits of a tf32 operand (or is

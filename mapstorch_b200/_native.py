@@ -11,7 +11,7 @@ MT_OK = 0
 MT_ERR_INVALID, MT_ERR_CUDA, MT_ERR_UNSUPPORTED, MT_ERR_NO_DEVICE = -1, -2, -3, -4  # include/mapstorch_b200.h
 MT_DTYPE_F32, MT_DTYPE_F16 = 0, 1
 MT_TERM_GAUSS, MT_TERM_STEP, MT_TERM_TAIL = 0, 1, 2
-MT_SNIP_BACKGROUND, MT_SNIP_RESIDUAL, MT_SNIP_RESIDUAL_HILO = 0, 1, 2
+MT_SNIP_BACKGROUND, MT_SNIP_RESIDUAL, MT_SNIP_RESIDUAL_HILO, MT_SNIP_RESIDUAL_HILO_F16 = 0, 1, 2, 3
 MT_X_ELEMENT_MAJOR, MT_X_PIXEL_MAJOR = 0, 1
 
 _LIB_NAME = "libmapstorch_b200.so"
@@ -69,6 +69,7 @@ SIGNATURES = {
     "mt_snip_scaled_pitch": [_i32],
     "mt_snip_scale_tables": [_vp, _i32, _i32, _vp, _i32, _vp],
     "mt_snip_scaled": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp],
+    "mt_snip_residual_f16": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp],
     "mt_fit_contract": [_vp, _i32, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp,
                         _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "mt_nnls_list": [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
@@ -121,8 +122,8 @@ def check(status):
 
 # kernels launched per successful call of each entry point (bench.py reports the total)
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
-                    "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 1, "mt_refine": 1,
-                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1,
+                    "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 2, "mt_refine": 1,
+                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_snip_residual_f16": 1,
                     "mt_peer_wait": 1}
 launch_count = 0
 

@@ -41,6 +41,19 @@ def snip_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode,
     return out
 
 
+def snip_residual_f16(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out_half, overflow, stream=None):
+    """The residual y - bkg as two fp16 planes [P, 2*n_ch] (hi | remainder) for the fp16 tensor-core contraction;
+    overflow (int32 [1]) is raised when a residual does not fit fp16."""
+    scaled = getattr(lohi_dev, "_mt_scaled", None)
+    use_scaled = scaled is not None and scaled.shape[0] == int(n_pass) + 1
+    tab = scaled if use_scaled else lohi_dev
+    _native.call("mt_snip_residual_f16", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.shape[0],
+                 spec2d.stride(0), int(ch0), int(n_ch), tab.data_ptr(), tab.stride(0) if use_scaled else int(n_ch),
+                 int(use_scaled), int(n_pass), int(boxcar_size), out_half.data_ptr(), out_half.stride(0),
+                 overflow.data_ptr(), _native.stream_ptr(stream))
+    return out_half
+
+
 def snip_op(background, current_width, max_of_xmin, min_of_xmax, device):
     """One clipping pass (bkg.py:53-66) on an already log-compressed background."""
     _native.require_device()

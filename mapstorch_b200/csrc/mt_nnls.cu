@@ -61,10 +61,11 @@ __global__ void __launch_bounds__(kNnlsThreads)
 nnls_fixup_kernel(float *__restrict__ x, long long ld_x, int pixel_major, long long n_px, int E,
                   const double *__restrict__ g_dev,
                   const double *__restrict__ h_dev, int *__restrict__ n_fixed, const int *__restrict__ list,
-                  const int *__restrict__ list_count, const MtPeers peers) {
+                  const int *__restrict__ list_count, int list_min, const MtPeers peers) {
     extern __shared__ double mats[];  // G[E*E], H[E*E]
-    // list mode: blocks beyond the (device-side) item count have nothing to do
-    if (list && (long long)blockIdx.x * kNnlsThreads >= (long long)*list_count) return;
+    // list mode: blocks beyond the (device-side) item count have nothing to do; lists of at most list_min items
+    // belong to the warp-per-pixel kernel
+    if (list && ((long long)blockIdx.x * kNnlsThreads >= (long long)*list_count || *list_count <= list_min)) return;
     double *G = mats, *H = mats + E * E;
     for (int i = threadIdx.x; i < E * E; i += kNnlsThreads) {
         G[i] = g_dev[i];
@@ -236,7 +237,7 @@ __device__ void fix_pixel(float *__restrict__ x, long long ld_x, int pixel_major
 
 template <int EMAX>
 int launch_nnls(float *x, int64_t ld_x, int pixel_major, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
-                const int *list, const int *list_count, const MtPeers &peers, cudaStream_t stream) {
+                const int *list, const int *list_count, int list_min, const MtPeers &peers, cudaStream_t stream) {
     auto kern = nnls_fixup_kernel<EMAX>;
     const size_t smem = sizeof(double) * 2 * (size_t)E * E;
     static int smem_set[16] = {0};
@@ -247,7 +248,8 @@ int launch_nnls(float *x, int64_t ld_x, int pixel_major, int64_t n_px, int E, co
         if (dev < 16) smem_set[dev] = (int)smem;
     }
     const unsigned grid = list ? (unsigned)(mt::num_sms() * 8) : (unsigned)((n_px + kNnlsThreads - 1) / kNnlsThreads);
-    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers);
+    kern<<<grid, kNnlsThreads, smem, stream>>>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, list_min,
+                                               peers);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
@@ -260,13 +262,17 @@ int launch_nnls(float *x, int64_t ld_x, int pixel_major, int64_t n_px, int E, co
 // with row r in lane r's registers, x_F = xu_F - H_FA z, duals on A are -z.  fp64, registers and
 // shuffles only; H = G^-1 in shared memory.
 constexpr int kListWarps = 4;
+// Lists longer than this go to the thread-per-pixel kernel instead (throughput, not latency, decides then: on the
+// SNIP workload of BASELINE config 3 most pixels clamp three or more components and the warp kernel took 0.79 ms
+// per 131 072-pixel shard).  The count lives on the device, so both kernels are launched and one returns at once.
+constexpr int kShortListMax = 6144;
 
 __global__ void __launch_bounds__(kListWarps * 32)
 nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ list,
                  const int *__restrict__ count, int E, const double *__restrict__ h_dev, const MtPeers peers) {
     extern __shared__ double Hs[];  // [E*E]
     const int n_items = *count;
-    if (blockIdx.x * kListWarps >= n_items) return;
+    if (blockIdx.x * kListWarps >= n_items || n_items > kShortListMax) return;
     for (int i = threadIdx.x; i < E * E; i += blockDim.x) Hs[i] = h_dev[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -359,7 +365,7 @@ nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ 
 }
 
 int dispatch_nnls(float *x, int64_t ld_x, int x_layout, int64_t n_px, int E, const double *g, const double *h, int *n_fixed,
-                  const int *list, const int *list_count, const MtPeers *peers_host, cudaStream_t stream) {
+                  const int *list, const int *list_count, int list_min, const MtPeers *peers_host, cudaStream_t stream) {
     MtPeers peers{};
     if (peers_host) {
         MT_REQUIRE(peers_host->n_peers >= 0 && peers_host->n_peers <= MT_MAX_PEERS, "non-negative solve: n_peers=%d",
@@ -370,10 +376,10 @@ int dispatch_nnls(float *x, int64_t ld_x, int x_layout, int64_t n_px, int E, con
                    (x_layout == MT_X_PIXEL_MAJOR && ld_x >= ((E + 3) & ~3) && ld_x % 4 == 0 && ((uintptr_t)x & 15) == 0),
                "non-negative solve: x_layout=%d ld_x=%lld", x_layout, (long long)ld_x);
     const int pixel_major = x_layout == MT_X_PIXEL_MAJOR;
-    if (E <= 16) return launch_nnls<16>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 32) return launch_nnls<32>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 64) return launch_nnls<64>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
-    if (E <= 104) return launch_nnls<104>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, peers, stream);
+    if (E <= 16) return launch_nnls<16>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, list_min, peers, stream);
+    if (E <= 32) return launch_nnls<32>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, list_min, peers, stream);
+    if (E <= 64) return launch_nnls<64>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, list_min, peers, stream);
+    if (E <= 104) return launch_nnls<104>(x, ld_x, pixel_major, n_px, E, g, h, n_fixed, list, list_count, list_min, peers, stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "non-negative solve: n_comp=%d > 104", E);
 }
 
@@ -400,7 +406,7 @@ extern "C" int mt_nnls_fixup(float *x_dev, int64_t ld_x, int32_t x_layout, int64
     MT_REQUIRE(n_px >= 0 && n_comp >= 1 && (x_layout == MT_X_PIXEL_MAJOR || ld_x >= n_px), "mt_nnls_fixup: bad sizes");
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    return dispatch_nnls(x_dev, ld_x, x_layout, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, nullptr, nullptr, peers_host,
+    return dispatch_nnls(x_dev, ld_x, x_layout, n_px, n_comp, g_dev, hinv_dev, n_fixed_dev, nullptr, nullptr, -1, peers_host,
                          stream);
 }
 
@@ -419,9 +425,11 @@ extern "C" int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const 
         nnls_warp_kernel<<<mt::num_sms() * 8, kListWarps * 32, smem, stream>>>(x_dev, ld_x, list_dev, count_dev, n_comp,
                                                                              hinv_dev, peers);
         MT_CUDA_TRY(cudaGetLastError());
-        return MT_OK;
+        // long lists: the thread-per-pixel kernel takes over (returns immediately for short ones)
+        return dispatch_nnls(x_dev, ld_x, x_layout, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, kShortListMax,
+                             peers_host, stream);
     }
-    return dispatch_nnls(x_dev, ld_x, x_layout, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, peers_host,
+    return dispatch_nnls(x_dev, ld_x, x_layout, 0, n_comp, g_dev, hinv_dev, nullptr, list_dev, count_dev, -1, peers_host,
                          static_cast<cudaStream_t>(stream_));
 }
 

@@ -80,7 +80,7 @@ template <typename T, int KCH, bool SCALED>
 __global__ void __launch_bounds__(kSnipThreads, (KCH <= 4 ? 3 : (KCH <= 8 ? 2 : 1)))
 snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int ch0, int n_ch,
             const uint32_t *__restrict__ lohi, int ld_tab, int n_pass, int boxcar, float *__restrict__ out,
-            long long ld_out, int out_mode) {
+            long long ld_out, int out_mode, int *__restrict__ overflow) {
     extern __shared__ float4 sb[];  // [n_ch] x (4 pixels)
     const int tid = threadIdx.x;
     const long long px0 = (long long)blockIdx.x * kSnipPix;
@@ -212,7 +212,16 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
             if (px >= n_px) continue;
             float *orow = out + px * ld_out;
             const float bkg = finite_or_zero(exp_m1(vals[p]));
-            if (out_mode == MT_SNIP_BACKGROUND) {
+            if (out_mode == MT_SNIP_RESIDUAL_HILO_F16) {
+                // two fp16 planes (4 bytes per channel instead of 8): hi = r rounded to fp16, lo = the remainder; the
+                // contraction then runs on the fp16 tensor-core path.  |r| beyond the fp16 range raises the flag.
+                __half *hrow = reinterpret_cast<__half *>(out) + px * ld_out;
+                const float r = __fsub_rn(y[p], bkg);
+                const __half hi = __float2half_rn(r);
+                hrow[i] = hi;
+                hrow[n_ch + i] = __float2half_rn(__fsub_rn(r, __half2float(hi)));
+                if (!(fabsf(r) <= 65504.f)) atomicOr(overflow, 1);
+            } else if (out_mode == MT_SNIP_BACKGROUND) {
                 orow[i] = bkg;
             } else {
                 const float r = __fsub_rn(y[p], bkg);
@@ -230,7 +239,7 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
 
 template <typename T, int KCH, bool SCALED>
 int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi, int ld_tab,
-                int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
+                int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, int *overflow, cudaStream_t stream) {
     auto kern = snip_kernel<T, KCH, SCALED>;
     const size_t smem = sizeof(float4) * (size_t)n_ch;
     static int smem_set[16] = {0};
@@ -242,7 +251,7 @@ int launch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_
     }
     const long long n_cta = (n_px + kSnipPix - 1) / kSnipPix;
     kern<<<(unsigned)n_cta, kSnipThreads, smem, stream>>>(static_cast<const T *>(spec), n_px, ld_spec, ch0, n_ch, lohi,
-                                                          ld_tab, n_pass, boxcar, out, ld_out, out_mode);
+                                                          ld_tab, n_pass, boxcar, out, ld_out, out_mode, overflow);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
@@ -256,14 +265,15 @@ int scaled_pitch(int n_ch) {
 
 template <typename T>
 int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi, int ld_tab,
-                  bool scaled, int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, cudaStream_t stream) {
+                  bool scaled, int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, int *overflow,
+                  cudaStream_t stream) {
 #define MT_SNIP_CASE(K)                                                                                             \
     if (n_ch <= kSnipThreads * K) {                                                                                 \
         if (scaled)                                                                                                 \
             return launch_snip<T, K, true>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, \
-                                           out_mode, stream);                                                       \
+                                           out_mode, overflow, stream);                                             \
         return launch_snip<T, K, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out,   \
-                                        out_mode, stream);                                                          \
+                                        out_mode, overflow, stream);                                                \
     }
     MT_SNIP_CASE(2)
     MT_SNIP_CASE(4)
@@ -271,7 +281,7 @@ int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int 
 #undef MT_SNIP_CASE
     if (n_ch <= kSnipThreads * 16 && !scaled)
         return launch_snip<T, 16, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, out_mode,
-                                         stream);
+                                         overflow, stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: n_ch=%d exceeds the on-chip limit of %d channels", n_ch,
                     kSnipThreads * (scaled ? 8 : 16));
 }
@@ -290,7 +300,7 @@ __global__ void snip_scale_tables_kernel(const uint32_t *__restrict__ lohi, int 
 
 int snip_common(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0, int32_t n_ch,
                 const uint32_t *tab_dev, int ld_tab, bool scaled, int32_t n_pass, int32_t boxcar, float *out_dev,
-                int64_t ld_out, int32_t out_mode, void *stream_) {
+                int64_t ld_out, int32_t out_mode, int *overflow, void *stream_) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(spec_dev && tab_dev && out_dev, "mt_snip: null pointer");
     MT_REQUIRE(n_px >= 0 && n_ch > 0 && ch0 >= 0 && ld_spec >= (int64_t)ch0 + n_ch,
@@ -298,19 +308,20 @@ int snip_common(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_sp
                (long long)ld_spec);
     MT_REQUIRE(n_pass >= 0, "mt_snip: n_pass=%d", n_pass);
     MT_REQUIRE(boxcar >= 1 && (boxcar & 1), "mt_snip: boxcar must be odd (got %d)", boxcar);
-    MT_REQUIRE(out_mode >= MT_SNIP_BACKGROUND && out_mode <= MT_SNIP_RESIDUAL_HILO, "mt_snip: out_mode=%d",
+    MT_REQUIRE(out_mode >= MT_SNIP_BACKGROUND && out_mode <= MT_SNIP_RESIDUAL_HILO_F16, "mt_snip: out_mode=%d",
                out_mode);
-    MT_REQUIRE(ld_out >= (out_mode == MT_SNIP_RESIDUAL_HILO ? 2 : 1) * (int64_t)n_ch,
+    MT_REQUIRE(out_mode != MT_SNIP_RESIDUAL_HILO_F16 || overflow, "mt_snip: fp16 planes need an overflow flag");
+    MT_REQUIRE(ld_out >= (out_mode >= MT_SNIP_RESIDUAL_HILO ? 2 : 1) * (int64_t)n_ch,
                "mt_snip: ld_out=%lld too small", (long long)ld_out);
     MT_REQUIRE(n_ch <= 65535, "mt_snip: n_ch=%d does not fit the 16-bit gather indices", n_ch);
     if (n_px == 0) return MT_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (dtype == MT_DTYPE_F32)
         return dispatch_snip<float>(spec_dev, n_px, ld_spec, ch0, n_ch, tab_dev, ld_tab, scaled, n_pass, boxcar, out_dev,
-                                    ld_out, out_mode, stream);
+                                    ld_out, out_mode, overflow, stream);
     if (dtype == MT_DTYPE_F16)
         return dispatch_snip<__half>(spec_dev, n_px, ld_spec, ch0, n_ch, tab_dev, ld_tab, scaled, n_pass, boxcar, out_dev,
-                                     ld_out, out_mode, stream);
+                                     ld_out, out_mode, overflow, stream);
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: dtype %d", dtype);
 }
 
@@ -319,8 +330,9 @@ int snip_common(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_sp
 extern "C" int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
                        int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar,
                        float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {
+    MT_REQUIRE(out_mode != MT_SNIP_RESIDUAL_HILO_F16, "mt_snip: fp16 planes are written by mt_snip_residual_f16");
     return snip_common(spec_dev, dtype, n_px, ld_spec, ch0, n_ch, lohi_dev, n_ch, false, n_pass, boxcar, out_dev, ld_out,
-                       out_mode, stream_);
+                       out_mode, nullptr, stream_);
 }
 
 extern "C" int mt_snip_scaled_pitch(int32_t n_ch) { return scaled_pitch(n_ch); }
@@ -345,6 +357,17 @@ extern "C" int mt_snip_scaled(const void *spec_dev, int32_t dtype, int64_t n_px,
                               float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {
     MT_REQUIRE(scaled_pitch(n_ch) > 0 && ld_scaled == scaled_pitch(n_ch), "mt_snip_scaled: table pitch %d for n_ch=%d",
                ld_scaled, n_ch);
+    MT_REQUIRE(out_mode != MT_SNIP_RESIDUAL_HILO_F16, "mt_snip_scaled: fp16 planes are written by mt_snip_residual_f16");
     return snip_common(spec_dev, dtype, n_px, ld_spec, ch0, n_ch, scaled_dev, ld_scaled, true, n_pass, boxcar, out_dev,
-                       ld_out, out_mode, stream_);
+                       ld_out, out_mode, nullptr, stream_);
+}
+
+extern "C" int mt_snip_residual_f16(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
+                                    int32_t n_ch, const uint32_t *tab_dev, int32_t ld_tab, int32_t scaled, int32_t n_pass,
+                                    int32_t boxcar, void *out_half_dev, int64_t ld_out, int32_t *overflow_dev, void *stream_) {
+    if (scaled)
+        MT_REQUIRE(scaled_pitch(n_ch) > 0 && ld_tab == scaled_pitch(n_ch), "mt_snip_residual_f16: table pitch %d for n_ch=%d",
+                   ld_tab, n_ch);
+    return snip_common(spec_dev, dtype, n_px, ld_spec, ch0, n_ch, tab_dev, scaled ? ld_tab : n_ch, scaled != 0, n_pass, boxcar,
+                       static_cast<float *>(out_half_dev), ld_out, MT_SNIP_RESIDUAL_HILO_F16, overflow_dev, stream_);
 }

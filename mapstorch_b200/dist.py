@@ -345,8 +345,11 @@ class ShardedMapFit:
         self._trailing_wait()
         torch.cuda.synchronize()
         kw = dict(fit_kw)
-        if shard2d.dtype == torch.float32 and not plan.use_snip and "exact_counts" not in kw:
-            kw["exact_counts"] = "split" if plan._last_wide else True  # no host sync inside the capture
+        if shard2d.dtype == torch.float32 and "exact_counts" not in kw:  # no host sync inside the capture
+            if plan.use_snip:
+                kw["exact_counts"] = True if plan._last_snip_half else "split"
+            else:
+                kw["exact_counts"] = "split" if plan._last_wide else True
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             plan.fit(shard2d, out=pm.local, peers=pm.peers, **kw)

@@ -162,6 +162,8 @@ class MapFitPlan:
         self._neg = None
         self._last_engine = None
         self._last_wide = False
+        self._last_snip_half = False
+        self.snip_planes = "f16"  # residual operand planes of the SNIP path: "f16" (4 B per channel) or "tf32" (8 B)
         self._side = None
         self.pipeline = False
         self.epilogue_fixup = True  # K3 epilogue fixes pixels whose zero set has <= 2 components itself
@@ -290,7 +292,7 @@ class MapFitPlan:
                      self.chan_mask.data_ptr() if self.chan_mask is not None else None, coef.data_ptr(),
                      *self._x_args(x), self.n_live, _native.stream_ptr(stream))
 
-    def _fit_serial(self, spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers, coef=None):
+    def _fit_serial(self, spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers, coef=None, snip_overflow=None):
         n_px = spec2d.shape[0]
         # the tensor-core epilogue compacts the pixels that need the non-negative fix-up
         neg = None
@@ -327,20 +329,45 @@ class MapFitPlan:
         else:
             lohi, n_pass = self._snip
             hilo = engine == "tensor"
+            # tensor-core path: the residual crosses HBM as two fp16 planes (4 bytes per channel), unless it does not
+            # fit fp16 (|y - bkg| > 65504: the kernel raises a flag) -- then as a tf32-exact high part + fp32 remainder
+            half = hilo and self.snip_planes == "f16" and exact_counts != "split"
             width = 2 * self.n_ch if hilo else self.n_ch
             chunk = min(SNIP_CHUNK_PX, n_px)
-            pitch = -(-width // 4) * 4  # 16-byte row pitch so that TMA can address the scratch rows
-            scratch = torch.empty((chunk, pitch), dtype=torch.float32, device="cuda")[:, :width]
-            mode = _native.MT_SNIP_RESIDUAL_HILO if hilo else _native.MT_SNIP_RESIDUAL
-            for p0 in range(0, n_px, chunk):
-                n = min(chunk, n_px - p0)
-                self._timed("snip", n, stream,
-                            lambda: _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass,
-                                                     self.boxcar_size, scratch[:n], mode, stream))
-                self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
-                               _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
-                if coef is not None:
-                    self._shift(scratch[:n], 0, 2 if hilo else 1, self._x_chunk(x, p0, n), coef, stream)
+            starts = list(range(0, n_px, chunk))
+            flags = None
+            if half:
+                flags = snip_overflow if snip_overflow is not None else torch.zeros(1, dtype=torch.int32, device="cuda")
+            self._last_snip_half = half
+
+            def run_chunks(which, as_half):
+                es_pitch = 8 if as_half else 4  # 16-byte row pitch so that TMA can address the scratch rows
+                pitch = -(-width // es_pitch) * es_pitch
+                scratch = torch.empty((chunk, pitch), dtype=torch.float16 if as_half else torch.float32, device="cuda")[:, :width]
+                mode = _native.MT_SNIP_RESIDUAL_HILO if hilo else _native.MT_SNIP_RESIDUAL
+                for p0 in which:
+                    n = min(chunk, n_px - p0)
+                    if as_half:
+                        self._timed("snip", n, stream,
+                                    lambda: _bkg.snip_residual_f16(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass,
+                                                                   self.boxcar_size, scratch[:n], flags, stream))
+                    else:
+                        self._timed("snip", n, stream,
+                                    lambda: _bkg.snip_launch(spec2d[p0: p0 + n], self.er[0], self.n_ch, lohi, n_pass,
+                                                             self.boxcar_size, scratch[:n], mode, stream))
+                    self._contract(scratch[:n], self._x_chunk(x, p0, n), 0, 2 if hilo else 1, 0, width, engine, stream, neg, p0,
+                                   _shift_peers(peers, p0, x.stride(0) if self._pixel_major else 1))
+                    if coef is not None:
+                        self._shift(scratch[:n], 0, 2 if hilo else 1, self._x_chunk(x, p0, n), coef, stream)
+
+            run_chunks(starts, half)
+            # fp16 volumes cannot overflow; exact_counts=True (graph replays, streamed slabs) defers the test to the caller
+            if half and snip_overflow is None and spec2d.dtype != torch.float16 and exact_counts is not True:
+                if bool(flags.item()):
+                    if neg is not None:
+                        neg[1].zero_()
+                    self._last_snip_half = False
+                    run_chunks(starts, False)
         if nonneg and n_px:
             if self._last_engine == "tensor" and neg is not None:
                 _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
@@ -388,7 +415,7 @@ class MapFitPlan:
             n_fixed.copy_(counts.sum().reshape(1))
 
     def fit(self, spec2d, out=None, nonneg=True, engine="tensor", stream=None, n_fixed=None, exact_counts=None,
-            peers=None, layout="ep", l1_lambda=0.0):
+            peers=None, layout="ep", l1_lambda=0.0, snip_overflow=None):
         """spec2d: CUDA [P, C_full] fp32/fp16 with contiguous rows.  Returns x [E, P] fp32 (CUDA),
         rows in `self.names` order (components without an open line stay 0).
 
@@ -407,6 +434,11 @@ class MapFitPlan:
         layout: "ep" (default) returns x [E, P], one contiguous map per component; "pe" returns
         x [P, e_pad], one 16-byte aligned record per pixel (columns >= E are zero) -- the layout
         whose stores are 128-bit wide, used for the peer-memory gather.
+
+        snip_overflow: optional int32 [1] device flag.  On the SNIP path the residual is handed to the contraction as
+        two fp16 planes; a residual beyond the fp16 range (> 65504 counts) raises the flag.  Without this argument
+        fit() reads the flag itself (one host sync per call for fp32 volumes) and repeats the fit with tf32 planes;
+        with it the caller does (fit_host does so once per volume); exact_counts="split" forces tf32 planes.
 
         l1_lambda > 0 adds the reference's amplitude-sparsity penalty (opt.py:372-396) to the MSE objective:
         the unconstrained amplitudes are shifted per pixel (mt_penalty_shift, one more read of the spectra)
@@ -441,7 +473,7 @@ class MapFitPlan:
             self._fit_pipelined(spec2d, x, n_fixed, peers)
         else:
             self._fit_serial(spec2d, x, nonneg, engine, stream, n_fixed, exact_counts, peers,
-                             self._penalty_coef(l1_lambda) if l1_lambda > 0 else None)
+                             self._penalty_coef(l1_lambda) if l1_lambda > 0 else None, snip_overflow)
         if not dense:
             out.zero_()  # components without an open line (caller-provided buffers included)
             out[torch.as_tensor(self.live, device="cuda")] = x
@@ -467,8 +499,10 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
     # every slab is fitted optimistically, its maximum lands in a device flag, and the (rare) slabs that turn
     # out to hold larger counts are redone through the exact split path after ONE synchronisation at the end
     check = host2d.dtype == torch.float32 and not self.use_snip and engine == "tensor"
+    # SNIP path, fp32 volumes: the fp16 residual planes overflow beyond 65504 counts; same deferred treatment
+    snip_check = host2d.dtype == torch.float32 and self.use_snip and engine == "tensor" and self.snip_planes == "f16"
     starts = list(range(0, n_px, chunk))
-    too_big = torch.zeros(len(starts), dtype=torch.int32, device="cuda") if check else None
+    too_big = torch.zeros(len(starts), dtype=torch.int32, device="cuda") if (check or snip_check) else None
     for i, p0 in enumerate(starts):
         b, n = i & 1, min(chunk, n_px - p0)
         with torch.cuda.stream(copier):
@@ -480,11 +514,12 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
         if check:
             self._operand_inexact(bufs[b][:n], too_big[i: i + 1])
         self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
-                 exact_counts=True if check else None, l1_lambda=l1_lambda)
+                 exact_counts=True if check else None, l1_lambda=l1_lambda,
+                 snip_overflow=too_big[i: i + 1] if snip_check else None)
         if after_slab is not None:
             after_slab(bufs[b][:n], p0, n, out[:, p0: p0 + n])
         consumed[b].record(compute)
-    if check:
+    if check or snip_check:
         for i in torch.nonzero(too_big).flatten().tolist():
             p0 = starts[i]
             n = min(chunk, n_px - p0)
@@ -504,7 +539,8 @@ def _make_graph(self, spec2d, out, nonneg=True, engine="tensor"):
     torch.cuda.CUDAGraph; call .replay()."""
     saved, self.timers = self.timers, None
     self.fit(spec2d, out=out, nonneg=nonneg, engine=engine)  # warm caches; checks the count range once
-    exact = "split" if self._last_wide else True             # no host sync inside the capture
+    # no host sync inside the capture: the warm run above has settled which operand form the volume needs
+    exact = "split" if (self._last_wide or (self.use_snip and engine == "tensor" and not self._last_snip_half)) else True
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
