@@ -242,22 +242,40 @@ int mt_peer_wait(const MtPeerSync *sync_host, const uint32_t *epoch_dev, int32_t
 
 /* ---- K4: batched per-pixel nonlinear refinement (BASELINE config 4) ----------------------------
  * Replaces fit_spec(..., fitting_params=[...], tune_params=True) (opt.py:165-327) applied per pixel:
- * every pixel refines up to four peak-shape parameters together with all amplitudes by a damped
+ * every pixel refines up to four calibration parameters together with all amplitudes by a damped
  * Gauss-Newton iteration with analytic Jacobians on sum_c (model_c + bkg_c - y_c)^2.
- * Model terms: Gaussian lines  x[comp] * factor * slope / (sigma sqrt(2 pi)) * exp(-(ev_c - energy)^2 / (2 sigma^2)),
- * sigma = sigma_scale * sqrt((FWHM_OFFSET / 2.3548)^2 + e296 * FWHM_FANOPRIME)  (map.py:57-58, 165-168, 208). */
+ * Model terms = model_spec's path (map.py:260-309: use_step=True, use_tail=False), per line
+ *   Gaussian  x[comp] * factor * slope / (sg sqrt(2 pi)) * exp(-(ev_c - energy)^2 / (2 sg^2))          (map.py:57-58, 208)
+ *   step      x[comp] * factor * step * slope / (2 energy) * erfc((ev_c - energy) / (sqrt(2) sb))     (map.py:61-62, 209-214)
+ * with sb = sqrt((FWHM_OFFSET / 2.3548)^2 + energy * 2.96 * FWHM_FANOPRIME), sg = sigma_scale * sb, and the energy of
+ * the two scatter lines following COHERENT_SCT_ENERGY / COMPTON_ANGLE (map.py:72-124).  The free parameters are the
+ * eight calibration parameters with a non-zero gradient on that path (the tail fractions of default_fitting_params,
+ * default.py:51-64, do not enter model_spec: use_tail=False at map.py:290,302). */
 #define MT_THETA_ENERGY_OFFSET 0
 #define MT_THETA_ENERGY_SLOPE 1
 #define MT_THETA_FWHM_OFFSET 2
 #define MT_THETA_FWHM_FANOPRIME 3
-#define MT_MAX_THETA 4
+#define MT_THETA_ENERGY_QUADRATIC 4
+#define MT_THETA_COHERENT_SCT_ENERGY 5
+#define MT_THETA_COMPTON_ANGLE 6
+#define MT_THETA_COMPTON_FWHM_CORR 7
+#define MT_N_THETA_IDS 8
+#define MT_MAX_THETA 8        /* free parameters of mt_model_jacobian */
+#define MT_MAX_THETA_REFINE 4 /* free parameters per pixel in mt_refine */
+
+#define MT_LINE_ELEMENT 0
+#define MT_LINE_ELASTIC 1 /* energy = COHERENT_SCT_ENERGY */
+#define MT_LINE_COMPTON 2 /* energy = Compton energy of COHERENT_SCT_ENERGY at COMPTON_ANGLE; Gaussian width x COMPTON_FWHM_CORR */
 
 typedef struct MtRefineLine {
-    float energy;      /* keV */
-    float factor;      /* branching ratio / normalisation of the line (amplitude excluded) */
+    float energy;      /* keV at the global parameters (scatter lines follow the free parameters) */
+    float factor;      /* branching ratio / normalisation of the line (amplitude excluded): ratio / (1 + f_step) */
     int32_t comp;      /* component (row of x) the line belongs to */
     float sigma_scale; /* 1, or COMPTON_FWHM_CORR for the Compton Gaussian (map.py:105) */
     float e296;        /* energy * 2.96 as the reference rounds it (map.py:167) */
+    float step;        /* f_step of the line (map.py:169-172; COMPTON_F_STEP for the Compton line); 0 = no step term */
+    int32_t kind;      /* MT_LINE_* */
+    int32_t reserved;
 } MtRefineLine;
 
 typedef struct MtRefineConfig {
@@ -266,8 +284,16 @@ typedef struct MtRefineConfig {
     int32_t theta_id[MT_MAX_THETA]; /* MT_THETA_* of each free parameter */
     float theta0[MT_MAX_THETA], theta_lo[MT_MAX_THETA], theta_hi[MT_MAX_THETA];
     float energy_offset, energy_slope, energy_quad, fwhm_offset, fwhm_fanoprime; /* global values */
+    float coherent_sct_energy, compton_angle, compton_fwhm_corr;
     float tol;          /* stop when steps fall below tol (relative) */
 } MtRefineConfig;
+
+/* Model of one spectrum and its analytic derivatives w.r.t. the free parameters at theta0, amplitudes x_dev [n_comp]
+ * fixed -- what torch.autograd gives the reference for d model_spec / d param (opt.py:249-317), and the Jacobian of
+ * fit_spec(tune_params=True) here.  model_dev [n_ch], dtheta_dev [n_theta][ld] (ld >= n_ch), up to MT_MAX_THETA
+ * parameters.  lines_host / chan_lines_host as for mt_refine. */
+int mt_model_jacobian(const MtRefineConfig *cfg_host, const MtRefineLine *lines_host, const uint32_t *chan_lines_host,
+                      const float *x_dev, float *model_dev, float *dtheta_dev, int64_t ld, void *stream);
 
 /* lines_host sorted by energy; chan_lines_host[c] = lo | hi << 16 is the range of line indices that can
  * contribute at channel c; comp_start_host/comp_lines_host list each component's lines;

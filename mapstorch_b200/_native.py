@@ -32,18 +32,25 @@ class MtTerm(ctypes.Structure):
                 ("p3", ctypes.c_float), ("amp", ctypes.c_float)]
 
 
+MT_MAX_THETA, MT_MAX_THETA_REFINE = 8, 4
+MT_LINE_ELEMENT, MT_LINE_ELASTIC, MT_LINE_COMPTON = 0, 1, 2
+
+
 class MtRefineLine(ctypes.Structure):
     _fields_ = [("energy", ctypes.c_float), ("factor", ctypes.c_float), ("comp", ctypes.c_int32),
-                ("sigma_scale", ctypes.c_float), ("e296", ctypes.c_float)]
+                ("sigma_scale", ctypes.c_float), ("e296", ctypes.c_float), ("step", ctypes.c_float),
+                ("kind", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class MtRefineConfig(ctypes.Structure):
     _fields_ = [("n_ch", ctypes.c_int32), ("ch0", ctypes.c_int32), ("n_comp", ctypes.c_int32),
                 ("n_lines", ctypes.c_int32), ("n_theta", ctypes.c_int32), ("max_iter", ctypes.c_int32),
-                ("theta_id", ctypes.c_int32 * 4), ("theta0", ctypes.c_float * 4), ("theta_lo", ctypes.c_float * 4),
-                ("theta_hi", ctypes.c_float * 4), ("energy_offset", ctypes.c_float), ("energy_slope", ctypes.c_float),
+                ("theta_id", ctypes.c_int32 * MT_MAX_THETA), ("theta0", ctypes.c_float * MT_MAX_THETA),
+                ("theta_lo", ctypes.c_float * MT_MAX_THETA), ("theta_hi", ctypes.c_float * MT_MAX_THETA),
+                ("energy_offset", ctypes.c_float), ("energy_slope", ctypes.c_float),
                 ("energy_quad", ctypes.c_float), ("fwhm_offset", ctypes.c_float), ("fwhm_fanoprime", ctypes.c_float),
-                ("tol", ctypes.c_float)]
+                ("coherent_sct_energy", ctypes.c_float), ("compton_angle", ctypes.c_float),
+                ("compton_fwhm_corr", ctypes.c_float), ("tol", ctypes.c_float)]
 
 
 class MtPeers(ctypes.Structure):
@@ -55,7 +62,9 @@ class MtPeerSync(ctypes.Structure):
     _fields_ = [("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32), ("flags", ctypes.c_void_p * 8)]
 
 
-THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3}
+# the calibration parameters with a non-zero gradient on model_spec's path (include/mapstorch_b200.h MT_THETA_*)
+THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3, "ENERGY_QUADRATIC": 4,
+             "COHERENT_SCT_ENERGY": 5, "COMPTON_ANGLE": 6, "COMPTON_FWHM_CORR": 7}
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
@@ -81,6 +90,7 @@ SIGNATURES = {
     "mt_nnls_singular_count": [_vp, _i32],
     "mt_peer_signal": [_vp, _vp, _vp],
     "mt_peer_wait": [_vp, _vp, _i32, _vp, _vp],
+    "mt_model_jacobian": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
                   _vp, _vp],
 }
@@ -123,7 +133,7 @@ def check(status):
 # kernels launched per successful call of each entry point (bench.py reports the total)
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 2, "mt_refine": 1,
-                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_snip_residual_f16": 1,
+                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_model_jacobian": 1, "mt_snip_residual_f16": 1,
                     "mt_peer_wait": 1}
 launch_count = 0
 

@@ -17,8 +17,12 @@
 //                       are exact, so the step is a Schur complement on an n_theta x n_theta system
 //
 // The gradient is exact, only the amplitude curvature is frozen at the global parameters, so the
-// fixed point is the true minimiser.  Model terms are the Gaussian lines of model_spec's default
-// path (map.py:152-208 with f_step = 0, elastic, Compton Gaussian); exp dominates (MUFU bound).
+// fixed point is the true minimiser.  Model terms are those of model_spec's path (map.py:260-309): the
+// Gaussian of every line, elastic and Compton peaks, and -- GENERAL instantiations -- the step terms
+// (map.py:61-62, 209-214, 111-114) and the scatter lines whose energy / width follow COHERENT_SCT_ENERGY,
+// COMPTON_ANGLE and COMPTON_FWHM_CORR.  Tail terms never enter model_spec (use_tail=False, map.py:290,302).
+// exp dominates (MUFU bound).  mt_model_jacobian exposes the same evaluation for one spectrum (model and
+// d model / d theta): the analytic Jacobian of fit_spec(tune_params=True).
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
@@ -43,8 +47,8 @@ constexpr int kRefThreads = 128;  // 256 threads per pixel measured the same (70
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kMaxLines = 512;
 constexpr int kMaxComp = 64;
-constexpr int kMaxTheta = MT_MAX_THETA;
-constexpr int kRefDefaultMinBlocks = 6;  // measured on B200 (c4): 4 -> 77.0 ms, 5 -> 72.3, 6 -> 69.6, 7/8 -> 70.0
+constexpr int kMaxTheta = MT_MAX_THETA_REFINE;
+constexpr int kRefMinBlocks = 6;  // measured on B200 (c4): 4 -> 77.0 ms, 5 -> 72.3, 6 -> 69.6, 7/8 -> 70.0
 
 struct RefParams {
     MtRefineConfig cfg;
@@ -88,19 +92,186 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename T, int MINB, int NT>
-__global__ void __launch_bounds__(kRefThreads, MINB)
+// ---- calibration state and per-line constants ---------------------------------------------------------------
+struct Calib {
+    float off, slope, quad, fo, fa, e0, angle, corr;
+};
+
+__device__ __forceinline__ Calib calib_of(const MtRefineConfig &cfg, const float *theta, int n_theta) {
+    Calib c{cfg.energy_offset, cfg.energy_slope, cfg.energy_quad, cfg.fwhm_offset, cfg.fwhm_fanoprime,
+            cfg.coherent_sct_energy, cfg.compton_angle, cfg.compton_fwhm_corr};
+    for (int k = 0; k < n_theta; ++k) {
+        const float v = theta[k];
+        switch (cfg.theta_id[k]) {
+            case MT_THETA_ENERGY_OFFSET: c.off = v; break;
+            case MT_THETA_ENERGY_SLOPE: c.slope = v; break;
+            case MT_THETA_FWHM_OFFSET: c.fo = v; break;
+            case MT_THETA_FWHM_FANOPRIME: c.fa = v; break;
+            case MT_THETA_ENERGY_QUADRATIC: c.quad = v; break;
+            case MT_THETA_COHERENT_SCT_ENERGY: c.e0 = v; break;
+            case MT_THETA_COMPTON_ANGLE: c.angle = v; break;
+            case MT_THETA_COMPTON_FWHM_CORR: c.corr = v; break;
+        }
+    }
+    return c;
+}
+
+// Phase A for one line.  Shared-memory records (one 128-bit load each in the inner loops):
+//   lc0 = {energy, a = -log2(e) / (2 sg^2), amplitude * unit, window (first | last+1 << 16)}
+//   lc1 = {1 / sg^2, (d sg / d FWHM_OFFSET) / sg, (d sg / d FWHM_FANOPRIME) / sg, unit}
+// GENERAL only:
+//   lc2 = {amplitude * K, -log2(e) / (2 sb^2), 1 / (sqrt(2) sb), amplitude * K * 2 / sqrt(pi) / (sqrt(2) sb)}   (step term)
+//   lc3 = {K, 1 / energy, 0, 0}
+//   lck[k * L + l] = {(d sg / d theta_k) / sg, d energy / d theta_k, (d sb / d theta_k) / sb, 0}  (0 for the axis parameters)
+// with unit = factor * slope / (sg sqrt(2 pi)), K = factor * step * slope / (2 energy), sb the line width, sg = scale * sb.
+template <int NT, bool GENERAL>
+__device__ __forceinline__ void line_constants(const MtRefineConfig &cfg, const Calib &c, const MtRefineLine &ln, float amp,
+                                               uint32_t window, int l, int L, float4 *lc0, float4 *lc1, float4 *lc2,
+                                               float4 *lc3, float4 *lck) {
+    const float s0 = c.fo / 2.3548f;
+    float energy = ln.energy, e296 = ln.e296, scale = ln.sigma_scale, de_e0 = 0.f, de_ang = 0.f;
+    if (GENERAL && ln.kind != MT_LINE_ELEMENT) {
+        if (ln.kind == MT_LINE_ELASTIC) {
+            energy = c.e0;
+            de_e0 = 1.f;
+        } else {
+            const float rad = c.angle * 0.017453292519943295f;
+            const float aa = (c.e0 / 511.f) * (1.f - cosf(rad));
+            const float inv = 1.f / (1.f + aa);
+            energy = c.e0 * inv;
+            de_e0 = inv * inv;
+            de_ang = -c.e0 * inv * inv * (c.e0 / 511.f) * sinf(rad) * 0.017453292519943295f;
+            scale = c.corr;
+        }
+        e296 = energy * 2.96f;
+    }
+    const float sb = sqrtf(fmaxf(s0 * s0 + e296 * c.fa, 1e-12f));
+    const float sg = sb * scale;
+    const float unit = ln.factor * c.slope / (sg * 2.5066282746310002f);
+    const float is = 1.f / sg, is2 = is * is, isb2 = 1.f / (sb * sb);
+    const float c_fo = s0 * isb2 / 2.3548f;   // (d sb / d FWHM_OFFSET) / sb  (= the same for sg)
+    const float c_fa = e296 * isb2 * 0.5f;    // (d sb / d FWHM_FANOPRIME) / sb
+    lc0[l] = make_float4(energy, -0.72134752044448170f * is2, unit * amp, __uint_as_float(window));
+    lc1[l] = make_float4(is2, c_fo, c_fa, unit);
+    if (GENERAL) {
+        const float K = ln.step > 0.f ? ln.factor * ln.step * c.slope / (2.f * energy) : 0.f;
+        const float zs = 0.70710678118654752f / sb;
+        lc2[l] = make_float4(amp * K, -0.72134752044448170f * isb2, zs, amp * K * 1.1283791670955126f * zs);
+        lc3[l] = make_float4(K, 1.f / energy, 0.f, 0.f);
+        const float c_e = 1.48f * c.fa * isb2;  // (d sb / d energy) / sb
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            float csb = 0.f, csg = 0.f, ce = 0.f;
+            switch (cfg.theta_id[k]) {
+                case MT_THETA_FWHM_OFFSET: csb = csg = c_fo; break;
+                case MT_THETA_FWHM_FANOPRIME: csb = csg = c_fa; break;
+                case MT_THETA_COHERENT_SCT_ENERGY: ce = de_e0; csb = csg = c_e * de_e0; break;
+                case MT_THETA_COMPTON_ANGLE: ce = de_ang; csb = csg = c_e * de_ang; break;
+                case MT_THETA_COMPTON_FWHM_CORR: csg = ln.kind == MT_LINE_COMPTON ? 1.f / c.corr : 0.f; break;
+                default: break;  // axis parameters: handled after the line loop
+            }
+            lck[k * L + l] = make_float4(csg, ce, csb, 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ void erfc2(f32x2 z, float &lo, float &hi) {
+    float a, b;
+    unpack2(z, a, b);
+    lo = erfcf(a);
+    hi = erfcf(b);
+}
+
+// Model and theta derivatives of ONE PAIR of adjacent channels over the lines [l_begin, l_end): packed fp32 arithmetic
+// (FADD2 / FMUL2 / FFMA2: two channels per issue slot, the per-line constants enter as broadcast operands).
+// chan_lines ranges are unions of line windows, so a few (line, channel) pairs outside the line's own window are
+// evaluated too -- they are < e^-15 of the peak.
+template <int NT, bool GENERAL>
+__device__ __forceinline__ void eval_pair(const int (&id_k)[NT > 0 ? NT : 1], const Calib &c, f32x2 cg, int l_begin, int l_end,
+                                          int L, const float4 *lc0, const float4 *lc1, const float4 *lc2, const float4 *lck,
+                                          f32x2 &m_out, f32x2 (&d)[NT > 0 ? NT : 1]) {
+    const f32x2 ev = fma2(fma2(bcast2(c.quad), cg, bcast2(c.slope)), cg, bcast2(c.off));
+    const f32x2 minus_one2 = bcast2(-1.f);
+    f32x2 m = 0ull, d_ev = 0ull;
+    if (!GENERAL) {
+        f32x2 d_fo = 0ull, d_fa = 0ull;
+        for (int l = l_begin; l < l_end; ++l) {
+            const float4 a0 = lc0[l];
+            const float4 a1 = lc1[l];
+            const f32x2 dl = add2(ev, bcast2(-a0.x)), dl2 = mul2(dl, dl);
+            float e0, e1;
+            unpack2(mul2(dl2, bcast2(a0.y)), e0, e1);
+            const f32x2 v = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), bcast2(a0.z));  // amplitude * unit * exp(-u^2/2)
+            m = add2(m, v);
+            d_ev = fma2(mul2(v, dl), bcast2(-a1.x), d_ev);                 // -v u / sigma
+            const f32x2 w = mul2(v, fma2(dl2, bcast2(a1.x), minus_one2));  // v (u^2 - 1); 1 / sigma sits in a1.y, a1.z
+            d_fo = fma2(w, bcast2(a1.y), d_fo);
+            d_fa = fma2(w, bcast2(a1.z), d_fa);
+        }
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+            d[k] = id_k[k] == MT_THETA_FWHM_OFFSET ? d_fo : id_k[k] == MT_THETA_FWHM_FANOPRIME ? d_fa : 0ull;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NT; ++k) d[k] = 0ull;
+        for (int l = l_begin; l < l_end; ++l) {
+            const float4 a0 = lc0[l];
+            const float4 a1 = lc1[l];
+            const f32x2 dl = add2(ev, bcast2(-a0.x)), dl2 = mul2(dl, dl);
+            float e0, e1;
+            unpack2(mul2(dl2, bcast2(a0.y)), e0, e1);
+            const f32x2 v = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), bcast2(a0.z));
+            m = add2(m, v);
+            const f32x2 t1 = mul2(mul2(v, dl), bcast2(a1.x));              // -d v / d ev = d v / d energy
+            d_ev = add2(d_ev, mul2(t1, minus_one2));
+            const f32x2 t2 = mul2(v, fma2(dl2, bcast2(a1.x), minus_one2));  // sg * d v / d sg
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float4 ck = lck[k * L + l];
+                d[k] = fma2(t2, bcast2(ck.x), fma2(t1, bcast2(ck.y), d[k]));
+            }
+            const float4 a2 = lc2[l];
+            if (a2.x != 0.f) {
+                // step term: s = A K erfc(z), z = dl / (sqrt(2) sb);  -d s / d ev = q = A K 2/sqrt(pi) exp(-z^2) / (sqrt(2) sb)
+                float r0, r1, g0, g1;
+                erfc2(mul2(dl, bcast2(a2.z)), r0, r1);
+                unpack2(mul2(dl2, bcast2(a2.y)), g0, g1);
+                const f32x2 sv = mul2(pack2(r0, r1), bcast2(a2.x));
+                const f32x2 q = mul2(pack2(ex2_approx(g0), ex2_approx(g1)), bcast2(a2.w));
+                m = add2(m, sv);
+                d_ev = add2(d_ev, mul2(q, minus_one2));
+                const f32x2 qdl = mul2(q, dl);
+                const f32x2 qe = fma2(sv, bcast2(-1.f / a0.x), q);  // d s / d energy = q - s / energy
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const float4 ck = lck[k * L + l];
+                    d[k] = fma2(qdl, bcast2(ck.z), fma2(qe, bcast2(ck.y), d[k]));
+                }
+            }
+        }
+    }
+    // the energy-axis parameters act through ev alone (+ the gain factor of ENERGY_SLOPE, map.py:57-62)
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        if (id_k[k] == MT_THETA_ENERGY_OFFSET) d[k] = d_ev;
+        if (id_k[k] == MT_THETA_ENERGY_SLOPE) d[k] = fma2(d_ev, cg, mul2(m, bcast2(1.f / c.slope)));
+        if (id_k[k] == MT_THETA_ENERGY_QUADRATIC) d[k] = mul2(mul2(d_ev, cg), cg);
+    }
+    m_out = m;
+}
+
+template <typename T, int NT, bool GENERAL>
+__global__ void __launch_bounds__(kRefThreads, GENERAL ? 4 : kRefMinBlocks)
 refine_kernel(const RefParams p) {
-    extern __shared__ float4 dyn4[];  // lc0[L], lc1[L], then r[n_ch], d[n_theta][n_ch]
+    extern __shared__ float4 dyn4[];  // lc0[L], lc1[L], (GENERAL: lc2[L], lc3[L], lck[NT][L]), then r[n_ch], d[n_theta][n_ch]
     const MtRefineConfig &cfg = p.cfg;
     const int n_ch = cfg.n_ch, E = cfg.n_comp, L = cfg.n_lines;  // NT (free parameters) is a template argument
-    // per-line constants, packed so that one 128-bit load feeds the inner loops:
-    //   lc0 = {energy, a = -log2(e) / (2 sigma^2), amplitude * unit, window (first | last+1 << 16)}
-    //   lc1 = {1 / sigma^2, dsigma/dFWHM_OFFSET / sigma, dsigma/dFWHM_FANOPRIME / sigma, unit}
     float4 *lc0 = dyn4;
     float4 *lc1 = dyn4 + L;
+    float4 *lc2 = dyn4 + 2 * L, *lc3 = dyn4 + 3 * L, *lck = dyn4 + 4 * L;
+    const int n_rec = GENERAL ? (4 + NT) * L : 2 * L;
     const int ld = (n_ch + 1) & ~1;  // even pitch: channel pairs are read and written with 64-bit accesses
-    float *r_s = reinterpret_cast<float *>(dyn4 + 2 * L);
+    float *r_s = reinterpret_cast<float *>(dyn4 + n_rec);
     float *d_s = r_s + ld;  // d_s[k] = r_s + (k + 1) * ld
     __shared__ float xs[kMaxComp], x_prev[kMaxComp], dx[kMaxComp], gx[kMaxComp], w_s[kMaxComp];
     __shared__ float hthx[kMaxTheta][kMaxComp], t1[kMaxComp][kMaxTheta];
@@ -132,35 +303,16 @@ refine_kernel(const RefParams p) {
     int iter = 0;
     for (;; ++iter) {
         // ---- current calibration ------------------------------------------------------------
-        float off = cfg.energy_offset, slope = cfg.energy_slope, fo = cfg.fwhm_offset, fa = cfg.fwhm_fanoprime;
-        for (int k = 0; k < NT; ++k) {
-            const int id = cfg.theta_id[k];
-            if (id == MT_THETA_ENERGY_OFFSET) off = theta[k];
-            if (id == MT_THETA_ENERGY_SLOPE) slope = theta[k];
-            if (id == MT_THETA_FWHM_OFFSET) fo = theta[k];
-            if (id == MT_THETA_FWHM_FANOPRIME) fa = theta[k];
-        }
-        const float s0 = fo / 2.3548f;
+        const Calib cal = calib_of(cfg, theta, NT);
+        const float off = cal.off, slope = cal.slope;
         // ---- A: per-line shape constants ---------------------------------------------------
         for (int l = tid; l < L; l += kRefThreads) {
             const MtRefineLine ln = p.lines[l];
-            const float base = sqrtf(fmaxf(s0 * s0 + ln.e296 * fa, 1e-12f));
-            const float sigma = base * ln.sigma_scale;
-            const float unit = ln.factor * slope / (sigma * 2.5066282746310002f);
-            const float is = 1.f / sigma, is2 = is * is;
-            const float dfo = ln.sigma_scale * s0 / (2.3548f * base);   // d sigma / d FWHM_OFFSET
-            const float dfa = ln.sigma_scale * ln.e296 / (2.f * base);  // d sigma / d FWHM_FANOPRIME
-            lc0[l] = make_float4(ln.energy, -0.72134752044448170f * is2, unit * xs[ln.comp],
-                                 __uint_as_float(__ldg(p.line_window + l)));
-            lc1[l] = make_float4(is2, dfo * is, dfa * is, unit);
+            line_constants<NT, GENERAL>(cfg, cal, ln, xs[ln.comp], __ldg(p.line_window + l), l, L, lc0, lc1, lc2, lc3, lck);
         }
         __syncthreads();
 
         // ---- B1: channels -> model, theta derivatives, residual ---------------------------
-        // Every thread takes PAIRS of adjacent channels through packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2:
-        // two channels per issue slot, the per-line constants enter as broadcast operands); the line range of a
-        // pair is the union of its channels' ranges.  chan_lines ranges are unions of line windows, so a few
-        // (line, channel) pairs outside the line's own window are evaluated too -- they are < e^-15 of the peak.
         constexpr int kAcc = 1 + NT + NT * NT;  // loss, D^T r, D^T D
         f32x2 acc[kAcc > 0 ? kAcc : 1];
 #pragma unroll
@@ -168,38 +320,17 @@ refine_kernel(const RefParams p) {
         int id_k[NT > 0 ? NT : 1];
 #pragma unroll
         for (int k = 0; k < NT; ++k) id_k[k] = cfg.theta_id[k];
-        const f32x2 inv_slope2 = bcast2(1.f / slope), off2 = bcast2(off), slope2 = bcast2(slope),
-                    quad2 = bcast2(cfg.energy_quad), minus_one2 = bcast2(-1.f);
+        const f32x2 off2 = bcast2(off), slope2 = bcast2(slope), quad2 = bcast2(cal.quad);
         for (int q = tid; q < (ld >> 1); q += kRefThreads) {
             const int c0 = 2 * q;
             const bool has1 = c0 + 1 < n_ch;
             const float cg0 = (float)(cfg.ch0 + c0);
             const f32x2 cg = pack2(cg0, cg0 + 1.f);
-            const f32x2 ev = fma2(fma2(quad2, cg, slope2), cg, off2);
             const uint32_t ra = __ldg(p.chan_lines + c0), rb = has1 ? __ldg(p.chan_lines + c0 + 1) : ra;
             const int l_begin = min((int)(ra & 0xffffu), (int)(rb & 0xffffu));
             const int l_end = max((int)(ra >> 16), (int)(rb >> 16));
-            f32x2 m = 0ull, d_ev = 0ull, d_fo = 0ull, d_fa = 0ull;
-            for (int l = l_begin; l < l_end; ++l) {
-                const float4 a0 = lc0[l];
-                const float4 a1 = lc1[l];
-                const f32x2 dl = add2(ev, bcast2(-a0.x)), dl2 = mul2(dl, dl);
-                float e0, e1;
-                unpack2(mul2(dl2, bcast2(a0.y)), e0, e1);
-                const f32x2 v = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), bcast2(a0.z));  // amplitude * unit * exp(-u^2/2)
-                m = add2(m, v);
-                d_ev = fma2(mul2(v, dl), bcast2(-a1.x), d_ev);              // -v u / sigma
-                const f32x2 w = mul2(v, fma2(dl2, bcast2(a1.x), minus_one2));  // v (u^2 - 1); 1 / sigma sits in a1.y, a1.z
-                d_fo = fma2(w, bcast2(a1.y), d_fo);
-                d_fa = fma2(w, bcast2(a1.z), d_fa);
-            }
-            const f32x2 d_slope = fma2(d_ev, cg, mul2(m, inv_slope2));
-            f32x2 d[NT > 0 ? NT : 1];
-#pragma unroll
-            for (int k = 0; k < NT; ++k)
-                d[k] = id_k[k] == MT_THETA_ENERGY_OFFSET ? d_ev
-                       : id_k[k] == MT_THETA_ENERGY_SLOPE ? d_slope
-                       : id_k[k] == MT_THETA_FWHM_OFFSET ? d_fo : d_fa;
+            f32x2 m, d[NT > 0 ? NT : 1];
+            eval_pair<NT, GENERAL>(id_k, cal, cg, l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
             const float y0 = ld_spec<T>(row + c0) - (brow ? __ldg(brow + c0) : 0.f);
             const float y1 = has1 ? ld_spec<T>(row + c0 + 1) - (brow ? __ldg(brow + c0 + 1) : 0.f) : 0.f;
             f32x2 res = add2(m, pack2(-y0, -y1));
@@ -250,6 +381,11 @@ refine_kernel(const RefParams p) {
                 const float4 a0 = lc0[l];
                 const uint32_t win = __float_as_uint(a0.w);
                 const f32x2 unit2 = bcast2(lc1[l].w), ay2 = bcast2(a0.y), me2 = bcast2(-a0.x);
+                float kstep = 0.f, zs = 0.f;
+                if (GENERAL) {
+                    kstep = lc3[l].x;
+                    zs = lc2[l].z;
+                }
                 const int c_end = min(((int)(win >> 16) + 1) & ~1, ld);
                 int c = ((int)(win & 0xffffu) & ~1) + 2 * lane;
                 const float cg0 = (float)(cfg.ch0 + c);
@@ -259,7 +395,12 @@ refine_kernel(const RefParams p) {
                     const f32x2 dl = add2(fma2(fma2(quad2, cg, slope2), cg, off2), me2);
                     float e0, e1;
                     unpack2(mul2(mul2(dl, dl), ay2), e0, e1);
-                    const f32x2 b = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), unit2);
+                    f32x2 b = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), unit2);
+                    if (GENERAL && kstep != 0.f) {
+                        float r0, r1;
+                        erfc2(mul2(dl, bcast2(zs)), r0, r1);
+                        b = fma2(pack2(r0, r1), bcast2(kstep), b);
+                    }
                     g = fma2(b, *reinterpret_cast<const f32x2 *>(rp), g);
 #pragma unroll
                     for (int k = 0; k < NT; ++k) h[k] = fma2(b, *reinterpret_cast<const f32x2 *>(rp + (k + 1) * ld), h[k]);
@@ -444,6 +585,45 @@ refine_kernel(const RefParams p) {
     }
 }
 
+// ---- model and d model / d theta of one spectrum (the Jacobian of fit_spec(tune_params=True)) ---------------------
+template <int NT>
+__global__ void __launch_bounds__(kRefThreads)
+jacobian_kernel(const MtRefineConfig cfg, const MtRefineLine *__restrict__ lines, const uint32_t *__restrict__ chan_lines,
+                const float *__restrict__ x, float *__restrict__ model, float *__restrict__ dtheta, long long ld_out) {
+    extern __shared__ float4 dyn4[];
+    const int L = cfg.n_lines, n_ch = cfg.n_ch;
+    float4 *lc0 = dyn4, *lc1 = dyn4 + L, *lc2 = dyn4 + 2 * L, *lc3 = dyn4 + 3 * L, *lck = dyn4 + 4 * L;
+    const Calib cal = calib_of(cfg, cfg.theta0, NT);
+    for (int l = threadIdx.x; l < L; l += kRefThreads) {
+        const MtRefineLine ln = lines[l];
+        line_constants<NT, true>(cfg, cal, ln, fmaxf(__ldg(x + ln.comp), 0.f), 0u, l, L, lc0, lc1, lc2, lc3, lck);
+    }
+    __syncthreads();
+    int id_k[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) id_k[k] = cfg.theta_id[k];
+    const int q = blockIdx.x * kRefThreads + threadIdx.x;
+    const int c0 = 2 * q;
+    if (c0 >= n_ch) return;
+    const bool has1 = c0 + 1 < n_ch;
+    const float cg0 = (float)(cfg.ch0 + c0);
+    const uint32_t ra = __ldg(chan_lines + c0), rb = has1 ? __ldg(chan_lines + c0 + 1) : ra;
+    const int l_begin = min((int)(ra & 0xffffu), (int)(rb & 0xffffu));
+    const int l_end = max((int)(ra >> 16), (int)(rb >> 16));
+    f32x2 m, d[NT > 0 ? NT : 1];
+    eval_pair<NT, true>(id_k, cal, pack2(cg0, cg0 + 1.f), l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
+    float lo, hi;
+    unpack2(m, lo, hi);
+    model[c0] = lo;
+    if (has1) model[c0 + 1] = hi;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        unpack2(d[k], lo, hi);
+        dtheta[k * ld_out + c0] = lo;
+        if (has1) dtheta[k * ld_out + c0 + 1] = hi;
+    }
+}
+
 // ---- device-resident copies of the host tables, keyed by content -------------------------------------------
 struct TableEntry {
     int device = -1;
@@ -512,11 +692,16 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
                "mt_refine: channel window");
     MT_REQUIRE(cfg.n_comp >= 1 && cfg.n_comp <= kMaxComp, "mt_refine: n_comp=%d (max %d)", cfg.n_comp, kMaxComp);
     MT_REQUIRE(cfg.n_lines >= 1 && cfg.n_lines <= kMaxLines, "mt_refine: n_lines=%d (max %d)", cfg.n_lines, kMaxLines);
-    MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= kMaxTheta, "mt_refine: n_theta=%d", cfg.n_theta);
+    MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= kMaxTheta, "mt_refine: n_theta=%d (at most %d per pixel)", cfg.n_theta,
+               kMaxTheta);
     MT_REQUIRE(n_px >= 0 && ld_x >= n_px && (!bkg_dev || ld_bkg >= cfg.n_ch), "mt_refine: sizes");
     MT_REQUIRE(!theta_dev || cfg.n_theta == 0 || ld_theta >= n_px, "mt_refine: ld_theta=%lld < n_px", (long long)ld_theta);
     for (int l = 0; l < cfg.n_lines; ++l)
-        MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp, "mt_refine: line %d component", l);
+        MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp && lines_host[l].kind >= MT_LINE_ELEMENT &&
+                       lines_host[l].kind <= MT_LINE_COMPTON && lines_host[l].step >= 0.f,
+                   "mt_refine: line %d (component / kind / step)", l);
+    for (int k = 0; k < cfg.n_theta; ++k)
+        MT_REQUIRE(cfg.theta_id[k] >= 0 && cfg.theta_id[k] < MT_N_THETA_IDS, "mt_refine: theta_id[%d]=%d", k, cfg.theta_id[k]);
     {
         bool seen[kMaxComp] = {false};
         for (int e = 0; e < cfg.n_comp; ++e) {
@@ -575,33 +760,35 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.loss_out = loss_dev;
     p.iters_out = iters_dev;
     p.n_px = n_px;
+    // GENERAL instantiations carry the step terms and the scatter-line parameters; plain Gaussian line lists with
+    // axis / width parameters keep the lean kernel
+    bool general = false;
+    for (int k = 0; k < cfg.n_theta; ++k) general = general || cfg.theta_id[k] >= MT_THETA_COHERENT_SCT_ENERGY;
+    for (int l = 0; l < cfg.n_lines; ++l) general = general || lines_host[l].step > 0.f;
     const size_t smem = sizeof(float) * (size_t)((cfg.n_ch + 1) & ~1) * (1 + cfg.n_theta) +
-                        2 * sizeof(float4) * (size_t)cfg.n_lines;
+                        sizeof(float4) * (size_t)cfg.n_lines * (general ? 4 + cfg.n_theta : 2);
     if (smem > 200 * 1024)
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: %zu bytes of shared memory needed (channels x free parameters)",
                         smem);
-    // resident CTAs per SM the compiler must leave room for (register cap 65536 / (128 * MINB))
-    const char *env = getenv("MT_REFINE_MINB");
-    const int minb = env ? atoi(env) : kRefDefaultMinBlocks;
-#define MT_LAUNCH_REFINE_NT(T, B, N)                                                                                    \
+#define MT_LAUNCH_REFINE_NT(T, N, G)                                                                                     \
     do {                                                                                                                 \
-        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, B, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        refine_kernel<T, B, N><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                        \
+        MT_CUDA_TRY(cudaFuncSetAttribute(refine_kernel<T, N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        refine_kernel<T, N, G><<<(unsigned)n_px, kRefThreads, smem, stream>>>(p);                                        \
     } while (0)
-#define MT_LAUNCH_REFINE_B(T, B)                                \
+#define MT_LAUNCH_REFINE_G(T, G)                                \
     do {                                                        \
         switch (cfg.n_theta) {                                  \
-            case 0: MT_LAUNCH_REFINE_NT(T, B, 0); break;        \
-            case 1: MT_LAUNCH_REFINE_NT(T, B, 1); break;        \
-            case 2: MT_LAUNCH_REFINE_NT(T, B, 2); break;        \
-            case 3: MT_LAUNCH_REFINE_NT(T, B, 3); break;        \
-            default: MT_LAUNCH_REFINE_NT(T, B, 4); break;       \
+            case 0: MT_LAUNCH_REFINE_NT(T, 0, G); break;        \
+            case 1: MT_LAUNCH_REFINE_NT(T, 1, G); break;        \
+            case 2: MT_LAUNCH_REFINE_NT(T, 2, G); break;        \
+            case 3: MT_LAUNCH_REFINE_NT(T, 3, G); break;        \
+            default: MT_LAUNCH_REFINE_NT(T, 4, G); break;       \
         }                                                       \
     } while (0)
 #define MT_LAUNCH_REFINE(T)                                     \
     do {                                                        \
-        if (minb <= 4) MT_LAUNCH_REFINE_B(T, 4);                \
-        else MT_LAUNCH_REFINE_B(T, 6);                          \
+        if (general) MT_LAUNCH_REFINE_G(T, true);               \
+        else MT_LAUNCH_REFINE_G(T, false);                      \
     } while (0)
     if (dtype == MT_DTYPE_F32) {
         MT_LAUNCH_REFINE(float);
@@ -610,6 +797,50 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     } else {
         return mt::fail(MT_ERR_UNSUPPORTED, "mt_refine: dtype %d", dtype);
     }
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
+
+extern "C" int mt_model_jacobian(const MtRefineConfig *cfg_host, const MtRefineLine *lines_host, const uint32_t *chan_lines_host,
+                                 const float *x_dev, float *model_dev, float *dtheta_dev, int64_t ld, void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(cfg_host && lines_host && chan_lines_host && x_dev && model_dev, "mt_model_jacobian: null pointer");
+    const MtRefineConfig &cfg = *cfg_host;
+    MT_REQUIRE(cfg.n_ch > 0 && cfg.n_ch <= 8192 && cfg.ch0 >= 0, "mt_model_jacobian: channel window");
+    MT_REQUIRE(cfg.n_lines >= 1 && cfg.n_lines <= 2048 && cfg.n_comp >= 1, "mt_model_jacobian: n_lines=%d n_comp=%d", cfg.n_lines,
+               cfg.n_comp);
+    MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= MT_MAX_THETA && (cfg.n_theta == 0 || (dtheta_dev && ld >= cfg.n_ch)),
+               "mt_model_jacobian: n_theta=%d ld=%lld", cfg.n_theta, (long long)ld);
+    for (int l = 0; l < cfg.n_lines; ++l)
+        MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp && lines_host[l].kind >= MT_LINE_ELEMENT &&
+                       lines_host[l].kind <= MT_LINE_COMPTON && lines_host[l].step >= 0.f,
+                   "mt_model_jacobian: line %d (component / kind / step)", l);
+    for (int k = 0; k < cfg.n_theta; ++k)
+        MT_REQUIRE(cfg.theta_id[k] >= 0 && cfg.theta_id[k] < MT_N_THETA_IDS, "mt_model_jacobian: theta_id[%d]=%d", k,
+                   cfg.theta_id[k]);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t b_lines = sizeof(MtRefineLine) * cfg.n_lines, b_chan = sizeof(uint32_t) * cfg.n_ch;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    std::vector<char> packed(up(b_lines) + up(b_chan));
+    memcpy(packed.data(), lines_host, b_lines);
+    memcpy(packed.data() + up(b_lines), chan_lines_host, b_chan);
+    const char *tables = nullptr;
+    if (int rc = cached_tables(packed, &tables)) return rc;
+    const MtRefineLine *lines = reinterpret_cast<const MtRefineLine *>(tables);
+    const uint32_t *chan = reinterpret_cast<const uint32_t *>(tables + up(b_lines));
+    const size_t smem = sizeof(float4) * (size_t)cfg.n_lines * (4 + cfg.n_theta);
+    if (smem > 200 * 1024) return mt::fail(MT_ERR_UNSUPPORTED, "mt_model_jacobian: %zu bytes of shared memory needed", smem);
+    const unsigned grid = (unsigned)(((cfg.n_ch + 1) / 2 + kRefThreads - 1) / kRefThreads);
+#define MT_LAUNCH_JAC(N)                                                                                              \
+    case N:                                                                                                           \
+        MT_CUDA_TRY(cudaFuncSetAttribute(jacobian_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        jacobian_kernel<N><<<grid, kRefThreads, smem, stream>>>(cfg, lines, chan, x_dev, model_dev, dtheta_dev, ld);   \
+        break;
+    switch (cfg.n_theta) {
+        MT_LAUNCH_JAC(0) MT_LAUNCH_JAC(1) MT_LAUNCH_JAC(2) MT_LAUNCH_JAC(3) MT_LAUNCH_JAC(4)
+        MT_LAUNCH_JAC(5) MT_LAUNCH_JAC(6) MT_LAUNCH_JAC(7) MT_LAUNCH_JAC(8)
+    }
+#undef MT_LAUNCH_JAC
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }

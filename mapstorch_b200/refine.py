@@ -1,9 +1,10 @@
 """Per-pixel nonlinear refinement (kernel K4) and the global-parameter fit of one spectrum.
 
-``refine_map`` frees up to four peak-shape parameters per pixel (ENERGY_OFFSET, ENERGY_SLOPE,
-FWHM_OFFSET, FWHM_FANOPRIME) together with all amplitudes -- the per-pixel version of the
-reference's ``fit_spec(..., fitting_params=[...], tune_params=True)`` (opt.py:165-327) -- starting
-from the linear solve of ``MapFitPlan.fit``.  ``fit_spec_global`` is ``fit_spec`` with
+``refine_map`` frees up to four calibration parameters per pixel (any of the eight with a non-zero gradient on
+model_spec's path: ENERGY_OFFSET / SLOPE / QUADRATIC, FWHM_OFFSET / FANOPRIME, COHERENT_SCT_ENERGY, COMPTON_ANGLE,
+COMPTON_FWHM_CORR) together with all amplitudes; step terms (F_STEP_*, COMPTON_F_STEP) are part of the model -- the
+per-pixel version of the reference's ``fit_spec(..., fitting_params=[...], tune_params=True)`` (opt.py:165-327) --
+starting from the linear solve of ``MapFitPlan.fit``.  ``fit_spec_global`` is ``fit_spec`` with
 ``tune_params=True`` for one (integrated) spectrum: variable projection over the tunable calibration
 parameters, every model evaluation on the GPU (K1 basis + the non-negative solve).
 """
@@ -20,43 +21,57 @@ f32 = np.float32
 REFINE_WARPS = 4  # warps per CTA of mt_refine (csrc/mt_refine.cu: kRefThreads / 32)
 
 DEFAULT_BOUNDS = {
-    "ENERGY_OFFSET": ("abs", 0.03),       # +- keV around the global value
-    "ENERGY_SLOPE": ("rel", 0.01),        # +- 1 %
-    "FWHM_OFFSET": ("rel", 0.30),         # +- 30 %
-    "FWHM_FANOPRIME": ("rel", 0.50),      # +- 50 %
+    "ENERGY_OFFSET": ("abs", 0.03),        # +- keV around the global value
+    "ENERGY_SLOPE": ("rel", 0.01),         # +- 1 %
+    "FWHM_OFFSET": ("rel", 0.30),          # +- 30 %
+    "FWHM_FANOPRIME": ("rel", 0.50),       # +- 50 %
+    "ENERGY_QUADRATIC": ("abs", 2e-8),     # keV / channel^2
+    "COHERENT_SCT_ENERGY": ("abs", 0.15),  # +- keV
+    "COMPTON_ANGLE": ("abs", 15.0),        # +- degrees
+    "COMPTON_FWHM_CORR": ("rel", 0.40),    # +- 40 %
 }
 
 
-def gaussian_lines(params, names, e_consts=default_energy_consts, elem_info=default_elem_info):
-    """(energy, factor, comp, sigma_scale, e296) of every Gaussian term of model_spec's default
-    path (use_step=True with f_step == 0, use_tail=False), amplitudes excluded."""
+def model_lines(params, names, e_consts=default_energy_consts, elem_info=default_elem_info):
+    """(energy, factor, comp, sigma_scale, e296, step, kind) of every line on model_spec's path (map.py:260-309:
+    use_step=True, use_tail=False), amplitudes excluded.  factor = ratio / (1 + f_step) as model_elem_spec forms it
+    (map.py:183-207), step = f_step of the line (map.py:169-172), COMPTON_F_STEP for the Compton peak (map.py:94-114)."""
     p32 = {k: tables.scalar32(v) for k, v in params.items() if k in default_param_vals}
     e0 = p32["COHERENT_SCT_ENERGY"]
     out = []
     for comp, name in enumerate(names):
         if name == "COHERENT_SCT_AMPLITUDE":
-            out.append((e0, f32(1.0), comp, f32(1.0), e0 * f32(2.96)))
+            out.append((e0, f32(1.0), comp, f32(1.0), e0 * f32(2.96), f32(0.0), _native.MT_LINE_ELASTIC))
         elif name == "COMPTON_AMPLITUDE":
-            if p32["COMPTON_F_STEP"] > 0:
-                raise NotImplementedError("refinement with a Compton step term (COMPTON_F_STEP > 0)")
+            fs = p32["COMPTON_F_STEP"] if p32["COMPTON_F_STEP"] > 0 else f32(0.0)
             ce = tables.compton_energy(params)
-            out.append((ce, f32(1.0), comp, p32["COMPTON_FWHM_CORR"], ce * f32(2.96)))
+            out.append((ce, f32(1.0) / (f32(1.0) + fs), comp, p32["COMPTON_FWHM_CORR"], ce * f32(2.96), fs,
+                        _native.MT_LINE_COMPTON))
         else:
             for s in e_consts[name]:
                 if s.ratio == 0 or s.energy <= 0 or not s.check_binding_energy(elem_info, e0):
                     continue
                 mu, e = f32(s.mu_fraction), f32(s.energy)
                 f_step = np.abs(mu * (p32["F_STEP_OFFSET"] + p32["F_STEP_LINEAR"] * e))
-                if f_step > 0:
-                    raise NotImplementedError("refinement with step terms (F_STEP_* != 0)")
-                out.append((e, f32(s.ratio), comp, f32(1.0), f32(s.energy * 2.96)))
+                fac = f32(s.ratio)
+                if s.ptype.startswith("Ka") or s.ptype.startswith("L") or s.ptype.startswith("Kb"):
+                    fac = fac / (f32(1.0) + f_step)
+                out.append((e, fac, comp, f32(1.0), f32(s.energy * 2.96), f32(f_step), _native.MT_LINE_ELEMENT))
     return out
 
 
-def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
-    """Host tables of mt_refine for the components `names` over channels er[0]..er[1]."""
+def gaussian_lines(params, names, e_consts=default_energy_consts, elem_info=default_elem_info):
+    """(energy, factor, comp, sigma_scale, e296) of the Gaussian terms (kept for callers of the round-1 tables)."""
+    return [t[:5] for t in model_lines(params, names, e_consts, elem_info)]
+
+
+def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, max_theta=_native.MT_MAX_THETA_REFINE, **kw):
+    """Host tables of mt_refine / mt_model_jacobian for the components `names` over channels er[0]..er[1]."""
     bounds = dict(DEFAULT_BOUNDS, **(bounds or {}))
-    lines = sorted(gaussian_lines(params, names, **kw), key=lambda t: float(t[0]))
+    free = list(free)
+    if len(free) > max_theta or any(f not in _native.THETA_IDS for f in free):
+        raise ValueError(f"free parameters: at most {max_theta} of {sorted(_native.THETA_IDS)}, got {free}")
+    lines = sorted(model_lines(params, names, **kw), key=lambda t: float(t[0]))
     n_ch = er[1] - er[0] + 1
     p32 = {k: float(tables.scalar32(params[k])) for k in default_param_vals}
     cfg = _native.MtRefineConfig()
@@ -71,9 +86,12 @@ def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
         lo_hi[name] = (v - span, v + span)
     cfg.energy_offset, cfg.energy_slope, cfg.energy_quad = p32["ENERGY_OFFSET"], p32["ENERGY_SLOPE"], p32["ENERGY_QUADRATIC"]
     cfg.fwhm_offset, cfg.fwhm_fanoprime = p32["FWHM_OFFSET"], p32["FWHM_FANOPRIME"]
-    # windows: widest sigma and largest energy-axis excursion the bounds allow
+    cfg.coherent_sct_energy, cfg.compton_angle = p32["COHERENT_SCT_ENERGY"], p32["COMPTON_ANGLE"]
+    cfg.compton_fwhm_corr = p32["COMPTON_FWHM_CORR"]
+    # windows: widest sigma and largest energy-axis / line-energy excursion the bounds allow
     fo_hi = lo_hi.get("FWHM_OFFSET", (0, p32["FWHM_OFFSET"]))[1]
     fa_hi = lo_hi.get("FWHM_FANOPRIME", (0, p32["FWHM_FANOPRIME"]))[1]
+    corr_hi = lo_hi.get("COMPTON_FWHM_CORR", (0, p32["COMPTON_FWHM_CORR"]))[1]
     ch = np.arange(er[0], er[1] + 1, dtype=np.float64)
     ev = p32["ENERGY_OFFSET"] + p32["ENERGY_SLOPE"] * ch + p32["ENERGY_QUADRATIC"] * ch * ch
     shift = 0.0
@@ -81,15 +99,34 @@ def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
         shift += lo_hi["ENERGY_OFFSET"][1] - p32["ENERGY_OFFSET"]
     if "ENERGY_SLOPE" in lo_hi:
         shift += (lo_hi["ENERGY_SLOPE"][1] - p32["ENERGY_SLOPE"]) * ch.max()
+    if "ENERGY_QUADRATIC" in lo_hi:
+        shift += (lo_hi["ENERGY_QUADRATIC"][1] - p32["ENERGY_QUADRATIC"]) * ch.max() ** 2
+    # how far the scatter lines can move: the elastic line with COHERENT_SCT_ENERGY, the Compton line with both
+    move = {_native.MT_LINE_ELEMENT: 0.0, _native.MT_LINE_ELASTIC: 0.0, _native.MT_LINE_COMPTON: 0.0}
+    if "COHERENT_SCT_ENERGY" in lo_hi:
+        span = lo_hi["COHERENT_SCT_ENERGY"][1] - p32["COHERENT_SCT_ENERGY"]
+        move[_native.MT_LINE_ELASTIC] += span
+        move[_native.MT_LINE_COMPTON] += span
+    if "COMPTON_ANGLE" in lo_hi:
+        e0 = p32["COHERENT_SCT_ENERGY"] + move[_native.MT_LINE_ELASTIC]
+        ce = [e0 / (1 + (e0 / 511.0) * (1 - np.cos(np.deg2rad(a)))) for a in np.linspace(*lo_hi["COMPTON_ANGLE"], 33)]
+        move[_native.MT_LINE_COMPTON] += max(abs(c - float(tables.compton_energy(params))) for c in ce)
     arr = (_native.MtRefineLine * len(lines))()
     window = np.zeros(len(lines), dtype=np.uint32)
     first = np.full(n_ch, len(lines), dtype=np.int64)
     last = np.zeros(n_ch, dtype=np.int64)
-    for i, (e, fac, comp, scale, e296) in enumerate(lines):
+    for i, (e, fac, comp, scale, e296, step, kind) in enumerate(lines):
         arr[i].energy, arr[i].factor, arr[i].comp, arr[i].sigma_scale, arr[i].e296 = float(e), float(fac), comp, float(scale), float(e296)
-        sigma = float(scale) * np.sqrt((fo_hi / 2.3548) ** 2 + float(e296) * fa_hi)
-        reach = k_sigma * sigma + shift
+        arr[i].step, arr[i].kind = float(step), int(kind)
+        widest = max(float(scale), corr_hi) if kind == _native.MT_LINE_COMPTON else float(scale)
+        e_hi = float(e) + move[kind]
+        sigma = widest * np.sqrt((fo_hi / 2.3548) ** 2 + e_hi * 2.96 * fa_hi)
+        reach = k_sigma * sigma + shift + move[kind]
         inside = np.nonzero(np.abs(ev - float(e)) <= reach)[0]
+        if step > 0:
+            # the step term is a plateau below the line (erfc -> 2): its window runs down to the first channel
+            top = np.nonzero(ev <= float(e) + reach)[0]
+            inside = np.arange(0, (int(top[-1]) + 1) if top.size else 0)
         if inside.size:
             lo_c, hi_c = int(inside[0]), int(inside[-1]) + 1
             window[i] = lo_c | (hi_c << 16)
@@ -118,6 +155,25 @@ def refine_tables(params, names, er, free, bounds=None, k_sigma=5.5, **kw):
     return cfg, arr, chan_lines, comp_start, comp_lines, window, comp_order
 
 
+def model_jacobian(params, energy_range, names, amps, free, e_consts=default_energy_consts, elem_info=default_elem_info):
+    """Model spectrum of model_spec's path and its analytic derivatives w.r.t. the calibration parameters `free` (any of
+    _native.THETA_IDS, up to 8) at fixed linear amplitudes `amps` (CUDA fp32 [len(names)]): what torch.autograd gives
+    the reference for d model_spec / d param (opt.py:249-317).  Returns (model [C], d_theta [len(free), C]) on the device."""
+    er = (int(energy_range[0]), int(energy_range[1]))
+    # windows wide enough for exact values everywhere that matters: no bounds (the parameters do not move here)
+    zero = {k: ("abs", 0.0) for k in DEFAULT_BOUNDS}
+    cfg, lines, chan_lines, _, _, _, _ = refine_tables(params, names, er, free, zero, k_sigma=7.0,
+                                                       max_theta=_native.MT_MAX_THETA, e_consts=e_consts, elem_info=elem_info)
+    n_ch = er[1] - er[0] + 1
+    x = amps.detach().to("cuda", torch.float32).contiguous()
+    model = torch.empty(n_ch, dtype=torch.float32, device="cuda")
+    d = torch.empty((max(len(free), 1), n_ch), dtype=torch.float32, device="cuda")
+    _native.call("mt_model_jacobian", ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p),
+                 chan_lines.ctypes.data_as(ctypes.c_void_p), x.data_ptr(), model.data_ptr(), d.data_ptr(), d.stride(0),
+                 _native.stream_ptr())
+    return model, d[: len(free)]
+
+
 def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=None, max_iter=12, tol=1e-6,
                bkg=None, stream=None):
     """Refine amplitudes x [E, P] (CUDA, from plan.fit) and the `free` parameters per pixel in place.
@@ -134,8 +190,9 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
         raise NotImplementedError("per-pixel refinement with escape peaks (escape_factor > 0)")
     free = list(free)
     unknown = [f for f in free if f not in _native.THETA_IDS]
-    if unknown or len(free) > 4:
-        raise ValueError(f"free parameters must be a subset of {sorted(_native.THETA_IDS)}, got {free}")
+    if unknown or len(free) > _native.MT_MAX_THETA_REFINE:
+        raise ValueError(f"free parameters: at most {_native.MT_MAX_THETA_REFINE} of {sorted(_native.THETA_IDS)} per pixel, "
+                         f"got {free}")
     # the host tables depend only on the plan and the free parameters: built once, reused for every slab
     key = (tuple(free), tuple(sorted((bounds or {}).items())))
     cache = plan.__dict__.setdefault("_refine_tables", {})
@@ -172,8 +229,13 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     The reference runs Adam on all tunable calibration parameters and log-amplitudes at once.  Here the
     amplitudes are projected out (for given calibration parameters they are the non-negative
     least-squares solution) and the remaining small problem is solved by
-    Levenberg-Marquardt with forward-difference Jacobians; every evaluation runs K1 (basis), K2 (SNIP,
-    which depends on the calibration too) and the non-negative solve on the device.
+    Levenberg-Marquardt.  Every evaluation runs K1 (basis), K2 (SNIP, which depends on the calibration too) and
+    the non-negative solve on the device; the Jacobian is ANALYTIC -- one launch of mt_model_jacobian (the
+    derivative code of the per-pixel refinement kernel, checked against torch.autograd of the reference) gives
+    d model / d parameter for all free parameters, projected orthogonally to the unclamped basis columns
+    (Kaufman's variable-projection Jacobian) -- so an iteration costs one derivative launch plus the trial
+    evaluations instead of 1 + len(free) evaluations.  Forward differences remain for escape peaks and the
+    l1_lambda penalty.
 
     ``loss="l1"`` wraps that in iteratively re-weighted rounds (weights 1/max(|res|, eps), eps annealed);
     the ``l1_lambda`` penalty c*sum(A) enters the amplitude solve as a shifted right-hand side and the
@@ -218,24 +280,52 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         return vec, dict(x=x, names=names, basis=basis, bkg=bkg, params=pp, res=res, bm=bm, tm=tm, c=c,
                          objective=robust.objective(bm, tm, x, loss, c))
 
-    def run_lm(theta, w, max_it, trace):
-        resid, info = evaluate(theta, w)
-        value = float(resid @ resid)
-        lam = 1e-3
-        for it in range(max_it if free else 0):
+    # Parameters that move the model: the tail fractions of default_fitting_params never enter model_spec
+    # (use_tail=False, map.py:290,302), their gradient is zero in the reference as well and they keep their values.
+    active = [k for k, name in enumerate(free) if name in _native.THETA_IDS]
+    # analytic Jacobian (mt_model_jacobian) wherever the device model is the whole model: no escape peaks, no penalty
+    # entries in the residual vector; otherwise forward differences (1 + len(free) evaluations per iteration)
+    analytic = escape_factor == 0.0 and not (l1_lambda > 0) and len(active) <= _native.MT_MAX_THETA
+
+    def jacobian(theta, w, resid, info):
+        if not analytic:
             cols = []
             for k in range(len(free)):
                 t2 = theta.copy()
                 t2[k] += 0.05 * scale[k]
                 r2, _ = evaluate(t2, w)
                 cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
-            jac = torch.stack(cols, dim=1)
+            return torch.stack(cols, dim=1)
+        # variable projection (Kaufman): d r / d theta_k = P (d model / d theta_k at fixed amplitudes), P the projector
+        # orthogonal to the basis columns of the components that are not clamped (weighted for the robust loss)
+        x = info["x"]
+        _, d = model_jacobian(info["params"], er, info["names"], x.float(), [free[k] for k in active], e_consts, elem_info)
+        d = d.double() if idx is None else d.double()[:, idx]
+        bf = info["bm"][x > 0]
+        wv = torch.ones_like(info["tm"]) if w is None else w
+        if bf.shape[0]:
+            gram = (bf * wv) @ bf.T
+            coef = torch.linalg.solve(gram + 1e-12 * torch.diag(torch.diagonal(gram)), (bf * wv) @ d.T)
+            d = d - coef.T @ bf
+        jac = torch.zeros((resid.shape[0], len(free)), dtype=torch.float64, device=d.device)
+        for j, k in enumerate(active):
+            jac[:, k] = torch.sqrt(wv) * d[j] * scale[k]
+        return jac
+
+    def run_lm(theta, w, max_it, trace):
+        resid, info = evaluate(theta, w)
+        value = float(resid @ resid)
+        lam = 1e-3
+        for it in range(max_it if free else 0):
+            jac = jacobian(theta, w, resid, info)
             jtj = (jac.T @ jac).cpu().numpy()
             jtr = (jac.T @ resid).cpu().numpy()
             improved = False
             for _ in range(8):
                 try:
-                    step = np.linalg.solve(jtj + lam * (np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))), -jtr)
+                    damp = np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))
+                    dead = np.diag(jtj) <= 0  # parameters without influence (zero column): no step
+                    step = np.linalg.solve(jtj + lam * damp + np.diag(dead.astype(float)), -jtr)
                 except np.linalg.LinAlgError:
                     lam *= 10
                     continue

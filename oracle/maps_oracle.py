@@ -509,7 +509,8 @@ def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENER
 
     def solve(theta):
         pp = dict(params, **dict(zip(free, theta)))
-        _, _, B, _ = gaussian_model_jacobian(pp, energy_range, elements_to_fit, np.ones(n_comp))
+        # the full path of model_spec: Gaussians, step terms, scatter lines following their parameters
+        _, _, B = model_jacobian(pp, energy_range, elements_to_fit, np.ones(n_comp), free=())
         x, _ = nnls(B, y, maxiter=50 * n_comp)
         return B, x
 
@@ -522,3 +523,104 @@ def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENER
     theta = sol.x * scale
     B, x = solve(theta)
     return theta, x, float(np.sum((B @ x - y) ** 2))
+
+
+# ---- general analytic Jacobian of model_spec (Gaussians + step terms, all effective calibration parameters) ------
+THETA_NAMES = ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "FWHM_FANOPRIME", "ENERGY_QUADRATIC",
+               "COHERENT_SCT_ENERGY", "COMPTON_ANGLE", "COMPTON_FWHM_CORR")
+
+
+def model_lines(params, elements_to_fit, e_consts=None, elem_info=None):
+    """Every term of model_spec's path (map.py:260-309: use_step=True, use_tail=False) as a line record
+    (component, kind, energy, factor, step fraction): kind 0 = element line, 1 = elastic peak (energy =
+    COHERENT_SCT_ENERGY), 2 = Compton peak.  factor holds ratio / (1 + f_step) as model_elem_spec forms it
+    (map.py:183-207); gates are evaluated at the global COHERENT_SCT_ENERGY."""
+    d = _defaults()
+    e_consts = d.default_energy_consts if e_consts is None else e_consts
+    elem_info = d.default_elem_info if elem_info is None else elem_info
+    P = {k: float(p32(params, k)) for k in d.default_param_vals}
+    e0 = P["COHERENT_SCT_ENERGY"]
+    out = []
+    for comp, name in enumerate(component_names(elements_to_fit, e_consts)):
+        if name == "COHERENT_SCT_AMPLITUDE":
+            out.append((comp, 1, e0, 1.0, 0.0))
+        elif name == "COMPTON_AMPLITUDE":
+            fs = P["COMPTON_F_STEP"] if P["COMPTON_F_STEP"] > 0 else 0.0
+            out.append((comp, 2, float(compton_energy(params)), 1.0 / (1.0 + fs), fs))
+        else:
+            for s in e_consts[name]:
+                if s.ratio == 0 or s.energy <= 0 or not s.check_binding_energy(elem_info, e0):
+                    continue
+                f_step = abs(float(s.mu_fraction) * (P["F_STEP_OFFSET"] + P["F_STEP_LINEAR"] * float(s.energy)))
+                fac = float(s.ratio)
+                if s.ptype.startswith("Ka") or s.ptype.startswith("L") or s.ptype.startswith("Kb"):
+                    fac = fac / (1.0 + f_step)
+                out.append((comp, 0, float(s.energy), fac, f_step))
+    return out
+
+
+def model_jacobian(params, energy_range, elements_to_fit, amps, free=THETA_NAMES, e_consts=None, elem_info=None):
+    """float64 model of model_spec's path and its analytic derivatives w.r.t. the calibration parameters in `free`
+    (any of THETA_NAMES) at fixed linear amplitudes `amps`.  Returns (model [C], d_theta [len(free), C], basis [C, E]).
+    The formulas are the ones csrc/mt_refine.cu evaluates; checked against torch.autograd of the reference
+    (tests/golden/make_golden.py --only jacobian)."""
+    from scipy.special import erfc
+
+    d = _defaults()
+    P = {k: float(p32(params, k)) for k in d.default_param_vals}
+    names = component_names(elements_to_fit, e_consts)
+    lines = model_lines(params, elements_to_fit, e_consts, elem_info)
+    ch = np.arange(energy_range[0], energy_range[1] + 1, dtype=np.float64)
+    off, slope, quad = P["ENERGY_OFFSET"], P["ENERGY_SLOPE"], P["ENERGY_QUADRATIC"]
+    ev = off + slope * ch + quad * ch * ch
+    s0 = P["FWHM_OFFSET"] / 2.3548
+    fa = P["FWHM_FANOPRIME"]
+    e0, ang, corr = P["COHERENT_SCT_ENERGY"], P["COMPTON_ANGLE"], P["COMPTON_FWHM_CORR"]
+    rad = ang * 2.0 * M_PI / 360.0
+    a = (e0 / 511.0) * (1.0 - np.cos(rad))
+    basis = np.zeros((ch.size, len(names)))
+    s_ev = np.zeros(ch.size)  # sum of d(term)/d(ev)
+    acc = {k: np.zeros(ch.size) for k in ("FWHM_OFFSET", "FWHM_FANOPRIME", "COHERENT_SCT_ENERGY", "COMPTON_ANGLE",
+                                          "COMPTON_FWHM_CORR")}
+    amps = np.asarray(amps, dtype=np.float64)
+    for comp, kind, energy, fac, fstep in lines:
+        # line energy and its derivatives w.r.t. the incident energy / scattering angle
+        d_e = {"COHERENT_SCT_ENERGY": 0.0, "COMPTON_ANGLE": 0.0}
+        if kind == 1:
+            energy, d_e["COHERENT_SCT_ENERGY"] = e0, 1.0
+        elif kind == 2:
+            energy = e0 / (1.0 + a)
+            d_e["COHERENT_SCT_ENERGY"] = 1.0 / (1.0 + a) ** 2
+            d_e["COMPTON_ANGLE"] = -e0 / (1.0 + a) ** 2 * (e0 / 511.0) * np.sin(rad) * (2.0 * M_PI / 360.0)
+        sb = np.sqrt(s0 * s0 + energy * 2.96 * fa)  # width of the line (step terms use it as it is)
+        scale = corr if kind == 2 else 1.0
+        sg = sb * scale                              # width of the Gaussian
+        # d(sb)/d(theta) / sb
+        c_sb = {"FWHM_OFFSET": s0 / (2.3548 * sb * sb), "FWHM_FANOPRIME": energy * 2.96 / (2.0 * sb * sb),
+                "COHERENT_SCT_ENERGY": 2.96 * fa / (2.0 * sb * sb) * d_e["COHERENT_SCT_ENERGY"],
+                "COMPTON_ANGLE": 2.96 * fa / (2.0 * sb * sb) * d_e["COMPTON_ANGLE"], "COMPTON_FWHM_CORR": 0.0}
+        c_sg = dict(c_sb, COMPTON_FWHM_CORR=(1.0 / corr if kind == 2 else 0.0))
+        dl = ev - energy
+        g = np.exp(-0.5 * (dl / sg) ** 2)
+        b = fac * slope / (sg * SQRT_2XPI) * g
+        v = amps[comp] * b
+        t1 = v * dl / (sg * sg)                 # -d v / d ev
+        t2 = v * ((dl / sg) ** 2 - 1.0)         # sg * d v / d sg
+        s_ev += -t1
+        for k in acc:
+            acc[k] += t2 * c_sg[k] + t1 * d_e.get(k, 0.0)
+        if fstep > 0:
+            z = dl / (M_SQRT2 * sb)
+            kk = fac * fstep * slope / (2.0 * energy)
+            bs = kk * erfc(z)
+            b = b + bs
+            s = amps[comp] * bs
+            q = amps[comp] * kk * (2.0 / np.sqrt(M_PI)) * np.exp(-z * z) / (M_SQRT2 * sb)  # -d s / d ev
+            s_ev += -q
+            for k in acc:
+                acc[k] += q * (dl / sb) * sb * c_sb[k] + (q - s / energy) * d_e.get(k, 0.0)
+        basis[:, comp] += b
+    model = basis @ amps
+    full = {"ENERGY_OFFSET": s_ev, "ENERGY_SLOPE": s_ev * ch + model / slope, "ENERGY_QUADRATIC": s_ev * ch * ch}
+    full.update(acc)
+    return model, (np.stack([full[k] for k in free]) if len(free) else np.zeros((0, ch.size))), basis

@@ -10,6 +10,7 @@ Outputs (np.savez_compressed):
   model_golden.npz  model_elem_spec / compton_peak / elastic_peak / model_spec outputs
   snip_golden.npz   snip_bkg inputs+outputs and the per-pass gather indices
   fit_golden.npz    per-spectrum fit_spec(tune_params=False) runs (converged Adam) + loss traces
+  jacobian_golden.npz  d model_spec / d calibration parameter by torch.autograd of the reference (--only jacobian)
   fit_c3_golden.npz the same at BASELINE config 3's shape: 4096 channels, 30 elements, SNIP (--only fit_c3)
   host_golden.npz   init_elem_amps, get_peak_ranges, escape bins
   objectives_golden.npz  fit_spec(tune_params=False) with loss="l1", l1_lambda > 0 and `indices` (--only objectives)
@@ -281,6 +282,47 @@ def gen_fit_c3(out):
         print(tag, "final loss", trace[-1], flush=True)
 
 
+JAC_PARAMS = ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "FWHM_FANOPRIME", "ENERGY_QUADRATIC",
+              "COHERENT_SCT_ENERGY", "COMPTON_ANGLE", "COMPTON_FWHM_CORR")
+
+
+def gen_jacobian(out):
+    """d model_spec / d param by torch.autograd through the reference's own model (what its optimiser differentiates,
+    opt.py:249-317), in float64 with fp32-representable parameter values, for the eight calibration parameters that
+    have a gradient on that path; with and without step terms, full and cropped energy range."""
+    from torch.autograd.functional import jacobian
+
+    elems = ["K", "Ca", "Fe", "Cu", "Zn", "Au_L", "Pt_M", "Si_Si"]
+    rng = np.random.default_rng(17)
+    cases = (("plain", params_a(), (0, 2047)), ("steps", dict(params_b(), COHERENT_SCT_ENERGY=12.5), (50, 1450)),
+             ("steps4096", dict(params_4096(), F_STEP_OFFSET=0.003, F_STEP_LINEAR=0.0002, COMPTON_F_STEP=0.02), (0, 4095)))
+    out["jac_cases"] = np.array([c[0] for c in cases])
+    out["jac_params"] = np.array(JAC_PARAMS)
+    out["jac_elems"] = np.array(elems)
+    names = elems + ["COMPTON_AMPLITUDE", "COHERENT_SCT_AMPLITUDE"]
+    for tag, p, er in cases:
+        p = {k: float(np.float32(v)) for k, v in p.items()}
+        logamp = {n: float(np.float32(rng.uniform(1.5, 3.0))) for n in names}
+        base = {k: torch.tensor(v, dtype=torch.float64) for k, v in p.items()}
+        base.update({n: torch.tensor(v, dtype=torch.float64) for n, v in logamp.items()})
+
+        def model(*theta):
+            t = dict(base)
+            t.update(dict(zip(JAC_PARAMS, theta)))
+            return rmap.model_spec(t, er, elems)
+
+        point = tuple(base[k].clone() for k in JAC_PARAMS)
+        jac = jacobian(model, point)
+        out[f"jac_{tag}_er"] = np.array(er)
+        out[f"jac_{tag}_param_names"] = np.array(list(p.keys()))
+        out[f"jac_{tag}_param_vals"] = np.array([p[k] for k in p], dtype=np.float64)
+        out[f"jac_{tag}_amp_names"] = np.array(names)
+        out[f"jac_{tag}_logamps"] = np.array([logamp[n] for n in names], dtype=np.float64)
+        out[f"jac_{tag}_model"] = model(*point).numpy()
+        out[f"jac_{tag}_jac"] = np.stack([j.numpy() for j in jac])
+        print(tag, "max |J| per parameter", [float(np.abs(j.numpy()).max()) for j in jac], flush=True)
+
+
 def gen_random_tables(out, n_sets=40):
     """Index arithmetic under randomly perturbed calibrations: CRC32 of every SNIP gather table, pass
     counts, escape bins, amplitude-guess windows and peak ranges, all computed by the reference's own
@@ -516,6 +558,12 @@ def main():
         gen_objectives(out)
         np.savez_compressed(HERE / "objectives_golden.npz", **out)
         print("wrote objectives", (HERE / "objectives_golden.npz").stat().st_size, flush=True)
+        return
+    if args.only == "jacobian":
+        out = {}
+        gen_jacobian(out)
+        np.savez_compressed(HERE / "jacobian_golden.npz", **out)
+        print("wrote jacobian", (HERE / "jacobian_golden.npz").stat().st_size, flush=True)
         return
     if args.only == "fit_c3":
         out = {}

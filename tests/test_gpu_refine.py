@@ -186,3 +186,100 @@ def test_host_volume_is_refined_slab_by_slab_with_the_same_result():
             assert torch.equal(on_device[k], from_host[k]), (use_snip, k)
             assert torch.equal(on_device[k], pinned[k].reshape(-1)), (use_snip, k)
         assert pinned["Fe"].shape == (20, 15) and pinned["iterations"].dtype == torch.int32
+
+
+def test_model_jacobian_matches_reference_autograd():
+    """mt_model_jacobian (the evaluation K4 runs per pixel, exposed for one spectrum) against d model_spec / d param
+    by torch.autograd of the reference -- all eight calibration parameters, with and without step terms
+    (tests/golden/jacobian_golden.npz).  Tolerance: model 1e-5 of its maximum (north_star), derivatives 1e-4 of the
+    column maximum."""
+    from mapstorch_b200 import refine
+    from oracle import maps_oracle as mo
+
+    g = np.load(GOLDEN / "jacobian_golden.npz", allow_pickle=False)
+    free = [str(k) for k in g["jac_params"]]
+    elems = [str(e) for e in g["jac_elems"]]
+    for tag in [str(t) for t in g["jac_cases"]]:
+        p = dict(zip([str(k) for k in g[f"jac_{tag}_param_names"]], [float(v) for v in g[f"jac_{tag}_param_vals"]]))
+        er = tuple(int(v) for v in g[f"jac_{tag}_er"])
+        logamp = dict(zip([str(n) for n in g[f"jac_{tag}_amp_names"]], g[f"jac_{tag}_logamps"]))
+        names = mo.component_names(elems)
+        amps = torch.tensor([10.0 ** float(np.float32(logamp[n])) for n in names], dtype=torch.float32)
+        model, d = refine.model_jacobian(p, er, names, amps, free)
+        model, d = model.cpu().numpy(), d.cpu().numpy()
+        ref_model, ref_jac = g[f"jac_{tag}_model"], g[f"jac_{tag}_jac"]
+        err_m = np.abs(model - ref_model).max() / ref_model.max()
+        errs = {name: float(np.abs(d[k] - ref_jac[k]).max() / np.abs(ref_jac[k]).max()) for k, name in enumerate(free)}
+        print(f"{tag}: model {err_m:.2e}; derivatives " + ", ".join(f"{n} {e:.1e}" for n, e in errs.items()))
+        assert err_m <= 1e-5, tag
+        assert max(errs.values()) <= 1e-4, (tag, errs)
+        # a subset in another order gives the same columns
+        sub = ["COMPTON_ANGLE", "ENERGY_SLOPE", "FWHM_OFFSET"]
+        _, d3 = refine.model_jacobian(p, er, names, amps, sub)
+        for j, n in enumerate(sub):
+            assert np.allclose(d3[j].cpu().numpy(), d[free.index(n)], rtol=1e-5, atol=1e-6 * np.abs(d[free.index(n)]).max())
+
+
+def test_refinement_with_step_terms_and_scatter_parameters():
+    """Per-pixel refinement on the full path of model_spec: step terms on (F_STEP_*, COMPTON_F_STEP) and the scatter
+    peaks' own parameters free (COHERENT_SCT_ENERGY, COMPTON_ANGLE, COMPTON_FWHM_CORR) next to ENERGY_QUADRATIC --
+    against the float64 variable-projection oracle on the same model."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    elems = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0, F_STEP_OFFSET=0.002, F_STEP_LINEAR=0.0004, COMPTON_F_STEP=0.01)
+    er = (0, 2047)
+    rng = np.random.default_rng(21)
+    names = mo.component_names(elems)
+    free = ("COHERENT_SCT_ENERGY", "COMPTON_ANGLE", "COMPTON_FWHM_CORR", "ENERGY_QUADRATIC")
+    ys, truth = [], []
+    for i in range(4):
+        pp = dict(p, COHERENT_SCT_ENERGY=12.0 + rng.uniform(-0.04, 0.04), COMPTON_ANGLE=p["COMPTON_ANGLE"] + rng.uniform(-4, 4),
+                  COMPTON_FWHM_CORR=p["COMPTON_FWHM_CORR"] * rng.uniform(0.9, 1.1),
+                  ENERGY_QUADRATIC=p["ENERGY_QUADRATIC"] + rng.uniform(-4e-9, 4e-9))
+        amps = 10.0 ** rng.uniform(2.5, 3.5, size=len(names))
+        amps[-2:] *= 20.0  # strong scatter peaks: their parameters are well determined
+        model, _, _ = mo.model_jacobian(pp, er, elems, amps, free=())
+        ys.append(rng.poisson(model).astype(np.float32))
+        truth.append(pp)
+    y = np.stack(ys)
+    maps = opt.fit_map(y, er, elems, init_param_vals=p, use_snip=False, refine=free, refine_iters=40, device="cpu")
+    lin = opt.fit_map(y, er, elems, init_param_vals=p, use_snip=False, device="cpu")
+    for i in range(4):
+        theta, x, loss = mo.refine_spectrum(y[i], p, er, elems, free=free)
+        got = float(maps["loss"][i])
+        print(f"pixel {i}: loss {got:.6g} (oracle {loss:.6g}); theta " +
+              ", ".join(f"{n} {float(maps[n][i]):.6g} / {t:.6g}" for n, t in zip(free, theta)))
+        assert got <= loss * (1 + 1e-3), i
+        assert abs(float(maps["COHERENT_SCT_ENERGY"][i]) - theta[0]) < 2e-4, i
+        assert abs(float(maps["COMPTON_ANGLE"][i]) - theta[1]) < 0.05, i
+        assert abs(float(maps["COMPTON_FWHM_CORR"][i]) / theta[2] - 1) < 5e-3, i
+        mine = np.array([float(maps[n][i]) for n in names])
+        interior = x > 1e-3 * x.max()
+        assert (np.abs(mine - x)[interior] / x[interior]).max() < 1e-3, i
+        # the linear fit at the global parameters is visibly worse
+        B = mo.model_jacobian(p, er, elems, np.ones(len(names)), free=())[2]
+        lin_x = np.array([float(lin[n][i]) for n in names])
+        assert got < ((y[i] - B @ lin_x) ** 2).sum()
+
+
+def test_linear_fit_includes_step_terms():
+    """The basis of the map fit (K1) and the refinement kernel model the same spectrum when step terms are on."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    elems = ["Ca", "Fe", "Cu", "Zn"]
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0, F_STEP_OFFSET=0.004, F_STEP_LINEAR=0.0006, COMPTON_F_STEP=0.02)
+    er = (0, 2047)
+    names = mo.component_names(elems)
+    rng = np.random.default_rng(5)
+    amps = 10.0 ** rng.uniform(2.5, 3.5, size=len(names))
+    model, _, B = mo.model_jacobian(p, er, elems, amps, free=())
+    y = rng.poisson(model).astype(np.float32)[None]
+    maps = opt.fit_map(y, er, elems, init_param_vals=p, use_snip=False, refine=("ENERGY_OFFSET",), refine_iters=10, device="cpu")
+    # data were generated AT the global parameters: the refined offset stays put and the loss is the Poisson noise
+    assert abs(float(maps["ENERGY_OFFSET"][0]) - p["ENERGY_OFFSET"]) < 5e-4
+    assert float(maps["loss"][0]) < 1.3 * model.sum()

@@ -222,3 +222,25 @@ def test_oracle_matches_reference_fit_at_config3_shape():
         print(tag, "reference Adam vs oracle NNLS conditioned on the reference's leftover clamped amplitudes:", rel.max())
         assert rel.max() < 1e-4, (tag, rel.max())
         assert np.all(ref_amp[x == 0] <= 1e-2 * x.max())  # what the reference still carries on the clamped components
+
+
+def test_oracle_jacobian_matches_reference_autograd():
+    """jacobian_golden: d model_spec / d param by torch.autograd of the reference (with and without step terms) --
+    pins oracle.model_jacobian, the float64 statement of the formulas csrc/mt_refine.cu evaluates."""
+    from conftest import GOLDEN
+
+    g = np.load(GOLDEN / "jacobian_golden.npz", allow_pickle=False)
+    free = [str(k) for k in g["jac_params"]]
+    elems = [str(e) for e in g["jac_elems"]]
+    for tag in [str(t) for t in g["jac_cases"]]:
+        p = dict(zip([str(k) for k in g[f"jac_{tag}_param_names"]], [float(v) for v in g[f"jac_{tag}_param_vals"]]))
+        er = tuple(int(v) for v in g[f"jac_{tag}_er"])
+        logamp = dict(zip([str(n) for n in g[f"jac_{tag}_amp_names"]], g[f"jac_{tag}_logamps"]))
+        names = mo.component_names(elems)
+        amps = [10.0 ** float(np.float32(logamp[n])) for n in names]
+        model, d_theta, basis = mo.model_jacobian(p, er, elems, amps, free)
+        ref_model, ref_jac = g[f"jac_{tag}_model"], g[f"jac_{tag}_jac"]
+        assert np.abs(model - ref_model).max() <= 1e-5 * ref_model.max(), tag
+        for k, name in enumerate(free):
+            err = np.abs(d_theta[k] - ref_jac[k]).max() / np.abs(ref_jac[k]).max()
+            assert err <= 1e-4, (tag, name, err)
