@@ -287,15 +287,21 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     # entries in the residual vector; otherwise forward differences (1 + len(free) evaluations per iteration)
     analytic = escape_factor == 0.0 and not (l1_lambda > 0) and len(active) <= _native.MT_MAX_THETA
 
+    state = {"fd": not analytic}
+
     def jacobian(theta, w, resid, info):
-        if not analytic:
-            cols = []
-            for k in range(len(free)):
-                t2 = theta.copy()
-                t2[k] += 0.05 * scale[k]
-                r2, _ = evaluate(t2, w)
-                cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
-            return torch.stack(cols, dim=1)
+        if not state["fd"]:
+            return jacobian_analytic(theta, w, resid, info)
+        # forward differences: 1 + len(free) evaluations
+        cols = []
+        for k in range(len(free)):
+            t2 = theta.copy()
+            t2[k] += 0.05 * scale[k]
+            r2, _ = evaluate(t2, w)
+            cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
+        return torch.stack(cols, dim=1)
+
+    def jacobian_analytic(theta, w, resid, info):
         # variable projection (Kaufman): d r / d theta_k = P (d model / d theta_k at fixed amplitudes), P the projector
         # orthogonal to the basis columns of the components that are not clamped (weighted for the robust loss)
         x = info["x"]
@@ -312,10 +318,20 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
             jac[:, k] = torch.sqrt(wv) * d[j] * scale[k]
         return jac
 
+    # physical ranges (the optimiser never leaves them) and a trust region in the scaled variables: one iteration
+    # moves a parameter by at most `radius` x 10 learning rates (default.py:102-116) -- what the reference's Adam
+    # covers in ten steps.  Exact derivatives make the raw Gauss-Newton step long on the first, badly conditioned
+    # iterations (a Compton angle 70 degrees away was accepted once: lower loss, wrong basin).
+    limits = {"ENERGY_SLOPE": (1e-6, np.inf), "FWHM_OFFSET": (1e-4, np.inf), "FWHM_FANOPRIME": (1e-9, np.inf),
+              "COMPTON_ANGLE": (1.0, 179.0), "COMPTON_FWHM_CORR": (0.1, 20.0), "COHERENT_SCT_ENERGY": (0.5, 300.0)}
+    lo = np.array([limits.get(name, (-np.inf, np.inf))[0] for name in free])
+    hi = np.array([limits.get(name, (-np.inf, np.inf))[1] for name in free])
+
     def run_lm(theta, w, max_it, trace):
         resid, info = evaluate(theta, w)
         value = float(resid @ resid)
         lam = 1e-3
+        radius = 1.0
         for it in range(max_it if free else 0):
             jac = jacobian(theta, w, resid, info)
             jtj = (jac.T @ jac).cpu().numpy()
@@ -329,19 +345,34 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                 except np.linalg.LinAlgError:
                     lam *= 10
                     continue
-                cand = theta + step * scale
+                longest = float(np.max(np.abs(step))) if step.size else 0.0
+                clipped = longest > radius
+                if clipped:
+                    step = step * (radius / longest)
+                cand = np.clip(theta + step * scale, lo, hi)
                 r_new, info_new = evaluate(cand, w)
                 value_new = float(r_new @ r_new)
                 if value_new < value:
                     rel = (value - value_new) / max(value, 1e-30)
                     theta, resid, info, value = cand, r_new, info_new, value_new
                     lam = max(lam / 5, 1e-9)
+                    if clipped:
+                        radius = min(radius * 2.0, 16.0)
+                        rel = max(rel, 1.0)  # a clipped step says nothing about convergence
                     improved = True
                     break
                 lam *= 5
+                radius = max(radius * 0.5, 1e-3)
             trace.append(info["objective"])
             if verbose:
                 print(f"fit_spec_global iter {it}: objective {info['objective']:.6g} lambda {lam:.2g}")
+            if (not improved or rel < 1e-10) and not state["fd"]:
+                # The analytic Jacobian leaves out what is not differentiable: the SNIP background follows the width
+                # and energy-axis parameters through integer window tables, and the non-negative solve changes its
+                # active set.  Where that stalls the iteration, finish with forward differences of the whole residual.
+                state["fd"] = True
+                lam, radius = 1e-3, 1.0
+                continue
             if not improved or rel < 1e-10:
                 break
         return theta, info
