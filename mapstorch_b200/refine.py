@@ -230,12 +230,12 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     amplitudes are projected out (for given calibration parameters they are the non-negative
     least-squares solution) and the remaining small problem is solved by
     Levenberg-Marquardt.  Every evaluation runs K1 (basis), K2 (SNIP, which depends on the calibration too) and
-    the non-negative solve on the device; the Jacobian is ANALYTIC -- one launch of mt_model_jacobian (the
-    derivative code of the per-pixel refinement kernel, checked against torch.autograd of the reference) gives
-    d model / d parameter for all free parameters, projected orthogonally to the unclamped basis columns
-    (Kaufman's variable-projection Jacobian) -- so an iteration costs one derivative launch plus the trial
-    evaluations instead of 1 + len(free) evaluations.  Forward differences remain for escape peaks and the
-    l1_lambda penalty.
+    the non-negative solve on the device.  Without SNIP the Jacobian is ANALYTIC -- one launch of
+    mt_model_jacobian (the derivative code of the per-pixel refinement kernel, checked against torch.autograd of
+    the reference) gives d model / d parameter for all free parameters, projected orthogonally to the unclamped
+    basis columns (Kaufman's variable-projection Jacobian) -- so an iteration costs one derivative launch plus the
+    trial evaluations instead of 1 + len(free) evaluations.  With SNIP, escape peaks or the l1_lambda penalty the
+    residual is differenced as a whole (forward differences).
 
     ``loss="l1"`` wraps that in iteratively re-weighted rounds (weights 1/max(|res|, eps), eps annealed);
     the ``l1_lambda`` penalty c*sum(A) enters the amplitude solve as a shifted right-hand side and the
@@ -285,7 +285,10 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     active = [k for k, name in enumerate(free) if name in _native.THETA_IDS]
     # analytic Jacobian (mt_model_jacobian) wherever the device model is the whole model: no escape peaks, no penalty
     # entries in the residual vector; otherwise forward differences (1 + len(free) evaluations per iteration)
-    analytic = escape_factor == 0.0 and not (l1_lambda > 0) and len(active) <= _native.MT_MAX_THETA
+    # ... and no SNIP: the background follows the width and energy-axis parameters through integer window tables, a
+    # dependence of the objective that only a finite difference of the WHOLE residual sees (measured on BASELINE
+    # config 1: final loss 7.6e5 with forward differences, 1.4e6 with the model-only Jacobian, reference 9.3e5)
+    analytic = (escape_factor == 0.0 and not (l1_lambda > 0) and len(active) <= _native.MT_MAX_THETA and not use_snip)
 
     state = {"fd": not analytic}
 
@@ -346,7 +349,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                     lam *= 10
                     continue
                 longest = float(np.max(np.abs(step))) if step.size else 0.0
-                clipped = longest > radius
+                clipped = longest > radius and not state["fd"]  # trust region: analytic mode only
                 if clipped:
                     step = step * (radius / longest)
                 cand = np.clip(theta + step * scale, lo, hi)
