@@ -77,7 +77,9 @@ typedef struct MtPeers {
     /* "component owner" exchange: component e of pixel p is additionally stored to owner_row[e][p]
      * (NULL: no extra store), a row of the buffer of the GPU that assembles the full map of e.  Every GPU
      * then receives only its own components from the others: a balanced all-to-all, (N-1)/N of the map
-     * bytes per GPU instead of N-1 times at a single root. */
+     * bytes per GPU instead of N-1 times at a single root.  With n_owned > 0 the final amplitudes are stored to
+     * the owner rows ONLY (give a row for every component, the local GPU's own included); x_dev then just
+     * carries the pixels handed to the non-negative solver. */
     float *owner_row[MT_MAX_OWNED];
 } MtPeers;
 
@@ -228,6 +230,17 @@ int mt_nnls_list(float *x_dev, int64_t ld_x, int32_t x_layout, const int32_t *li
                  int32_t short_list,
                  int32_t n_comp, const double *g_dev, const double *hinv_dev,
                  const MtPeers *peers_host /* optional */, void *stream);
+
+/* Channel-first slabs (raw XRF-Maps MAPS/Spectra/mca_arr is [C][H][W]; create_dataset moves the energy axis last on
+ * the host, io.py:154-156): dst[p * ld_dst + c] = src[c * ld_src + p] for c < n_ch, p < n_px, same dtype. */
+int mt_transpose_cf(const void *src_dev, int32_t dtype, int32_t n_ch, int64_t n_px, int64_t ld_src, void *dst_dev,
+                    int64_t ld_dst, void *stream);
+
+/* Integrated spectrum (MAPS/int_spec, io.py:159): acc_dev[c] += sum_p spec[p * ld_spec + c], fp64 accumulators
+ * (exact and order-independent for integer counts), accumulated over successive calls (slabs); the caller zeroes
+ * acc_dev first. */
+int mt_int_spec(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t n_ch, double *acc_dev,
+                void *stream);
 
 /* The collective that is left of the map gather once the stores are fused into the fit:
  * mt_peer_signal increments *epoch_dev and publishes it to every rank's flag array after everything queued on

@@ -327,7 +327,10 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                         for (int e = 0; e < 32; ++e) {
                             if (e < p.n_comp) {
                                 const long long at = (long long)e * p.ld_x + px;
-                                p.x[at] = xv[mt][e];
+                                // component-owner exchange: final values live on the owners only; the local array
+                                // carries just the pixels that still go to the general solver (it reads them there).
+                                // One store per value instead of two: the epilogue has to keep pace with the MMAs.
+                                if (p.peers.n_owned == 0 || negative) p.x[at] = xv[mt][e];
                                 // Remote copies only of FINAL values: a pixel that still goes to the general
                                 // solver is pushed by that kernel, so no destination ever sees two stores
                                 // to the same address from different kernels.

@@ -75,7 +75,8 @@ class PeerMaps:
     ``barrier()`` then orders the remote stores before anybody reads ``maps.full``.
 
     mode "owner"     : component e is assembled on rank e % world (its "owner"): every rank stores its
-                       pixels of component e into the owner's buffer, a balanced all-to-all in which
+                       pixels of component e into the owner's buffer (and ONLY there: ``local`` is scratch
+                       for the non-negative solver in this mode), a balanced all-to-all in which
                        each GPU receives (world-1)/world of ONE share of the maps instead of world-1
                        shares at a single root.  ``owned`` lists this rank's components, ``full`` is
                        [ceil(E/world), P_total] with row j = component owned[j].
@@ -197,16 +198,24 @@ class PeerMaps:
     def signal(self, stream=None):
         """Publish "everything this rank has stored so far (on `stream`) has landed" to every rank."""
         import ctypes
+        import os
 
         from mapstorch_b200 import _native
+
+        if os.environ.get("MT_PEER_SYNC", "") == "none":  # measurement knob: what the signalling costs
+            return
 
         _native.call("mt_peer_signal", ctypes.byref(self.sync), self._epoch.data_ptr(), _native.stream_ptr(stream))
 
     def wait(self, lag=0, stream=None):
         """Block `stream` until every rank has signalled (this rank's count - lag) times."""
         import ctypes
+        import os
 
         from mapstorch_b200 import _native
+
+        if os.environ.get("MT_PEER_SYNC", "") in ("none", "signal"):
+            return
 
         _native.call("mt_peer_wait", ctypes.byref(self.sync), self._epoch.data_ptr(), int(lag),
                      self._timed_out.data_ptr(), _native.stream_ptr(stream))

@@ -69,6 +69,77 @@ def read_dataset(file_path, spec_vol_key=None, fit_elem_key=None, int_spec_key=N
     return {"spec_vol": spec_vol, "elems": elems, "int_spec": int_spec}
 
 
+class DatasetHandle:
+    """A dataset file opened for streaming (``open_dataset``).
+
+    ``volume`` is the spectral volume as a LAZILY read array -- an h5py dataset, a memory-mapped ``.npy`` file, or
+    (``.npz``: NumPy archives cannot be mapped) the loaded member -- in the layout it is stored in: ``energy_dim`` = 2
+    for files written by ``create_dataset`` (``MAPS/mca_arr``, [H, W, C]), 0 for raw XRF-Maps files
+    (``MAPS/Spectra/mca_arr``, [C, H, W]).  ``opt.fit_map(handle.volume, ..., energy_dim=handle.energy_dim)`` or
+    ``opt.fit_dataset(path, ...)`` stream it through the GPU slab by slab."""
+
+    def __init__(self, volume, energy_dim, elems, int_spec, closer=None):
+        self.volume, self.energy_dim, self.elems, self.int_spec, self._closer = volume, energy_dim, elems, int_spec, closer
+
+    @property
+    def shape(self):
+        return tuple(int(v) for v in self.volume.shape)
+
+    @property
+    def map_shape(self):
+        s = self.shape
+        return (s[1], s[2]) if self.energy_dim == 0 else (s[0], s[1])
+
+    @property
+    def n_channels(self):
+        return self.shape[0] if self.energy_dim == 0 else self.shape[2]
+
+    def close(self):
+        if self._closer is not None:
+            self._closer()
+            self._closer = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def open_dataset(file_path, spec_vol_key=None, fit_elem_key=None, int_spec_key=None, energy_dim=None):
+    """Open a dataset for streaming: the keys and fallbacks of read_dataset (io.py:63-112), but the volume is not read.
+    A bare ``.npy`` file is taken as the volume itself.  energy_dim: axis holding the channels; default 0 when the
+    volume is found under ``MAPS/Spectra/mca_arr`` (the raw XRF-Maps layout), 2 otherwise."""
+    path = str(file_path)
+    if path.endswith(".npy"):
+        vol = np.load(path, mmap_mode="r")
+        return DatasetHandle(vol, 2 if energy_dim is None else int(energy_dim), None, None)
+    handle = _open(path, "r")
+    store = handle if handle is not None else np.load(path, allow_pickle=False)
+    keys = (spec_vol_key,) if spec_vol_key is not None else _VOL_KEYS
+    vol, found = None, None
+    for key in keys:
+        try:
+            vol = store[key]
+            found = key
+            break
+        except Exception:
+            continue
+    if vol is None:
+        store.close()
+        raise KeyError(f"Could not find spectra volume in the dataset (keys tried: {', '.join(map(str, keys))})")
+    elems = _lookup(store, fit_elem_key, _ELEM_KEYS, "fitting elements") if (fit_elem_key or any(k in store for k in _ELEM_KEYS)) else None
+    int_spec = _lookup(store, int_spec_key, _INT_KEYS, "integrated spectra") if (int_spec_key or any(k in store for k in _INT_KEYS)) else None
+    if elems is not None:
+        elems = [e.decode("utf-8") if isinstance(e, bytes) else str(e) for e in elems]
+        for name in _SCATTER:
+            if name not in elems:
+                elems.append(name)
+    if energy_dim is None:
+        energy_dim = 0 if str(found).endswith("Spectra/mca_arr") else 2
+    return DatasetHandle(vol, int(energy_dim), elems, int_spec, closer=store.close)
+
+
 def create_dataset(spec_vol, energy_dim, output_path, fit_elems=None, dtype=np.float32, compression="gzip",
                    compression_opts=4):
     """Write a dataset readable by read_dataset; `energy_dim` says which axis holds the channels."""

@@ -480,27 +480,30 @@ class MapFitPlan:
         return out
 
 
-def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0, after_slab=None):
-    """Stream a HOST volume [P, C] through the device in row slabs: slab k+1 is copied
-    host->device on a second stream while slab k is being fitted (pinned host memory makes the
-    copies asynchronous).  Returns x [E, P] on the device.
+def _fit_slabs(self, n_px, n_ch, dtype, load, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0, after_slab=None,
+               int_spec=None):
+    """Stream a volume that is NOT resident on the device through it in slabs of pixels: `load(p0, n, dst)` brings
+    pixels [p0, p0 + n) into the device buffer dst [n, n_ch] (energy last) on the current stream -- a host-to-device
+    copy, plus the transposition of a channel-first slab.  Slab k+1 is loaded on a second stream while slab k is
+    being fitted.  Returns x [E, P] on the device.
 
     after_slab(dev_slab, p0, n, x_slab), if given, runs on the compute stream right after the fit of each
-    slab while the slab is still resident (per-pixel refinement uses it), so the volume crosses PCIe once."""
-    n_px, n_ch = host2d.shape
+    slab while the slab is still resident (per-pixel refinement uses it), so the volume crosses PCIe once.
+    int_spec: optional fp64 [n_ch] device accumulator; the integrated spectrum (io.py:159) is summed slab by slab
+    as a by-product of the pass (mt_int_spec)."""
     out = torch.zeros((len(self.names), n_px), dtype=torch.float32, device="cuda")
     chunk = max(1, min(int(chunk_px), n_px))
     compute = torch.cuda.current_stream()
     copier = torch.cuda.Stream()
-    bufs = [torch.empty((chunk, n_ch), dtype=host2d.dtype, device="cuda") for _ in range(2)]
+    bufs = [torch.empty((chunk, n_ch), dtype=dtype, device="cuda") for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     # fp32 volumes without SNIP: the operand-exactness check (counts < 2048) must not stall the pipeline, so
     # every slab is fitted optimistically, its maximum lands in a device flag, and the (rare) slabs that turn
     # out to hold larger counts are redone through the exact split path after ONE synchronisation at the end
-    check = host2d.dtype == torch.float32 and not self.use_snip and engine == "tensor"
+    check = dtype == torch.float32 and not self.use_snip and engine == "tensor"
     # SNIP path, fp32 volumes: the fp16 residual planes overflow beyond 65504 counts; same deferred treatment
-    snip_check = host2d.dtype == torch.float32 and self.use_snip and engine == "tensor" and self.snip_planes == "f16"
+    snip_check = dtype == torch.float32 and self.use_snip and engine == "tensor" and self.snip_planes == "f16"
     starts = list(range(0, n_px, chunk))
     too_big = torch.zeros(len(starts), dtype=torch.int32, device="cuda") if (check or snip_check) else None
     for i, p0 in enumerate(starts):
@@ -508,9 +511,12 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
         with torch.cuda.stream(copier):
             if i >= 2:
                 copier.wait_event(consumed[b])
-            bufs[b][:n].copy_(host2d[p0: p0 + n], non_blocking=True)
+            load(p0, n, bufs[b][:n])
             copied[b].record(copier)
         compute.wait_event(copied[b])
+        if int_spec is not None:
+            _native.call("mt_int_spec", bufs[b].data_ptr(), _native.dtype_code(dtype), n, bufs[b].stride(0), n_ch,
+                         int_spec.data_ptr(), _native.stream_ptr())
         if check:
             self._operand_inexact(bufs[b][:n], too_big[i: i + 1])
         self.fit(bufs[b][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine,
@@ -523,7 +529,7 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
         for i in torch.nonzero(too_big).flatten().tolist():
             p0 = starts[i]
             n = min(chunk, n_px - p0)
-            bufs[0][:n].copy_(host2d[p0: p0 + n])
+            load(p0, n, bufs[0][:n])
             self.fit(bufs[0][:n], out=out[:, p0: p0 + n], nonneg=nonneg, engine=engine, exact_counts="split",
                      l1_lambda=l1_lambda)
             if after_slab is not None:
@@ -531,6 +537,93 @@ def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lam
     for buf in bufs:
         buf.record_stream(compute)
     return out
+
+
+def _fit_host(self, host2d, nonneg=True, engine="tensor", chunk_px=16384, l1_lambda=0.0, after_slab=None, int_spec=None):
+    """Stream a HOST volume [P, C] (energy last) through the device in row slabs (pinned host memory makes the
+    copies asynchronous); see fit_slabs."""
+    n_px, n_ch = host2d.shape
+
+    def load(p0, n, dst):
+        dst.copy_(host2d[p0: p0 + n], non_blocking=True)
+
+    return self.fit_slabs(n_px, n_ch, host2d.dtype, load, nonneg, engine, chunk_px, l1_lambda, after_slab, int_spec)
+
+
+class ChannelFirstLoader:
+    """load() of fit_slabs for volumes stored channel-first, [C, H, W] (raw XRF-Maps MAPS/Spectra/mca_arr): a slab of
+    whole rows [C, rows, W] is staged in pinned memory (that is where a memory-mapped file is actually read), copied
+    to the device and transposed there to [rows * W, C] (mt_transpose_cf) -- the reference does this on the host with
+    np.moveaxis over the whole volume (io.py:154-156).  `source[c, r0:r1, :]` may be a NumPy array / memmap, an
+    h5py dataset or a torch tensor (host or CUDA)."""
+
+    def __init__(self, source, n_rows, width, n_ch, dtype, rows_per_slab):
+        self.source, self.n_rows, self.width, self.n_ch, self.dtype = source, n_rows, width, n_ch, dtype
+        self.rows = max(1, int(rows_per_slab))
+        self.on_device = isinstance(source, torch.Tensor) and source.is_cuda
+        self._stage, self._pinned, self._turn = None, None, 0
+        self._staged = [None, None]
+
+    @property
+    def chunk_px(self):
+        return self.rows * self.width
+
+    def __call__(self, p0, n, dst):
+        r0, rows = p0 // self.width, n // self.width
+        assert p0 % self.width == 0 and n % self.width == 0, "channel-first slabs are whole rows"
+        if self.on_device:
+            src = self.source[:, r0: r0 + rows, :]
+            flat, ld = src, self.source.stride(0)
+            ptr = src.data_ptr()
+        else:
+            if self._stage is None:
+                self._stage = [torch.empty((self.n_ch, self.rows * self.width), dtype=self.dtype, device="cuda") for _ in range(2)]
+                self._pinned = [torch.empty((self.n_ch, self.rows * self.width), dtype=self.dtype, pin_memory=True)
+                                for _ in range(2)]
+            t = self._turn
+            self._turn ^= 1
+            if self._staged[t] is not None:
+                self._staged[t].synchronize()  # the pinned buffer's previous copy has left the host
+            pinned = self._pinned[t][:, :n].reshape(self.n_ch, rows, self.width)
+            block = self.source[:, r0: r0 + rows, :]
+            pinned.copy_(block if isinstance(block, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(block)))
+            stage = self._stage[t][:, :n]
+            stage.copy_(self._pinned[t][:, :n], non_blocking=True)
+            self._staged[t] = torch.cuda.Event()
+            self._staged[t].record()
+            ptr, ld = stage.data_ptr(), self._stage[t].stride(0)
+        _native.call("mt_transpose_cf", ptr, _native.dtype_code(self.dtype), self.n_ch, n, ld, dst.data_ptr(),
+                     dst.stride(0), _native.stream_ptr())
+
+
+class RowLoader:
+    """load() of fit_slabs for energy-last volumes [H, W, C] that are read lazily (np.memmap, h5py dataset): each slab
+    of whole rows is read into pinned memory -- the file is touched here, slab by slab, never as a whole -- and copied
+    to the device asynchronously."""
+
+    def __init__(self, source, n_rows, width, n_ch, dtype, rows_per_slab):
+        self.source, self.n_rows, self.width, self.n_ch, self.dtype = source, n_rows, width, n_ch, dtype
+        self.rows = max(1, int(rows_per_slab))
+        self._pinned, self._turn, self._staged = None, 0, [None, None]
+
+    @property
+    def chunk_px(self):
+        return self.rows * self.width
+
+    def __call__(self, p0, n, dst):
+        r0, rows = p0 // self.width, n // self.width
+        assert p0 % self.width == 0 and n % self.width == 0, "file slabs are whole rows"
+        if self._pinned is None:
+            self._pinned = [torch.empty((self.rows * self.width, self.n_ch), dtype=self.dtype, pin_memory=True) for _ in range(2)]
+        t = self._turn
+        self._turn ^= 1
+        if self._staged[t] is not None:
+            self._staged[t].synchronize()
+        block = np.asarray(self.source[r0: r0 + rows]).reshape(n, self.n_ch)
+        self._pinned[t][:n].copy_(torch.from_numpy(np.ascontiguousarray(block)))
+        dst.copy_(self._pinned[t][:n], non_blocking=True)
+        self._staged[t] = torch.cuda.Event()
+        self._staged[t].record()
 
 
 def _make_graph(self, spec2d, out, nonneg=True, engine="tensor"):
@@ -559,6 +652,7 @@ def _to_host(self, x):
     return host
 
 
+MapFitPlan.fit_slabs = _fit_slabs
 MapFitPlan.fit_host = _fit_host
 MapFitPlan.make_graph = _make_graph
 MapFitPlan.to_host = _to_host
@@ -593,7 +687,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
             fixed_param_vals={}, indices=None, use_snip=True, e_consts=default_energy_consts,
             elem_info=default_elem_info, detector_type="Si", escape_factor=0.0, nonneg=True, as_log10=False,
             device="cuda", engine="tensor", plan=None, return_plan=False, chunk_px=16384, refine=None,
-            refine_iters=12, refine_bounds=None, loss="mse", l1_lambda=0.0, group=None, gather="all"):
+            refine_iters=12, refine_bounds=None, loss="mse", l1_lambda=0.0, group=None, gather="all", energy_dim=2,
+            rows_per_slab=None, int_spec=False):
     """Fit every pixel of spec_vol[..., C] with the global parameters held fixed.
 
     Equivalent to calling the reference's ``fit_spec(spec_vol[i, j], energy_range, elements_to_fit,
@@ -612,6 +707,15 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
 
     l1_lambda: the reference's sparsity penalty on the amplitudes (opt.py:372-396), per pixel.  loss="l1" is
     available for single spectra (fit_spec); per-pixel L1 maps are not built.
+
+    energy_dim: axis of spec_vol that holds the channels.  2 (default) is the layout create_dataset stores
+    (io.py:154-156); 0 is the channel-first layout of raw XRF-Maps files (MAPS/Spectra/mca_arr, [C, H, W]): row slabs
+    are then transposed on the device (mt_transpose_cf) instead of the reference's np.moveaxis over the whole volume on
+    the host.  spec_vol may also be a lazily read array (np.memmap, h5py dataset, io.open_dataset(...).volume): it is
+    streamed from the file slab by slab (rows_per_slab rows at a time), never loaded as a whole.
+
+    int_spec=True adds "int_spec" to the result: the integrated spectrum over all pixels (io.py:159), summed on the
+    device as a by-product of the streaming pass (fp64 accumulators; fp32 [C] result).
 
     group: a torch.distributed process group (one rank per GPU).  spec_vol is then THIS rank's block of rows of a
     row-sharded grid (dist.shard_rows) and the returned maps cover the whole grid: every component on every rank
@@ -633,17 +737,53 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
                                use_snip=use_snip, e_consts=e_consts, elem_info=elem_info, detector_type=detector_type,
                                escape_factor=escape_factor, nonneg=nonneg, l1_lambda=l1_lambda)
         return maps if torch.device(device).type == "cuda" else {k: v.cpu() for k, v in maps.items()}
-    if not isinstance(spec_vol, torch.Tensor):
-        arr = np.asarray(spec_vol)
-        if arr.dtype not in (np.float32, np.float16):
-            arr = arr.astype(np.float32)
-        spec_vol = torch.from_numpy(arr)
-    if spec_vol.dtype not in (torch.float32, torch.float16):
-        spec_vol = spec_vol.to(torch.float32)
-    lead = spec_vol.shape[:-1]
-    flat = spec_vol.reshape(-1, spec_vol.shape[-1])
-    if flat.stride(1) != 1:
-        flat = flat.contiguous()
+    if energy_dim not in (0, 1, 2):
+        raise ValueError("energy_dim must be 0, 1, or 2")
+    lazy = not isinstance(spec_vol, (torch.Tensor, np.ndarray)) or isinstance(spec_vol, np.memmap)
+    if lazy and not (hasattr(spec_vol, "shape") and hasattr(spec_vol, "dtype") and len(spec_vol.shape) == 3):
+        lazy = False
+    loader = None
+    if lazy or energy_dim == 0:
+        # streamed sources: lazily read files (either layout) and channel-first volumes wherever they live
+        if energy_dim == 1:
+            raise NotImplementedError("energy_dim=1 for lazily read volumes; convert with io.create_dataset first")
+        if isinstance(spec_vol, np.ndarray) and not isinstance(spec_vol, np.memmap):
+            if spec_vol.dtype not in (np.float32, np.float16):
+                spec_vol = spec_vol.astype(np.float32)
+            spec_vol = torch.from_numpy(spec_vol)
+        np_dtype = np.dtype(spec_vol.dtype) if not isinstance(spec_vol, torch.Tensor) else None
+        if isinstance(spec_vol, torch.Tensor):
+            if spec_vol.dtype not in (torch.float32, torch.float16):
+                spec_vol = spec_vol.to(torch.float32)
+            t_dtype = spec_vol.dtype
+        else:
+            t_dtype = torch.float16 if np_dtype == np.float16 else torch.float32
+            if np_dtype not in (np.float16, np.float32):
+                raise NotImplementedError(f"lazily read volumes must be stored as float16 or float32, not {np_dtype}")
+        shape = tuple(int(v) for v in spec_vol.shape)
+        if energy_dim == 0:
+            n_ch_all, n_rows, width = shape
+        else:
+            n_rows, width, n_ch_all = shape
+        lead = (n_rows, width)
+        rows = rows_per_slab or max(1, int(chunk_px) // max(width, 1))
+        cls = ChannelFirstLoader if energy_dim == 0 else RowLoader
+        loader = cls(spec_vol, n_rows, width, n_ch_all, t_dtype, min(rows, n_rows))
+        flat = None
+    else:
+        if not isinstance(spec_vol, torch.Tensor):
+            arr = np.asarray(spec_vol)
+            if arr.dtype not in (np.float32, np.float16):
+                arr = arr.astype(np.float32)
+            spec_vol = torch.from_numpy(arr)
+        if spec_vol.dtype not in (torch.float32, torch.float16):
+            spec_vol = spec_vol.to(torch.float32)
+        if energy_dim == 1:
+            spec_vol = spec_vol.movedim(1, 2)
+        lead = spec_vol.shape[:-1]
+        flat = spec_vol.reshape(-1, spec_vol.shape[-1])
+        if flat.stride(1) != 1:
+            flat = flat.contiguous()
     if plan is None:
         params = dict(init_param_vals)
         params.update(fixed_param_vals)
@@ -656,7 +796,7 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         # neither a host volume nor the SNIP background has to be resident as a whole
         from mapstorch_b200.refine import refine_map
 
-        n_px = flat.shape[0]
+        n_px = flat.shape[0] if flat is not None else lead[0] * lead[1]
         theta = torch.empty((len(refine), n_px), dtype=torch.float32, device="cuda")
         loss_px = torch.empty(n_px, dtype=torch.float32, device="cuda")
         iters = torch.empty(n_px, dtype=torch.int32, device="cuda")
@@ -673,7 +813,17 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
 
         extra = {name: theta[i] for i, name in enumerate(refine)}
         extra["loss"], extra["iterations"] = loss_px, iters
-    if flat.device.type == "cuda":
+    acc = None
+    if int_spec:
+        n_all = loader.n_ch if loader is not None else flat.shape[1]
+        acc = torch.zeros(n_all, dtype=torch.float64, device="cuda")
+    if loader is not None:
+        x = plan.fit_slabs(lead[0] * lead[1], loader.n_ch, loader.dtype, loader, nonneg=nonneg, engine=engine,
+                           chunk_px=loader.chunk_px, l1_lambda=l1_lambda, after_slab=refine_slab, int_spec=acc)
+    elif flat.device.type == "cuda":
+        if acc is not None:
+            _native.call("mt_int_spec", flat.data_ptr(), _native.dtype_code(flat.dtype), flat.shape[0], flat.stride(0),
+                         flat.shape[1], acc.data_ptr(), _native.stream_ptr())
         x = plan.fit(flat, nonneg=nonneg, engine=engine, l1_lambda=l1_lambda)
         if refine_slab is not None:
             for p0 in range(0, flat.shape[0], SNIP_CHUNK_PX):
@@ -683,7 +833,7 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         # the slab is fitted and refined while it is resident: the volume crosses PCIe once, and the next slab's
         # copy overlaps both kernels
         x = plan.fit_host(flat, nonneg=nonneg, engine=engine, chunk_px=chunk_px, l1_lambda=l1_lambda,
-                          after_slab=refine_slab)
+                          after_slab=refine_slab, int_spec=acc)
     if as_log10:
         x = torch.log10(x)
     if torch.device(device).type != "cuda":
@@ -692,7 +842,28 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     for name, val in extra.items():
         val = val if torch.device(device).type == "cuda" else val.cpu()
         maps[name] = val.reshape(lead)
+    if acc is not None:
+        maps["int_spec"] = acc.float() if torch.device(device).type == "cuda" else acc.float().cpu()
     return (maps, plan) if return_plan else maps
+
+
+def fit_dataset(file_path, energy_range, elements_to_fit=None, spec_vol_key=None, energy_dim=None, rows_per_slab=None,
+                int_spec=True, device="cpu", **fit_map_kw):
+    """Fit every pixel of a dataset FILE (io.open_dataset: HDF5 via h5py, .npy, .npz) without loading it: row slabs are
+    read into pinned memory, copied to the device while the previous slab is being fitted, transposed there if the
+    file is channel-first, and the integrated spectrum is accumulated on the way.  elements_to_fit defaults to the
+    channel names stored in the file.  Returns fit_map's dictionary (+ "int_spec")."""
+    from mapstorch_b200 import io as _io
+
+    with _io.open_dataset(file_path, spec_vol_key=spec_vol_key, energy_dim=energy_dim) as handle:
+        if elements_to_fit is None:
+            elements_to_fit = [e for e in (handle.elems or default_fitting_elems)
+                               if e not in ("COHERENT_SCT_AMPLITUDE", "COMPTON_AMPLITUDE")]
+        vol = handle.volume
+        if not isinstance(vol, np.memmap) and isinstance(vol, np.ndarray):
+            vol = torch.from_numpy(vol if vol.dtype in (np.float32, np.float16) else vol.astype(np.float32))
+        return fit_map(vol, energy_range, elements_to_fit, energy_dim=handle.energy_dim, rows_per_slab=rows_per_slab,
+                       int_spec=int_spec, device=device, **fit_map_kw)
 
 
 def fit_spec(int_spec, energy_range, elements_to_fit=default_fitting_elems, fitting_params=default_fitting_params,

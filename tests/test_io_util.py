@@ -47,3 +47,22 @@ def test_scatter_peak_heuristic_recovers_slope_and_angle():
     assert util.estimate_and_update_params([], (0, 10), 12.0) == {}
     assert util.get_channel_from_energy(6.4, np.linspace(0, 12, 1201)) == 640
     assert util.get_channel_from_energy(99.0, np.linspace(0, 12, 1201)) == 1200
+
+
+def test_open_dataset_is_lazy_and_knows_the_layout(tmp_path):
+    from mapstorch_b200 import io as mio
+
+    vol = np.random.default_rng(0).poisson(5, size=(6, 7, 64)).astype(np.float32)
+    path = tmp_path / "a.npz"
+    mio.create_dataset(vol, 2, str(path), fit_elems=["Fe", "Cu"])
+    with mio.open_dataset(str(path)) as h:
+        assert h.shape == (6, 7, 64) and h.energy_dim == 2 and h.map_shape == (6, 7) and h.n_channels == 64
+        assert h.elems == ["Fe", "Cu", "COHERENT_SCT_AMPLITUDE", "COMPTON_AMPLITUDE"]
+        assert np.allclose(h.int_spec, vol.sum(axis=(0, 1)))
+    raw = tmp_path / "b.npy"
+    np.save(raw, np.moveaxis(vol, 2, 0))
+    with mio.open_dataset(str(raw), energy_dim=0) as h:
+        assert isinstance(h.volume, np.memmap) and h.map_shape == (6, 7) and h.n_channels == 64
+        assert np.array_equal(np.asarray(h.volume[:, 2:4, :]), np.moveaxis(vol, 2, 0)[:, 2:4, :])
+    with pytest.raises(KeyError):
+        mio.open_dataset(str(path), spec_vol_key="MAPS/none")
