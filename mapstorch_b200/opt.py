@@ -369,16 +369,36 @@ class MapFitPlan:
                     self._last_snip_half = False
                     run_chunks(starts, False)
         if nonneg and n_px:
-            if self._last_engine == "tensor" and neg is not None:
-                _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
-                             int(self.epilogue_fixup and self.e_pad <= 32), self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
-                             ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
-                if n_fixed is not None:
-                    n_fixed.copy_(neg[1])
-            else:
-                _native.call("mt_nnls_fixup", *self._x_args(x), n_px, self.n_live, self.gram_dev.data_ptr(),
-                             self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
-                             ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
+            self._nonneg_tail(x, n_px, neg, n_fixed, peers, stream)
+
+    def _nonneg_tail(self, x, n_px, neg, n_fixed, peers, stream):
+        """Batched non-negative solve after a contraction: driven by the pixel list the K3 epilogue compacted (neg),
+        or a scan of all pixels."""
+        if self._last_engine == "tensor" and neg is not None:
+            _native.call("mt_nnls_list", *self._x_args(x), neg[0].data_ptr(), neg[1].data_ptr(),
+                         int(self.epilogue_fixup and self.e_pad <= 32), self.n_live, self.gram_dev.data_ptr(), self.hinv_dev.data_ptr(),
+                         ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
+            if n_fixed is not None:
+                n_fixed.copy_(neg[1])
+        else:
+            _native.call("mt_nnls_fixup", *self._x_args(x), n_px, self.n_live, self.gram_dev.data_ptr(),
+                         self.hinv_dev.data_ptr(), n_fixed.data_ptr() if n_fixed is not None else None,
+                         ctypes.byref(peers) if peers is not None else None, _native.stream_ptr(stream))
+
+    def fit_operand_hilo(self, q2d, x, nonneg=True, stream=None):
+        """x [n_live, P] <- (non-negative) least squares of a target given as operand planes q2d [P, 2 * n_ch] fp32
+        (tf32-exact high part | remainder, the layout of MT_SNIP_RESIDUAL_HILO): contraction on the tensor cores +
+        fix-up.  The x-update of the per-pixel loss="l1" iteration (robust.fit_map_lad)."""
+        n_px = q2d.shape[0]
+        self._pixel_major = False
+        neg = None
+        if nonneg and n_px and len(self.groups) == 1:
+            neg = self._neg_buffers(n_px)
+            neg[1].zero_()
+        self._contract(q2d, x, 0, 2, 0, 2 * self.n_ch, "tensor", stream, neg, 0, None)
+        if nonneg and n_px:
+            self._nonneg_tail(x, n_px, neg, None, None, stream)
+        return x
 
     def _fit_pipelined(self, spec2d, x, n_fixed, peers, rounds_per_chunk=4):
         """Contraction and non-negative solve overlapped: the volume is cut into chunks of whole
@@ -705,8 +725,10 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     FWHM_FANOPRIME) to free PER PIXEL together with the amplitudes, like fit_spec(fitting_params=refine,
     tune_params=True) per pixel; their maps, the final "loss" and "iterations" are added to the result.
 
-    l1_lambda: the reference's sparsity penalty on the amplitudes (opt.py:372-396), per pixel.  loss="l1" is
-    available for single spectra (fit_spec); per-pixel L1 maps are not built.
+    l1_lambda: the reference's sparsity penalty on the amplitudes (opt.py:372-396), per pixel.
+    loss="l1": the sum of absolute residuals instead of squares (opt.py:232-233, 371-375) for every pixel: ADMM whose
+    x-update is the ordinary tensor-core map fit of a modified target (robust.fit_map_lad, csrc/mt_lad.cu); the
+    per-pixel objective comes back as "loss".
 
     energy_dim: axis of spec_vol that holds the channels.  2 (default) is the layout create_dataset stores
     (io.py:154-156); 0 is the channel-first layout of raw XRF-Maps files (MAPS/Spectra/mca_arr, [C, H, W]): row slabs
@@ -721,8 +743,10 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     row-sharded grid (dist.shard_rows) and the returned maps cover the whole grid: every component on every rank
     (gather="all"), each rank's own components ("owner": component e on rank e % world) or everything on rank 0
     ("root").  The exchange is fused into the fit kernels (peer stores over NVLink), see dist.ShardedMapFit."""
-    if loss != "mse":
-        raise NotImplementedError('fit_map minimises the MSE objective; loss="l1" exists for fit_spec only')
+    if loss not in ("mse", "l1"):
+        raise ValueError("Loss function not supported")
+    if loss == "l1" and (l1_lambda > 0 or refine or group is not None or energy_dim != 2):
+        raise NotImplementedError('fit_map(loss="l1") is the plain per-pixel L1 fit (no l1_lambda / refine / group / energy_dim)')
     _native.require_device()
     if group is not None:
         # multi-GPU form: spec_vol is this rank's block of rows; maps of the whole grid come back (dist.py)
@@ -813,6 +837,17 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
 
         extra = {name: theta[i] for i, name in enumerate(refine)}
         extra["loss"], extra["iterations"] = loss_px, iters
+    if loss == "l1":
+        # sum of absolute residuals per pixel (opt.py:232-233): ADMM around the same contraction, robust.fit_map_lad
+        from mapstorch_b200 import robust
+
+        x, objective = robust.fit_map_lad(plan, flat, nonneg=nonneg)
+        if as_log10:
+            x = torch.log10(x)
+        on_dev = torch.device(device).type == "cuda"
+        maps = {name: (x[i] if on_dev else x[i].cpu()).reshape(lead) for i, name in enumerate(plan.names)}
+        maps["loss"] = (objective if on_dev else objective.cpu()).reshape(lead)
+        return (maps, plan) if return_plan else maps
     acc = None
     if int_spec:
         n_all = loader.n_ch if loader is not None else flat.shape[1]
