@@ -245,12 +245,14 @@ int mt_int_spec(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_sp
 /* Per-pixel loss="l1" maps (opt.py:232-233, 371-375) by ADMM on z = model - target; see csrc/mt_lad.cu.  For every
  * pixel p and channel c < n_ch (row pitches ld_*, element-major x_dev [n_comp][ld_x], basis_dev [n_comp][ld_b] fp32):
  *   m = sum_e x[e][p] basis[e][c],  r = m - t[p][c],  obj_dev[p] = sum_c |r|   (optional output: the L1 objective of x)
- * and, with mode = 1:  v = r + u;  z = soft(v, kappa_dev[p]);  u <- v - z;  q[p][c], q[p][n_ch + c] <- t + z - u split
- * into a tf32-exact high part and remainder -- the operand of the next x-update (mt_fit_contract over 2 n_ch columns
- * with the pack repeated twice, then the non-negative fix-up).  mode = 0 only evaluates the objective. */
+ * and, with mode = 1:  v = r + u;  z = soft(v, kappa_dev[p]);  u <- v - z;  target = t + z - u;  dq = target -
+ * qstate[p][c];  qstate <- target;  q[p][c], q[p][n_ch + c] <- dq split into a tf32-exact high part and remainder -- the
+ * operand of the next x-update: xu += mt_fit_contract(dq) (2 n_ch columns, pack repeated twice, no fix-up), then the
+ * non-negative fix-up of a copy of xu.  qstate starts as t with xu the least-squares solution of t.  mode = 0 only
+ * evaluates the objective. */
 int mt_lad_update(const float *t_dev, int64_t ld_t, const float *x_dev, int64_t ld_x, const float *basis_dev, int64_t ld_b,
                   int32_t n_comp, int32_t n_ch, int64_t n_px, float *u_dev, int64_t ld_u, const float *kappa_dev,
-                  float *q_dev, int64_t ld_q, float *obj_dev, int32_t mode, void *stream);
+                  float *qstate_dev, int64_t ld_qs, float *q_dev, int64_t ld_q, float *obj_dev, int32_t mode, void *stream);
 
 /* The collective that is left of the map gather once the stores are fused into the fit:
  * mt_peer_signal increments *epoch_dev and publishes it to every rank's flag array after everything queued on

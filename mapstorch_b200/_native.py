@@ -92,7 +92,7 @@ SIGNATURES = {
     "mt_peer_wait": [_vp, _vp, _i32, _vp, _vp],
     "mt_transpose_cf": [_vp, _i32, _i32, _i64, _i64, _vp, _i64, _vp],
     "mt_int_spec": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
-    "mt_lad_update": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _vp],
+    "mt_lad_update": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp],
     "mt_model_jacobian": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
                   _vp, _vp],

@@ -606,7 +606,7 @@ class ChannelFirstLoader:
                 self._staged[t].synchronize()  # the pinned buffer's previous copy has left the host
             pinned = self._pinned[t][:, :n].reshape(self.n_ch, rows, self.width)
             block = self.source[:, r0: r0 + rows, :]
-            pinned.copy_(block if isinstance(block, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(block)))
+            pinned.copy_(block if isinstance(block, torch.Tensor) else torch.from_numpy(np.array(block)))
             stage = self._stage[t][:, :n]
             stage.copy_(self._pinned[t][:, :n], non_blocking=True)
             self._staged[t] = torch.cuda.Event()
@@ -640,7 +640,7 @@ class RowLoader:
         if self._staged[t] is not None:
             self._staged[t].synchronize()
         block = np.asarray(self.source[r0: r0 + rows]).reshape(n, self.n_ch)
-        self._pinned[t][:n].copy_(torch.from_numpy(np.ascontiguousarray(block)))
+        self._pinned[t][:n].copy_(torch.from_numpy(np.array(block)))  # np.array: a writable copy of the mapped pages
         dst.copy_(self._pinned[t][:n], non_blocking=True)
         self._staged[t] = torch.cuda.Event()
         self._staged[t].record()
