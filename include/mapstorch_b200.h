@@ -141,6 +141,25 @@ int mt_snip_scaled(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld
                    const uint32_t *scaled_dev, int32_t ld_scaled, int32_t n_pass, int32_t boxcar, float *out_dev,
                    int64_t ld_out, int32_t out_mode, void *stream);
 
+/* K2b -- the same computation (bit-identical results) for ALIGNED volumes, organised for throughput: contiguous channel
+ * runs per thread (late passes take their neighbours from registers), persistent CTAs that fetch the next four rows by
+ * cp.async.bulk while the current ones are written back, 128-bit global accesses (csrc/mt_snip_runs.cu).
+ * mt_snip_runs_pitch(n_ch): row pitch in words of its table, 0 when n_ch is not served (n_ch % 8 != 0 or n_ch > 4096).
+ * mt_snip_runs_tables: n_pass rows of ld_tabs words built from lohi_dev (gather words as swizzled shared-memory byte
+ * offsets, then one descriptor per run of channels); the kernel stages one row per pass in shared memory.
+ * mt_snip_runs_eligible: 1 when the kernel serves this problem: boxcar == 5, spec_dev / out_dev, the row pitches and the
+ * crop start 16-byte aligned.  mt_snip_runs fails with MT_ERR_UNSUPPORTED otherwise (use mt_snip / mt_snip_scaled).
+ * out_dev / ld_out / out_mode as in mt_snip, plus MT_SNIP_RESIDUAL_HILO_F16 (out_dev fp16, ld_out in fp16 elements,
+ * overflow_dev as in mt_snip_residual_f16; may be NULL for the other modes). */
+int mt_snip_runs_pitch(int32_t n_ch);
+int mt_snip_runs_tables(const uint32_t *lohi_dev, int32_t n_pass, int32_t n_ch, uint32_t *tabs_dev, int32_t ld_tabs,
+                        void *stream);
+int mt_snip_runs_eligible(const void *spec_dev, int32_t dtype, int64_t ld_spec, int32_t ch0, int32_t n_ch, int32_t boxcar,
+                          const void *out_dev, int64_t ld_out, int32_t out_mode);
+int mt_snip_runs(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0, int32_t n_ch,
+                 const uint32_t *tabs_dev, int32_t ld_tabs, int32_t n_pass, int32_t boxcar, void *out_dev, int64_t ld_out,
+                 int32_t out_mode, int32_t *overflow_dev, void *stream);
+
 /* K3 -- the per-pixel amplitude solve: replaces the Adam loop of fit_spec (opt.py:249-317)
  * for fixed global parameters, where the model is linear in the amplitudes.
  *   x[e][p] = colscale[e] * sum_d plane_ratio^d * ( sum_k spec[p][k] * wpack[d*e_pad + e][k] )

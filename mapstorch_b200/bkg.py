@@ -24,11 +24,37 @@ def snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_off
         _native.call("mt_snip_scale_tables", lohi.data_ptr(), tab.shape[0], int(n_ch), scaled.data_ptr(), pitch,
                      _native.stream_ptr())
         lohi._mt_scaled = scaled
+    pitch = _native.load().mt_snip_runs_pitch(int(n_ch))
+    if pitch > 0 and tab.shape[0] > 0:
+        # tables of the contiguous-run kernel (csrc/mt_snip_runs.cu): swizzled gather words + one descriptor per run
+        runs = torch.empty((tab.shape[0], pitch), dtype=torch.int32, device="cuda")
+        _native.call("mt_snip_runs_tables", lohi.data_ptr(), tab.shape[0], int(n_ch), runs.data_ptr(), pitch,
+                     _native.stream_ptr())
+        lohi._mt_runs = runs
     return lohi, tab.shape[0]
+
+
+def _runs_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode, overflow, stream):
+    """Launch the contiguous-run kernel where it applies (aligned rows and crops, n_ch % 8 == 0, boxcar 5); its results
+    are bit-identical to the strided kernel's.  Returns False when the caller has to use the strided kernel."""
+    runs = getattr(lohi_dev, "_mt_runs", None)
+    if runs is None or runs.shape[0] != int(n_pass):
+        return False
+    if not _native.load().mt_snip_runs_eligible(spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.stride(0),
+                                                int(ch0), int(n_ch), int(boxcar_size), out.data_ptr(), out.stride(0),
+                                                int(out_mode)):
+        return False
+    _native.call("mt_snip_runs", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.shape[0], spec2d.stride(0),
+                 int(ch0), int(n_ch), runs.data_ptr(), runs.stride(0), int(n_pass), int(boxcar_size), out.data_ptr(),
+                 out.stride(0), int(out_mode), overflow.data_ptr() if overflow is not None else None,
+                 _native.stream_ptr(stream))
+    return True
 
 
 def snip_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode, stream=None):
     """spec2d: CUDA [P, ld] fp32/fp16 (row-contiguous); out: CUDA fp32 [P, ld_out]."""
+    if _runs_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode, None, stream):
+        return out
     scaled = getattr(lohi_dev, "_mt_scaled", None)
     if scaled is not None and scaled.shape[0] == int(n_pass) + 1:
         _native.call("mt_snip_scaled", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), spec2d.shape[0],
@@ -44,6 +70,9 @@ def snip_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out, out_mode,
 def snip_residual_f16(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out_half, overflow, stream=None):
     """The residual y - bkg as two fp16 planes [P, 2*n_ch] (hi | remainder) for the fp16 tensor-core contraction;
     overflow (int32 [1]) is raised when a residual does not fit fp16."""
+    if _runs_launch(spec2d, ch0, n_ch, lohi_dev, n_pass, boxcar_size, out_half, _native.MT_SNIP_RESIDUAL_HILO_F16, overflow,
+                    stream):
+        return out_half
     scaled = getattr(lohi_dev, "_mt_scaled", None)
     use_scaled = scaled is not None and scaled.shape[0] == int(n_pass) + 1
     tab = scaled if use_scaled else lohi_dev
