@@ -579,7 +579,9 @@ def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(device).multi_processor_count
     eager_ms = ms_eager / steps
-    contract_bytes_px = w["n_ch"] * (es if not w["snip"] else 4 * 2) + n_comp * 4  # what K3 streams (hi/lo residual planes)
+    # what K3 streams: the spectrum, or on the SNIP path the two residual planes (fp16 pair = 4 B per channel, tf32 pair = 8)
+    plane_bytes = 4 if getattr(plan, "_last_snip_half", False) else 8
+    contract_bytes_px = w["n_ch"] * (es if not w["snip"] else plane_bytes) + n_comp * 4
     k3_roof = None
     if k3:
         achieved = contract_bytes_px * k3["px_per_launch"] / (k3["ms_per_launch"] * 1e-3) / 1e9
@@ -594,7 +596,7 @@ def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e
         achieved = smem_bytes_px * k2["px_per_launch"] / (k2["ms_per_launch"] * 1e-3) / 1e9
         smem_peak = n_sm * 128 * sm_mhz * 1e6 / 1e9
         roofline = {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
-                    "traffic": traffic, "kernel": "snip_kernel (K2)", "bytes_per_px": smem_bytes_px, "passes": n_pass,
+                    "traffic": traffic, "kernel": "snip_runs_kernel (K2b)" if getattr(plan._snip[0], "_mt_runs", None) is not None else "snip_kernel (K2)", "bytes_per_px": smem_bytes_px, "passes": n_pass,
                     "px_per_launch": k2["px_per_launch"], "kernel_ms": k2["ms_per_launch"],
                     "peak_source": f"{n_sm} SMs x 128 B/clk x {sm_mhz:.0f} MHz (SM clock sampled during the run)",
                     "share_of_step": k2["ms_per_step"] / eager_ms, "contraction": k3_roof}

@@ -205,7 +205,8 @@ snip_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, int c
 }
 
 // tuning knobs (environment): MT_SNIP_PREFETCH = CTAs ahead whose rows are prefetched into L2 (default 0 = off;
-// 2 x SM count = the CTA that takes this one's place), MT_SNIP_FASTMATH = 1 selects MUFU-based log / exp.  Measured on
+// 2 x SM count = the CTA that takes this one's place), MT_SNIP_FASTMATH (default 1 since the contiguous-run kernel, where
+// it is worth 10 %; 0 = the 1-ulp logf / expf) selects MUFU-based log / exp in BOTH kernels.  Measured on
 // B200 (c3 shard, 131 072 px): neither moves the kernel (1.091 ms per 32 768 px without, 1.095 with prefetch, 1.109 with
 // fast math): with two resident CTAs the phases that wait on memory or issue math are already hidden behind the other
 // CTA's pass loop, and the pass loop itself runs at the shared-memory rate one CTA can sustain between barriers.
@@ -245,25 +246,24 @@ template <typename T>
 int dispatch_snip(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *lohi, int ld_tab,
                   bool scaled, int n_pass, int boxcar, float *out, int64_t ld_out, int out_mode, int *overflow,
                   cudaStream_t stream) {
-    static const bool fast = env_int("MT_SNIP_FASTMATH", 0) != 0;
-#define MT_SNIP_CASE(K)                                                                                             \
-    if (n_ch <= kSnipThreads * K) {                                                                                 \
-        if (scaled && fast)                                                                                         \
-            return launch_snip<T, K, true, true>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out,    \
-                                                 ld_out, out_mode, overflow, stream);                               \
-        if (scaled)                                                                                                 \
-            return launch_snip<T, K, true, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out,   \
-                                                  ld_out, out_mode, overflow, stream);                              \
-        return launch_snip<T, K, false, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out,      \
-                                               ld_out, out_mode, overflow, stream);                                 \
+    static const bool fast = env_int("MT_SNIP_FASTMATH", 1) != 0;
+#define MT_SNIP_ARGS spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, out_mode, overflow, stream
+#define MT_SNIP_CASE(K)                                                                 \
+    if (n_ch <= kSnipThreads * K) {                                                     \
+        if (scaled && fast) return launch_snip<T, K, true, true>(MT_SNIP_ARGS);         \
+        if (scaled) return launch_snip<T, K, true, false>(MT_SNIP_ARGS);                \
+        if (fast) return launch_snip<T, K, false, true>(MT_SNIP_ARGS);                  \
+        return launch_snip<T, K, false, false>(MT_SNIP_ARGS);                           \
     }
     MT_SNIP_CASE(2)
     MT_SNIP_CASE(4)
     MT_SNIP_CASE(8)
 #undef MT_SNIP_CASE
-    if (n_ch <= kSnipThreads * 16 && !scaled)
-        return launch_snip<T, 16, false, false>(spec, n_px, ld_spec, ch0, n_ch, lohi, ld_tab, n_pass, boxcar, out, ld_out, out_mode,
-                                         overflow, stream);
+    if (n_ch <= kSnipThreads * 16 && !scaled) {
+        if (fast) return launch_snip<T, 16, false, true>(MT_SNIP_ARGS);
+        return launch_snip<T, 16, false, false>(MT_SNIP_ARGS);
+    }
+#undef MT_SNIP_ARGS
     return mt::fail(MT_ERR_UNSUPPORTED, "mt_snip: n_ch=%d exceeds the on-chip limit of %d channels", n_ch,
                     kSnipThreads * (scaled ? 8 : 16));
 }

@@ -498,7 +498,7 @@ int launch_runs(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_
 template <typename T>
 int dispatch_runs(const void *spec, int64_t n_px, int64_t ld_spec, int ch0, int n_ch, const uint32_t *tabs, int ld_tab,
                   int n_pass, void *out, int64_t ld_out, int out_mode, int *overflow, cudaStream_t stream) {
-    static const bool fast = env_int("MT_SNIP_FASTMATH", 0) != 0;
+    static const bool fast = env_int("MT_SNIP_FASTMATH", 1) != 0;
 #define MT_RUNS_CASE(R)                                                                                                \
     if (run_len(n_ch) == R) {                                                                                          \
         if (fast)                                                                                                      \
