@@ -705,7 +705,10 @@ def run_config1(device, repeats=3):
         tensors, spec_fit, bkg, trace = opt.fit_spec(spec, [50, 1450], **kw)
         torch.cuda.synchronize()
         secs.append(time.perf_counter() - t0)
+    from mapstorch_b200 import refine as _refine
+
     return {"seconds": float(np.median(secs)), "unit": "s per fit_spec call", "repeats": repeats, "final_loss": float(trace[-1]),
+            "work": dict(_refine.LAST_STATS),
             "first_loss": float(trace[0]), "workload": C1_DESC,
             "fitted": {k: float(tensors[k]) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "FWHM_OFFSET", "COMPTON_ANGLE")
                        if k in tensors}}

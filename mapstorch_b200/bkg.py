@@ -13,11 +13,15 @@ from mapstorch_b200 import _native, tables
 from mapstorch_b200.constant import M_SQRT2  # noqa: F401
 
 
-def snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+def snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime, aux=True):
     """(gather table [n_pass, n_ch] int32 on the device, n_pass).  For windows of up to 4096 channels the table
-    also carries its pre-scaled form (mt_snip_scale_tables) as attribute ``_mt_scaled``; snip_launch picks it up."""
+    also carries its pre-scaled form (mt_snip_scale_tables) as attribute ``_mt_scaled`` and the tables of the
+    contiguous-run kernel as ``_mt_runs``; snip_launch picks them up.  aux=False skips both (three launches and a
+    stream synchronisation that only pay off over many spectra): the plain table drives the strided kernel."""
     tab = tables.snip_tables(n_ch, er[0], e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
     lohi = torch.from_numpy(tab.view(np.int32)).to("cuda")
+    if not aux:
+        return lohi, tab.shape[0]
     pitch = _native.load().mt_snip_scaled_pitch(int(n_ch))
     if pitch > 0 and tab.shape[0] > 0:
         scaled = torch.empty((tab.shape[0] + 1, pitch), dtype=torch.int32, device="cuda")
@@ -109,7 +113,8 @@ def snip_bkg(spec, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_
     spec_dev = spec.detach().to("cuda")
     n_ch = spec_dev.shape[-1]
     flat = spec_dev.reshape(-1, n_ch).contiguous()
-    lohi, n_pass = snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
+    lohi, n_pass = snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime,
+                                      aux=flat.shape[0] >= 64)
     out = torch.empty((flat.shape[0], n_ch), dtype=torch.float32, device="cuda")
     snip_launch(flat, 0, n_ch, lohi, n_pass, boxcar_size, out, _native.MT_SNIP_BACKGROUND)
     out = out.reshape(spec_dev.shape)

@@ -221,6 +221,9 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
 
 
 # ---- fit_spec(tune_params=True): global calibration fit of one spectrum -------------------------
+LAST_STATS = {"evaluations": 0, "snip_launches": 0, "jacobians": 0}  # work done by the last fit_spec_global call
+
+
 def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, init_param_vals, fixed_param_vals,
                     indices, use_snip, n_iter, e_consts, elem_info, detector_type, escape_factor, device, verbose,
                     loss="mse", l1_lambda=0.0):
@@ -258,14 +261,24 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     idx = None if indices is None else torch.as_tensor(np.asarray(indices), device="cuda")
     scale = np.array([10.0 * default_learning_rates.get(p, default_learning_rates["default_lr"]) for p in free])
     robust_loss = loss == "l1"
+    bkg_cache = {}
+    LAST_STATS.update(evaluations=0, snip_launches=0, jacobians=0)
 
     def evaluate(theta, w=None):
+        LAST_STATS["evaluations"] += 1
         pp = dict(params, **dict(zip(free, (float(t) for t in theta))))
         basis, names = _map.element_basis(pp, er, elements, e_consts, elem_info, detector_type, escape_factor)
         if use_snip:
-            bkg = _bkg.snip_bkg(y, er, *(torch.tensor(float(pp[k])) for k in (
-                "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME")),
-                device="cuda")
+            # the background depends on six of the parameters only: trial points that move the others (scatter energy,
+            # Compton angle and width) reuse it instead of rebuilding the window tables and relaunching K2
+            key = tuple(float(pp[k]) for k in (
+                "ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC", "SNIP_WIDTH", "FWHM_OFFSET", "FWHM_FANOPRIME"))
+            bkg = bkg_cache.get(key)
+            if bkg is None:
+                if len(bkg_cache) > 64:
+                    bkg_cache.clear()
+                LAST_STATS["snip_launches"] += 1
+                bkg = bkg_cache[key] = _bkg.snip_bkg(y, er, *(torch.tensor(v) for v in key), device="cuda")
         else:
             bkg = torch.zeros_like(y)
         target = (y - bkg).double()
@@ -283,6 +296,8 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     # Parameters that move the model: the tail fractions of default_fitting_params never enter model_spec
     # (use_tail=False, map.py:290,302), their gradient is zero in the reference as well and they keep their values.
     active = [k for k, name in enumerate(free) if name in _native.THETA_IDS]
+    # what a finite difference can see at all: the model parameters above plus the SNIP width
+    moving = set(active) | {k for k, name in enumerate(free) if name == "SNIP_WIDTH" and use_snip}
     # analytic Jacobian (mt_model_jacobian) wherever the device model is the whole model: no escape peaks, no penalty
     # entries in the residual vector; otherwise forward differences (1 + len(free) evaluations per iteration)
     # ... and no SNIP: the background follows the width and energy-axis parameters through integer window tables, a
@@ -295,9 +310,15 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     def jacobian(theta, w, resid, info):
         if not state["fd"]:
             return jacobian_analytic(theta, w, resid, info)
-        # forward differences: 1 + len(free) evaluations
+        # forward differences: 1 + len(moving) evaluations.  Parameters that never enter model_spec or the background
+        # (the tail fractions, see `active`) have an identically zero column: no evaluation is spent on them.
         cols = []
+        zero = None
         for k in range(len(free)):
+            if k not in moving:
+                zero = torch.zeros_like(resid) if zero is None else zero
+                cols.append(zero)
+                continue
             t2 = theta.copy()
             t2[k] += 0.05 * scale[k]
             r2, _ = evaluate(t2, w)
@@ -335,12 +356,21 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         value = float(resid @ resid)
         lam = 1e-3
         radius = 1.0
-        for it in range(max_it if free else 0):
-            jac = jacobian(theta, w, resid, info)
+        # Forward differences cost one evaluation per moving parameter.  Between full differencings the Jacobian is
+        # carried along by Broyden's rank-one secant update (free: it uses the accepted trial point), refreshed every
+        # `refresh` accepted steps and whenever a step computed from a carried Jacobian fails.
+        jac, age, refresh = None, 0, 5
+        it = 0
+        while it < (max_it if free else 0):
+            fresh = jac is None or not state["fd"] or age >= refresh
+            if fresh:
+                LAST_STATS["jacobians"] += 1
+                jac = jacobian(theta, w, resid, info)
+                age = 0
             jtj = (jac.T @ jac).cpu().numpy()
             jtr = (jac.T @ resid).cpu().numpy()
             improved = False
-            for _ in range(8):
+            for _ in range(8 if fresh else 3):
                 try:
                     damp = np.diag(np.diag(jtj)) + 1e-12 * np.eye(len(free))
                     dead = np.diag(jtj) <= 0  # parameters without influence (zero column): no step
@@ -357,15 +387,26 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                 value_new = float(r_new @ r_new)
                 if value_new < value:
                     rel = (value - value_new) / max(value, 1e-30)
+                    if state["fd"] and r_new.shape == resid.shape:
+                        sv = torch.from_numpy((cand - theta) / scale).to(jac)
+                        denom = float(sv @ sv)
+                        if denom > 0:
+                            jac = jac + torch.outer(r_new - resid - jac @ sv, sv) / denom
                     theta, resid, info, value = cand, r_new, info_new, value_new
                     lam = max(lam / 5, 1e-9)
                     if clipped:
                         radius = min(radius * 2.0, 16.0)
                         rel = max(rel, 1.0)  # a clipped step says nothing about convergence
                     improved = True
+                    age += 1
                     break
                 lam *= 5
                 radius = max(radius * 0.5, 1e-3)
+            if (not improved or rel < 1e-10) and not fresh:
+                jac = None  # the carried Jacobian has gone stale: difference again before drawing conclusions
+                lam = min(lam, 1e-3)
+                continue
+            it += 1
             trace.append(info["objective"])
             if verbose:
                 print(f"fit_spec_global iter {it}: objective {info['objective']:.6g} lambda {lam:.2g}")
@@ -375,6 +416,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                 # active set.  Where that stalls the iteration, finish with forward differences of the whole residual.
                 state["fd"] = True
                 lam, radius = 1e-3, 1.0
+                jac = None
                 continue
             if not improved or rel < 1e-10:
                 break
