@@ -25,6 +25,7 @@
 // d model / d theta): the analytic Jacobian of fit_spec(tune_params=True).
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -54,6 +55,7 @@ struct RefParams {
     MtRefineConfig cfg;
     const MtRefineLine *lines;      // [n_lines], sorted by energy
     const uint32_t *chan_lines;     // [n_ch]: lo | hi << 16, line index range covering the channel
+    const uint32_t *pair_info;      // [ceil(n_ch / 2)]: channel pair | first line << 12 | line count << 22, sorted by count
     const int32_t *comp_start;      // [n_comp + 1] into comp_lines
     const int32_t *comp_lines;      // line indices grouped by component
     const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
@@ -321,14 +323,18 @@ refine_kernel(const RefParams p) {
 #pragma unroll
         for (int k = 0; k < NT; ++k) id_k[k] = cfg.theta_id[k];
         const f32x2 off2 = bcast2(off), slope2 = bcast2(slope), quad2 = bcast2(cal.quad);
-        for (int q = tid; q < (ld >> 1); q += kRefThreads) {
-            const int c0 = 2 * q;
+        // Channel pairs are visited in the order of pair_info: sorted by the number of lines that cover them, so that
+        // the 32 pairs a warp evaluates together run the same number of line iterations (in channel order a warp spent
+        // two thirds of its issue slots on lanes that had run out of lines: ncu r01_refine_v3, 78 thread instructions per
+        // (line, pair) against 16 in the loop body).
+        for (int i = tid; i < (ld >> 1); i += kRefThreads) {
+            const uint32_t info = __ldg(p.pair_info + i);
+            const int c0 = 2 * (int)(info & 0xfffu);
             const bool has1 = c0 + 1 < n_ch;
             const float cg0 = (float)(cfg.ch0 + c0);
             const f32x2 cg = pack2(cg0, cg0 + 1.f);
-            const uint32_t ra = __ldg(p.chan_lines + c0), rb = has1 ? __ldg(p.chan_lines + c0 + 1) : ra;
-            const int l_begin = min((int)(ra & 0xffffu), (int)(rb & 0xffffu));
-            const int l_end = max((int)(ra >> 16), (int)(rb >> 16));
+            const int l_begin = (int)((info >> 12) & 0x3ffu);
+            const int l_end = l_begin + (int)(info >> 22);
             f32x2 m, d[NT > 0 ? NT : 1];
             eval_pair<NT, GENERAL>(id_k, cal, cg, l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
             const float y0 = ld_spec<T>(row + c0) - (brow ? __ldg(brow + c0) : 0.f);
@@ -718,7 +724,29 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
                  b_cs = sizeof(int32_t) * (cfg.n_comp + 1), b_cl = sizeof(int32_t) * cfg.n_lines,
                  b_lw = sizeof(uint32_t) * cfg.n_lines, b_co = sizeof(int32_t) * cfg.n_comp;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co);
+    // channel pairs sorted by the number of lines covering them (ties in channel order): the visiting order of phase B1
+    const int n_pairs = (cfg.n_ch + 1) / 2;
+    std::vector<uint32_t> pair_info(n_pairs);
+    {
+        std::vector<int> count(n_pairs), first(n_pairs), order(n_pairs);
+        for (int q = 0; q < n_pairs; ++q) {
+            const uint32_t ra = chan_lines_host[2 * q], rb = 2 * q + 1 < cfg.n_ch ? chan_lines_host[2 * q + 1] : ra;
+            // union of the two channels' line ranges; a channel without lines (empty range, encoded 0 | 0) must not
+            // stretch its neighbour's range down to line 0
+            const int la = (int)(ra & 0xffffu), ha = (int)(ra >> 16), lb = (int)(rb & 0xffffu), hb = (int)(rb >> 16);
+            const int lo = ha <= la ? lb : (hb <= lb ? la : std::min(la, lb));
+            const int hi = ha <= la ? hb : (hb <= lb ? ha : std::max(ha, hb));
+            MT_REQUIRE(lo >= 0 && hi <= cfg.n_lines && hi - lo < 1024 && lo < 1024, "mt_refine: chan_lines[%d] out of range", 2 * q);
+            first[q] = lo;
+            count[q] = hi > lo ? hi - lo : 0;
+            order[q] = q;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return count[a] > count[b]; });
+        for (int i = 0; i < n_pairs; ++i)
+            pair_info[i] = (uint32_t)order[i] | ((uint32_t)first[order[i]] << 12) | ((uint32_t)count[order[i]] << 22);
+    }
+    const size_t b_pi = sizeof(uint32_t) * n_pairs;
+    const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co) + up(b_pi);
     std::vector<char> packed(total);
     size_t cursor = 0;
     RefParams p{};
@@ -736,6 +764,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     o_cl = stage(comp_lines_host, b_cl);
     o_lw = stage(line_window_host, b_lw);
     o_co = stage(comp_order_host, b_co);
+    const size_t o_pi = stage(pair_info.data(), b_pi);
     // The tables are the same for every slab of a map.  Uploading them per call would put a host-to-device copy
     // in front of every launch, and that copy queues on the DMA engine BEHIND the next slab of the volume that
     // a streaming caller is already sending -- the kernel would wait for it.  So device copies are kept in a small
@@ -748,6 +777,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.comp_lines = reinterpret_cast<const int32_t *>(tables + o_cl);
     p.line_window = reinterpret_cast<const uint32_t *>(tables + o_lw);
     p.comp_order = reinterpret_cast<const int32_t *>(tables + o_co);
+    p.pair_info = reinterpret_cast<const uint32_t *>(tables + o_pi);
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
     p.ld_bkg = ld_bkg;
