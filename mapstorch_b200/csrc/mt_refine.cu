@@ -56,6 +56,8 @@ struct RefParams {
     const MtRefineLine *lines;      // [n_lines], sorted by energy
     const uint32_t *chan_lines;     // [n_ch]: lo | hi << 16, line index range covering the channel
     const uint32_t *pair_info;      // [ceil(n_ch / 2)]: channel pair | first line << 12 | line count << 22, sorted by count
+    const uint32_t *b2_items;       // component-major pass, flattened: line | channel pair << 10 (line 0x3ff = padding); NULL:
+    const int32_t *b2_start;        // [n_comp + 1] item offsets (multiples of 32)      per-line window loops instead
     const int32_t *comp_start;      // [n_comp + 1] into comp_lines
     const int32_t *comp_lines;      // line indices grouped by component
     const uint32_t *line_window;    // [n_lines]: first | last+1 << 16 channel (local) of the line's window
@@ -210,9 +212,13 @@ __device__ __forceinline__ void eval_pair(const int (&id_k)[NT > 0 ? NT : 1], co
             d_fo = fma2(w, bcast2(a1.y), d_fo);
             d_fa = fma2(w, bcast2(a1.z), d_fa);
         }
+        // which of the three accumulated derivatives belongs to parameter k is the same for every pair of the launch:
+        // two multiplications by 0 / 1 instead of chains of selects on 64-bit register pairs (ncu r02_refine_v4:
+        // ~50 of the 106 instructions per pair were selects)
 #pragma unroll
         for (int k = 0; k < NT; ++k)
-            d[k] = id_k[k] == MT_THETA_FWHM_OFFSET ? d_fo : id_k[k] == MT_THETA_FWHM_FANOPRIME ? d_fa : 0ull;
+            d[k] = fma2(d_fo, bcast2(id_k[k] == MT_THETA_FWHM_OFFSET ? 1.f : 0.f),
+                        mul2(d_fa, bcast2(id_k[k] == MT_THETA_FWHM_FANOPRIME ? 1.f : 0.f)));
     } else {
 #pragma unroll
         for (int k = 0; k < NT; ++k) d[k] = 0ull;
@@ -253,11 +259,15 @@ __device__ __forceinline__ void eval_pair(const int (&id_k)[NT > 0 ? NT : 1], co
         }
     }
     // the energy-axis parameters act through ev alone (+ the gain factor of ENERGY_SLOPE, map.py:57-62)
+    // d[k] <- keep * d[k] + d_ev * (s0 + cg * (s1 + cg * s2)) + m * sm with launch-uniform 0 / 1 (and 1 / slope) factors
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
-        if (id_k[k] == MT_THETA_ENERGY_OFFSET) d[k] = d_ev;
-        if (id_k[k] == MT_THETA_ENERGY_SLOPE) d[k] = fma2(d_ev, cg, mul2(m, bcast2(1.f / c.slope)));
-        if (id_k[k] == MT_THETA_ENERGY_QUADRATIC) d[k] = mul2(mul2(d_ev, cg), cg);
+        const int id = id_k[k];
+        const bool axis = id == MT_THETA_ENERGY_OFFSET || id == MT_THETA_ENERGY_SLOPE || id == MT_THETA_ENERGY_QUADRATIC;
+        const float s0 = id == MT_THETA_ENERGY_OFFSET ? 1.f : 0.f, s1 = id == MT_THETA_ENERGY_SLOPE ? 1.f : 0.f,
+                    s2 = id == MT_THETA_ENERGY_QUADRATIC ? 1.f : 0.f, sm = id == MT_THETA_ENERGY_SLOPE ? 1.f / c.slope : 0.f;
+        const f32x2 poly = fma2(fma2(bcast2(s2), cg, bcast2(s1)), cg, bcast2(s0));
+        d[k] = fma2(d_ev, poly, fma2(m, bcast2(sm), mul2(d[k], bcast2(axis ? 0.f : 1.f))));
     }
     m_out = m;
 }
@@ -327,8 +337,17 @@ refine_kernel(const RefParams p) {
         // the 32 pairs a warp evaluates together run the same number of line iterations (in channel order a warp spent
         // two thirds of its issue slots on lanes that had run out of lines: ncu r01_refine_v3, 78 thread instructions per
         // (line, pair) against 16 in the loop body).
-        for (int i = tid; i < (ld >> 1); i += kRefThreads) {
+        // the counts of the pair are requested before its lines are evaluated and used after (in visiting order the
+        // loads are scattered: issued where they are used they stalled every pair for an L2 round trip)
+        const int n_pairs = ld >> 1;
+        for (int i = tid; i < n_pairs; i += kRefThreads) {
             const uint32_t info = __ldg(p.pair_info + i);
+            float y0, y1;
+            {
+                const int c = 2 * (int)(info & 0xfffu);
+                y0 = ld_spec<T>(row + c) - (brow ? __ldg(brow + c) : 0.f);
+                y1 = c + 1 < n_ch ? ld_spec<T>(row + c + 1) - (brow ? __ldg(brow + c + 1) : 0.f) : 0.f;
+            }
             const int c0 = 2 * (int)(info & 0xfffu);
             const bool has1 = c0 + 1 < n_ch;
             const float cg0 = (float)(cfg.ch0 + c0);
@@ -337,8 +356,6 @@ refine_kernel(const RefParams p) {
             const int l_end = l_begin + (int)(info >> 22);
             f32x2 m, d[NT > 0 ? NT : 1];
             eval_pair<NT, GENERAL>(id_k, cal, cg, l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
-            const float y0 = ld_spec<T>(row + c0) - (brow ? __ldg(brow + c0) : 0.f);
-            const float y1 = has1 ? ld_spec<T>(row + c0 + 1) - (brow ? __ldg(brow + c0 + 1) : 0.f) : 0.f;
             f32x2 res = add2(m, pack2(-y0, -y1));
             if (!has1) {
                 // phantom channel of an odd window: contributes nothing anywhere
@@ -381,7 +398,41 @@ refine_kernel(const RefParams p) {
             f32x2 g = 0ull, h[NT > 0 ? NT : 1];
 #pragma unroll
             for (int k = 0; k < NT; ++k) h[k] = 0ull;
-            const int j_end = __ldg(p.comp_start + e + 1);
+            if (p.b2_items != nullptr) {
+                // flattened: the (line, channel pair) items of the component, 32 per warp iteration whatever the
+                // lines' window lengths are (per-line window loops left a quarter of the lanes idle and spent more
+                // instructions on loop set-up than on the items: ncu r02_refine_v4)
+                const int i_end = __ldg(p.b2_start + e + 1);
+                int i = __ldg(p.b2_start + e) + lane;
+                uint32_t item_next = i < i_end ? __ldg(p.b2_items + i) : 0x3ffu;
+                for (; i < i_end; i += 32) {
+                    const uint32_t item = item_next;  // fetched an iteration ago: the table comes from L2 / L1
+                    if (i + 32 < i_end) item_next = __ldg(p.b2_items + i + 32);
+                    const int l = (int)(item & 0x3ffu);
+                    if (l == 0x3ff) continue;
+                    const int c = 2 * (int)(item >> 10);
+                    const float4 a0 = lc0[l];
+                    const float cg0 = (float)(cfg.ch0 + c);
+                    const f32x2 cg = pack2(cg0, cg0 + 1.f);
+                    const f32x2 dl = add2(fma2(fma2(quad2, cg, slope2), cg, off2), bcast2(-a0.x));
+                    float e0, e1;
+                    unpack2(mul2(mul2(dl, dl), bcast2(a0.y)), e0, e1);
+                    f32x2 b = mul2(pack2(ex2_approx(e0), ex2_approx(e1)), bcast2(lc1[l].w));
+                    if (GENERAL) {
+                        const float kstep = lc3[l].x;
+                        if (kstep != 0.f) {
+                            float r0, r1;
+                            erfc2(mul2(dl, bcast2(lc2[l].z)), r0, r1);
+                            b = fma2(pack2(r0, r1), bcast2(kstep), b);
+                        }
+                    }
+                    const float *rp = r_s + c;
+                    g = fma2(b, *reinterpret_cast<const f32x2 *>(rp), g);
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) h[k] = fma2(b, *reinterpret_cast<const f32x2 *>(rp + (k + 1) * ld), h[k]);
+                }
+            }
+            const int j_end = p.b2_items != nullptr ? 0 : __ldg(p.comp_start + e + 1);
             for (int j = __ldg(p.comp_start + e); j < j_end; ++j) {
                 const int l = __ldg(p.comp_lines + j);
                 const float4 a0 = lc0[l];
@@ -746,7 +797,26 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
             pair_info[i] = (uint32_t)order[i] | ((uint32_t)first[order[i]] << 12) | ((uint32_t)count[order[i]] << 22);
     }
     const size_t b_pi = sizeof(uint32_t) * n_pairs;
-    const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co) + up(b_pi);
+    // component-major pass: every component's (line, channel pair) items in one list, padded to whole warps
+    std::vector<uint32_t> b2_items;
+    std::vector<int32_t> b2_start(cfg.n_comp + 1, 0);
+    bool flat_b2 = cfg.n_lines < 0x3ff;
+    for (int e = 0; e < cfg.n_comp && flat_b2; ++e) {
+        b2_start[e] = (int32_t)b2_items.size();
+        for (int j = comp_start_host[e]; j < comp_start_host[e + 1]; ++j) {
+            const int l = comp_lines_host[j];
+            MT_REQUIRE(l >= 0 && l < cfg.n_lines, "mt_refine: comp_lines[%d]=%d", j, l);
+            const uint32_t win = line_window_host[l];
+            const int q0 = (int)(win & 0xffffu) / 2, q1 = std::min(((int)(win >> 16) + 1) / 2, n_pairs);
+            for (int q = q0; q < q1; ++q) b2_items.push_back((uint32_t)l | ((uint32_t)q << 10));
+        }
+        while (b2_items.size() % 32) b2_items.push_back(0x3ffu);
+        flat_b2 = b2_items.size() <= (1u << 18);  // 1 MB of table at most; beyond that the per-line loops serve
+    }
+    b2_start[cfg.n_comp] = (int32_t)b2_items.size();
+    if (!flat_b2) b2_items.assign(1, 0x3ffu);
+    const size_t b_it = sizeof(uint32_t) * b2_items.size(), b_is = sizeof(int32_t) * b2_start.size();
+    const size_t total = up(b_lines) + up(b_chan) + up(b_cs) + up(b_cl) + up(b_lw) + up(b_co) + up(b_pi) + up(b_it) + up(b_is);
     std::vector<char> packed(total);
     size_t cursor = 0;
     RefParams p{};
@@ -765,6 +835,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     o_lw = stage(line_window_host, b_lw);
     o_co = stage(comp_order_host, b_co);
     const size_t o_pi = stage(pair_info.data(), b_pi);
+    const size_t o_it = stage(b2_items.data(), b_it), o_is = stage(b2_start.data(), b_is);
     // The tables are the same for every slab of a map.  Uploading them per call would put a host-to-device copy
     // in front of every launch, and that copy queues on the DMA engine BEHIND the next slab of the volume that
     // a streaming caller is already sending -- the kernel would wait for it.  So device copies are kept in a small
@@ -778,6 +849,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.line_window = reinterpret_cast<const uint32_t *>(tables + o_lw);
     p.comp_order = reinterpret_cast<const int32_t *>(tables + o_co);
     p.pair_info = reinterpret_cast<const uint32_t *>(tables + o_pi);
+    p.b2_items = flat_b2 ? reinterpret_cast<const uint32_t *>(tables + o_it) : nullptr;
+    p.b2_start = reinterpret_cast<const int32_t *>(tables + o_is);
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
     p.ld_bkg = ld_bkg;
