@@ -140,7 +140,7 @@ def check(status):
 # kernels launched per successful call of each entry point (bench.py reports the total)
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 2, "mt_refine": 1,
-                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_lad_update": 1, "mt_transpose_cf": 1, "mt_int_spec": 1, "mt_model_jacobian": 1, "mt_snip_residual_f16": 1, "mt_snip_runs": 1, "mt_snip_runs_tables": 1,
+                    "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_lad_update": 1, "mt_transpose_cf": 1, "mt_int_spec": 1, "mt_model_jacobian": 1, "mt_snip_residual_f16": 1, "mt_snip_runs": 1, "mt_snip_runs_tables": 2,
                     "mt_peer_wait": 1}
 launch_count = 0
 
