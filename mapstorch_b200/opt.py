@@ -30,7 +30,7 @@ DIGIT_BITS = 10    # bits per operand plane of the pseudo-inverse (|digit| <= 51
 N_PLANES = 3       # 30 bits in total
 MAX_GROUP = 80     # components per tensor-core tile: N = N_PLANES * e_pad <= 256
 PLANE_RATIO = 2.0 ** -DIGIT_BITS
-SNIP_CHUNK_PX = 32768
+SNIP_CHUNK_PX = 131072  # pixels per scratch slab of the SNIP residual / split operand (2 GB of fp16 planes at 4096 channels): fewer, fuller launches of K2 and K3
 
 
 def init_elem_amps(elem, spec, e_sct, e_offset, e_slope, e_consts=default_energy_consts, verbose=False, *,
