@@ -425,31 +425,39 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     theta = np.array([params[p] for p in free], dtype=np.float64)
     trace = []
     budget = max(1, min(int(n_iter), 60))
-    if not robust_loss:
-        _, info0 = evaluate(theta)
-        trace.append(info0["objective"])
-        theta, info = run_lm(theta, None, budget, trace)
-    else:
-        _, info = evaluate(theta)
-        trace.append(info["objective"])
-        top = max(float(info["res"].abs().max()), 1e-30)
-        eps, floor = 1e-3 * top, 1e-10 * top
-        for rnd in range(16):
-            before = info["objective"]
-            theta, info = run_lm(theta, robust.irls_weights(info["res"], eps), min(budget, 12), trace)
-            if eps <= floor and abs(before - info["objective"]) <= 1e-8 * abs(before):
-                break
-            eps = max(eps * 0.2, floor)
-        # calibration settled: converge the amplitudes of the final model all the way
-        polished = robust.solve_amplitudes(info["bm"], info["tm"], loss, info["c"])
-        value = robust.objective(info["bm"], info["tm"], polished, loss, info["c"])
-        if value <= info["objective"]:
-            info = dict(info, x=polished, objective=value)
-            trace.append(value)
+    # The host side of an evaluation is a few dozen torch CPU ops on ~1400-element tensors (the reference's own op
+    # sequence for the SNIP window tables).  With a large intra-op thread pool every one of them pays a fork / join:
+    # 0.29 s per call became 0.88 s inside a process that had set 32 threads.  One thread for the duration of the fit.
+    host_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        if not robust_loss:
+            _, info0 = evaluate(theta)
+            trace.append(info0["objective"])
+            theta, info = run_lm(theta, None, budget, trace)
+        else:
+            _, info = evaluate(theta)
+            trace.append(info["objective"])
+            top = max(float(info["res"].abs().max()), 1e-30)
+            eps, floor = 1e-3 * top, 1e-10 * top
+            for rnd in range(16):
+                before = info["objective"]
+                theta, info = run_lm(theta, robust.irls_weights(info["res"], eps), min(budget, 12), trace)
+                if eps <= floor and abs(before - info["objective"]) <= 1e-8 * abs(before):
+                    break
+                eps = max(eps * 0.2, floor)
+            # calibration settled: converge the amplitudes of the final model all the way
+            polished = robust.solve_amplitudes(info["bm"], info["tm"], loss, info["c"])
+            value = robust.objective(info["bm"], info["tm"], polished, loss, info["c"])
+            if value <= info["objective"]:
+                info = dict(info, x=polished, objective=value)
+                trace.append(value)
 
-    pp, names, x = info["params"], info["names"], info["x"]
-    tensors, _ = create_tensors(names, free, pp, {k: pp[k] for k in pp if k not in free}, tune_params=True, device=device)
-    for n, a in zip(names, x.float()):
-        tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
-    spec_fit = (x.float() @ info["basis"]).reshape(-1)
-    return tensors, spec_fit.cpu().numpy(), info["bkg"].cpu().numpy(), trace
+        pp, names, x = info["params"], info["names"], info["x"]
+        tensors, _ = create_tensors(names, free, pp, {k: pp[k] for k in pp if k not in free}, tune_params=True, device=device)
+        for n, a in zip(names, x.float()):
+            tensors[n] = torch.log10(torch.clamp(a, min=1e-30)).to(device).requires_grad_(True)
+        spec_fit = (x.float() @ info["basis"]).reshape(-1)
+        return tensors, spec_fit.cpu().numpy(), info["bkg"].cpu().numpy(), trace
+    finally:
+        torch.set_num_threads(host_threads)
