@@ -120,8 +120,12 @@ def test_runs_kernel_is_bit_identical_to_the_strided_kernel(snip_golden, n_ch, c
     """csrc/mt_snip_runs.cu (contiguous runs, register neighbours, bulk-copy prefetch, persistent CTAs) performs the
     same fp32 operations as csrc/mt_snip.cu: every output mode must agree bit for bit, for every run length, through
     more quads than there are CTAs, with ragged last quads, crops inside wider rows and both storage types."""
+    import os
+
     from mapstorch_b200 import _native, bkg
 
+    if os.environ.get("MT_SNIP_RUNS") == "0":
+        pytest.skip("the contiguous-run kernel is switched off (MT_SNIP_RUNS=0)")
     pr = snip_golden["c4096_params"]
     rng = np.random.default_rng(n_ch + n_px)
     ld = ch0 + n_ch + 24
@@ -144,7 +148,12 @@ def test_runs_kernel_is_bit_identical_to_the_strided_kernel(snip_golden, n_ch, c
 
 
 def test_runs_kernel_overflow_flag_and_unaligned_problems_fall_back(snip_golden):
+    import os
+
     from mapstorch_b200 import _native, bkg
+
+    if os.environ.get("MT_SNIP_RUNS") == "0":
+        pytest.skip("the contiguous-run kernel is switched off (MT_SNIP_RUNS=0)")
 
     pr = snip_golden["c2048_params"]
     lohi, n_pass = bkg.snip_tables_device(2048, (0, 2047), *[torch.tensor(float(v)) for v in pr])
