@@ -49,7 +49,7 @@ constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kMaxLines = 512;
 constexpr int kMaxComp = 64;
 constexpr int kMaxTheta = MT_MAX_THETA_REFINE;
-constexpr int kRefMinBlocks = 6;  // measured on B200 (c4): 4 -> 77.0 ms, 5 -> 72.3, 6 -> 69.6, 7/8 -> 70.0
+constexpr int kRefMinBlocks = 7;  // round 1 (c4): 4 -> 77.0 ms, 5 -> 72.3, 6 -> 69.6, 7/8 -> 70.0; round 2 kernel: 6 -> 30.6 ms, 7 -> 29.6 (72 registers, no spills)
 
 struct RefParams {
     MtRefineConfig cfg;
