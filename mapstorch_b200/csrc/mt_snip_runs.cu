@@ -200,6 +200,19 @@ __device__ __forceinline__ float &comp(float4 &v) {
     return v.w;
 }
 
+// bounded spin: a protocol bug or a faulting copy must surface as a launch failure, not hang the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spin & 0xFFFu) == 0xFFFu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 8000000000ll) __trap();  // (no printf: its stack frame costs the kernel registers)
+        }
+    }
+}
+
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
@@ -269,8 +282,7 @@ snip_runs_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, 
         bulk_load(tab_base + b * tab_bytes, tabs + (long long)row * ld_tab, tab_bytes, bar + 8u + 8u * b);
     };
     auto wait_table = [&](uint32_t g) {
-        while (!mbar_try_wait(bar + 8u + 8u * (g & 1u), (g >> 1) & 1u)) {
-        }
+        mbar_wait_bounded(bar + 8u + 8u * (g & 1u), (g >> 1) & 1u);
         return tab_base + (g & 1u) * tab_bytes;
     };
 
@@ -291,8 +303,7 @@ snip_runs_kernel(const T *__restrict__ spec, long long n_px, long long ld_spec, 
     for (long long quad = blockIdx.x; quad < n_quad; quad += gridDim.x, parity ^= 1u) {
         const long long px0 = quad * kRunPix;
         float4 cur[R];
-        while (!mbar_try_wait(bar, parity)) {
-        }
+        mbar_wait_bounded(bar, parity);
 
         // ---- boxcar mean (zero padded, bkg.py:93-97) and log1p (bkg.py:100-101) from the staged rows --------------
         // (every thread takes part: the halo channels travel by warp shuffle; runs past the window compute values that
