@@ -195,6 +195,46 @@ def compile_terms(params, components, e_consts, elem_info, use_step=True, use_ta
 def snip_tables(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
     """Gather indices of every SNIP clipping pass: uint32 [n_pass, n_ch], lo | hi << 16.
 
+    The fp32 operation sequence of bkg.py:83-91 (widths), 104-112 (pass schedule) and 57-62 (clamp, then truncate to
+    int) in NumPy: IEEE single-precision adds, multiplies, divisions and square roots round identically in both
+    libraries, parameters given as 0-dim tensors enter as float32 scalars and Python floats as weakly typed scalars
+    exactly as under torch's promotion rules, and the indices of all passes are formed in one vectorised step.
+    Bit-identical to snip_tables_torch (the reference's ops verbatim) on every case of tests/test_tables.py; a
+    fifth of its time -- it runs once per trial point of fit_spec(tune_params=True)."""
+    if n_ch > 65535:
+        raise ValueError("snip tables hold 16-bit channel indices")
+
+    def operand(v):
+        return f32(v.detach().cpu().to(torch.float32).item()) if isinstance(v, torch.Tensor) else v
+
+    e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime = map(
+        operand, (e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime))
+    idx = np.arange(n_ch, dtype=np.float32)
+    gidx = idx + f32(ch0)
+    energy = (e_offset + (e_slope * gidx) + (e_quad * (gidx * gidx))).astype(np.float32)
+    if isinstance(fwhm_offset, np.floating):
+        t = fwhm_offset / f32(2.3548)
+        first = t * t
+    else:
+        first = (fwhm_offset / 2.3548) ** 2  # Python floats: double arithmetic, rounded when it meets the tensor
+    sigma_sq = np.maximum((first + energy * 2.96 * fwhm_fanoprime).astype(np.float32), f32(0.0))
+    width = ((snip_width * 2.35 * np.sqrt(sigma_sq)).astype(np.float32) / f32(e_slope)).astype(np.float32)
+    widths = [width, width]
+    while float(width.max()) >= 0.5:
+        widths.append(width)
+        width = width / f32(M_SQRT2)
+        if len(widths) > 4096:
+            raise ValueError("SNIP width does not shrink (check ENERGY_SLOPE / SNIP_WIDTH)")
+    w = np.stack(widths)
+    lo = np.clip(idx[None, :] - w, f32(0), f32(n_ch - 1)).astype(np.int64)
+    hi = np.clip(idx[None, :] + w, f32(0), f32(n_ch - 1)).astype(np.int64)
+    return np.ascontiguousarray((lo | (hi << 16)).astype(np.uint32))
+
+
+def snip_tables_torch(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+    """The table builder written with the reference's own torch CPU ops (bkg.py:83-91, 104-112, 57-62): what
+    snip_tables is checked against (tests/test_tables.py); uint32 [n_pass, n_ch], lo | hi << 16.
+
     Same torch-CPU op sequence as bkg.py:83-91 (widths), 104-112 (pass schedule) and 57-62
     (clamp, then truncate to int), so the indices are bit-identical to the reference's."""
     if n_ch > 65535:

@@ -159,3 +159,25 @@ def test_index_tables_under_random_calibrations():
         assert np.array_equal(np.array(got), wins)
         rr = util.get_peak_ranges(elems, e0, angle, off, slope, quad, (er0, er1))
         assert zlib.crc32(np.array(list(rr.values()), dtype=np.int64).tobytes()) == rcrc
+
+
+def test_snip_tables_numpy_builder_equals_the_torch_op_sequence():
+    """tables.snip_tables forms the SNIP window indices with NumPy; tables.snip_tables_torch is the same computation
+    written with the reference's own torch CPU ops (bkg.py:57-62, 83-112).  They must agree bit for bit -- for Python
+    float parameters, 0-dim tensor parameters and mixtures (the promotion rules differ in where double arithmetic
+    happens), every window size the kernels serve, and widths that make the pass count vary."""
+    import torch
+
+    from mapstorch_b200 import tables
+
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        n_ch = int(rng.choice([8, 512, 1401, 2048, 4096]))
+        ch0 = int(rng.integers(0, 100))
+        vals = [rng.uniform(-0.05, 0.05), rng.uniform(0.004, 0.02), rng.uniform(-5e-8, 5e-8), rng.uniform(0.1, 1.5),
+                rng.uniform(0.0, 0.25), rng.uniform(0, 3e-4)]
+        mode = trial % 3
+        args = [torch.tensor(float(v)) if (mode == 1 or (mode == 2 and rng.random() < 0.5)) else float(v) for v in vals]
+        ref = tables.snip_tables_torch(n_ch, ch0, *args)
+        got = tables.snip_tables(n_ch, ch0, *args)
+        assert got.dtype == ref.dtype and got.shape == ref.shape and np.array_equal(got, ref), (trial, n_ch, ch0, vals)
