@@ -38,7 +38,23 @@ struct StreamScratch {
     StreamScratch &operator=(const StreamScratch &) = delete;
     cudaError_t alloc(size_t bytes, cudaStream_t s) {
         stream = s;
+        keep_pool_memory();
         return cudaMallocAsync(reinterpret_cast<void **>(&ptr), bytes, s);
+    }
+    // The default memory pool hands freed blocks back to the driver at the next synchronisation (release threshold
+    // 0), so an entry point called in a host loop -- mt_model_terms once per trial point of fit_spec(tune_params=True)
+    // -- paid a driver allocation per call: 0.27 s per fit in a fresh process, 0.5-1.7 s after other work had freed
+    // gigabytes.  Keep what the pool has (these scratch blocks are kilobytes).
+    static void keep_pool_memory() {
+        static bool done[64] = {false};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        done[dev] = true;
     }
     ~StreamScratch() {
         if (ptr) cudaFreeAsync(ptr, stream);
