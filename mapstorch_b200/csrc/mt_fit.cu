@@ -52,6 +52,11 @@ struct FitParams {
     float *x;
     const float *colscale;
     int n_tiles;
+    // tile schedule: every CTA takes k_full whole tiles (tile = block + k * grid), then ONE partial tile of the remainder
+    // region [rem_row0, n_px): rem_base (+1 for the first rem_extra CTAs) granules of 64 pixels, contiguous per CTA
+    int k_full, rem_base, rem_extra;
+    long long rem_row0;
+    uint32_t idesc64;  // instruction descriptor of the 64-row MMA of a partial tile's last sub-tile
     int kb_begin, kb_end;
     int bke;  // elements per k-block (64 for fp16, 32 for fp32)
     int n_mma, e_pad, n_comp, n_planes;
@@ -169,8 +174,8 @@ __device__ __forceinline__ bool fixup_small(float (&x)[32], int E, const float *
 
 template <int KIND, int M_TILES>
 __global__ void __launch_bounds__(kFitThreads, 1)
-fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_constant__ CUtensorMap tm_w,
-                    const FitParams p) {
+fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_constant__ CUtensorMap tm_spec64,
+                    const __grid_constant__ CUtensorMap tm_w, const FitParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t ring = (raw_addr + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
@@ -188,9 +193,26 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_rows = kTileRows * M_TILES;
     const uint32_t acc_cols = (uint32_t)(M_TILES * p.n_mma);
+    // The k-th tile of this CTA: first pixel and size in 64-pixel granules (0: no such tile).  Whole tiles are dealt
+    // round-robin; what is left of the map (less than one tile per CTA) is cut into 64-pixel granules and every CTA
+    // takes its share as one last, partial tile -- a 128-row MMA per full pair of granules, a 64-row MMA for an odd
+    // one -- so that no SM idles through a last wave (c2: 512 half-tiles on 148 SMs ran as 4 rounds for 3.46 of work).
+    constexpr int kGranPerTile = 2 * M_TILES;
+    auto tile_at = [&](int k, long long &row0) -> int {
+        if (k < p.k_full) {
+            const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+            row0 = tile * block_rows;
+            return tile < p.n_tiles ? kGranPerTile : 0;
+        }
+        if (k > p.k_full) return 0;
+        const int b = (int)blockIdx.x;
+        row0 = p.rem_row0 + 64ll * ((long long)b * p.rem_base + (b < p.rem_extra ? b : p.rem_extra));
+        return p.rem_base + (b < p.rem_extra ? 1 : 0);
+    };
 
     if (threadIdx.x == 0) {
         prefetch_tensormap(&tm_spec);
+        prefetch_tensormap(&tm_spec64);
         prefetch_tensormap(&tm_w);
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(full_bar(s), 1);
@@ -220,13 +242,25 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int row0 = tile * block_rows;
+            for (int k = 0;; ++k) {
+                long long row0;
+                const int n_gran = tile_at(k, row0);
+                if (n_gran == 0) break;
+                const uint32_t w_bytes = (uint32_t)(p.n_mma * kRowBytes);
                 for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t dst = ring + (uint32_t)stage * p.stage_bytes;
-                    mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
-                    tma_load_2d(dst, &tm_spec, full_bar(stage), kb * p.bke, row0, kEvictFirst);
+                    if (n_gran == kGranPerTile) {
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                        tma_load_2d(dst, &tm_spec, full_bar(stage), kb * p.bke, (int)row0, kEvictFirst);
+                    } else {
+                        // partial tile: one 64-row box per granule (stacked boxes = the layout of a taller one: the
+                        // 128-byte swizzle repeats every 8 rows)
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)n_gran * (kSubTileBytes / 2) + w_bytes);
+                        for (int g = 0; g < n_gran; ++g)
+                            tma_load_2d(dst + (uint32_t)g * (kSubTileBytes / 2), &tm_spec64, full_bar(stage), kb * p.bke,
+                                        (int)row0 + 64 * g, kEvictFirst);
+                    }
                     tma_load_2d(dst + M_TILES * kSubTileBytes, &tm_w, full_bar(stage), kb * p.bke, 0, kEvictLast);
                     if (++stage == p.n_stages) {
                         stage = 0;
@@ -242,7 +276,11 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int k = 0;; ++k) {
+                long long row0;
+                const int n_gran = tile_at(k, row0);
+                if (n_gran == 0) break;
+                const int n_sub = (n_gran + 1) >> 1;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
@@ -252,13 +290,16 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                     const uint64_t w_desc = umma_desc_sw128(a_addr + M_TILES * kSubTileBytes);
 #pragma unroll
                     for (int mt = 0; mt < M_TILES; ++mt) {
-                        const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kSubTileBytes);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+                        if (mt < n_sub) {
+                            const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kSubTileBytes);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
+                            const uint32_t idesc = (mt == n_sub - 1 && (n_gran & 1)) ? p.idesc64 : p.idesc;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // 32 bytes (16 fp16 / 8 tf32) along K per instruction: +2 in 16-byte units
-                            tc_mma<KIND>(d_tmem, a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), p.idesc,
-                                         (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                // 32 bytes (16 fp16 / 8 tf32) along K per instruction: +2 in 16-byte units
+                                tc_mma<KIND>(d_tmem, a_desc + (uint64_t)(2 * kk), w_desc + (uint64_t)(2 * kk), idesc,
+                                             (kb > p.kb_begin || kk > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
@@ -280,7 +321,19 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int k = 0;; ++k) {
+            long long row0;
+            const int n_gran = tile_at(k, row0);
+            if (n_gran == 0) break;
+            const int n_sub = (n_gran + 1) >> 1;
+            // pixel of this lane in sub-tile mt: a 128-row MMA fills all 32 lanes of the warp's TMEM quarter, the 64-row
+            // MMA of an odd last granule only lanes 0..15 (rows 16 q .. 16 q + 15)
+            auto pixel_of = [&](int mt, bool &valid) -> long long {
+                const bool m64 = (mt == n_sub - 1) && (n_gran & 1);
+                const long long px = row0 + mt * kTileRows + (m64 ? q * 16 + lane : q * 32 + lane);
+                valid = mt < n_sub && (!m64 || lane < 16) && px < p.n_px;
+                return px;
+            };
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (p.reg_path) {
@@ -293,7 +346,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                         tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
 #pragma unroll
                     for (int c0 = 0; c0 < 32; c0 += 8) {
-                        if (c0 < p.e_pad) {
+                        if (c0 < p.e_pad && mt < n_sub) {
                             float a8[8], part[8];
                             tmem_ld8(taddr + (uint32_t)((p.n_planes - 1) * p.e_pad + c0), a8);
                             tmem_ld_wait();
@@ -316,13 +369,14 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
 #pragma unroll
                 for (int mt = 0; mt < M_TILES; ++mt) {
-                    const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
+                    bool valid;
+                    const long long px = pixel_of(mt, valid);
                     bool any_neg = false;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) any_neg |= (xv[mt][e] < 0.f);
-                    bool negative = any_neg && px < p.n_px;
+                    bool negative = any_neg && valid;
                     if (negative && p.hinv32 != nullptr) negative = !fixup_small(xv[mt], p.n_comp, hs);
-                    if (px < p.n_px) {
+                    if (valid) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             if (e < p.n_comp) {
@@ -366,7 +420,9 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
             }
 #pragma unroll
             for (int mt = 0; mt < M_TILES; ++mt) {
-                const long long px = (long long)tile * block_rows + mt * kTileRows + q * 32 + lane;
+                if (mt >= n_sub) continue;
+                bool valid;
+                const long long px = pixel_of(mt, valid);
                 const uint32_t taddr =
                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
                 bool negative = false;
@@ -382,7 +438,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], p.plane_ratio, part[j]);
                     }
-                    if (px < p.n_px) {
+                    if (valid) {
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -555,8 +611,8 @@ int make_tile_map(CUtensorMap *map, const void *base, int dtype, uint64_t cols, 
 }
 
 template <int KIND, int M_TILES>
-int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_w, const FitParams &p, size_t smem, int grid,
-               cudaStream_t stream) {
+int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_spec64, const CUtensorMap &tm_w, const FitParams &p,
+               size_t smem, int grid, cudaStream_t stream) {
     auto kern = fit_contract_kernel<KIND, M_TILES>;
     static int smem_set[16] = {0};  // per device: opt in to the large dynamic smem carve-out once
     int dev = 0;
@@ -565,7 +621,7 @@ int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_w, const FitPar
         MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         if (dev < 16) smem_set[dev] = kSmemLimit;
     }
-    kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_w, p);
+    kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_spec64, tm_w, p);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
@@ -658,20 +714,43 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.idesc = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, kTileRows, p.n_mma);
     const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
 
-    CUtensorMap tm_spec, tm_w;
+    CUtensorMap tm_spec, tm_spec64, tm_w;
     if (int rc = make_tile_map(&tm_spec, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec,
                                (uint32_t)block_rows))
+        return rc;
+    if (int rc = make_tile_map(&tm_spec64, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec, 64u))
         return rc;
     if (int rc = make_tile_map(&tm_w, wpack_dev, dtype, (uint64_t)n_ch_total, (uint64_t)p.n_mma, (uint64_t)ld_w,
                                (uint32_t)p.n_mma))
         return rc;
     const int sms = mt::num_sms();
-    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    // Tile schedule (see the kernel): whole tiles round-robin, then the remainder in 64-pixel granules, one partial tile
+    // per CTA.  MT_FIT_TAIL=0 restores whole tiles only (the last wave then runs partly empty).
+    static const bool tail = [] {
+        const char *v = getenv("MT_FIT_TAIL");
+        return !(v && atoi(v) == 0);
+    }();
+    const long long n_gran = (n_px + 63) / 64;
+    const int gran_per_tile = 2 * m_tiles;
+    int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    if (tail) {
+        grid = (int)(n_gran < sms ? n_gran : sms);
+        p.k_full = (int)(n_gran / ((long long)gran_per_tile * grid));
+        const long long rem = n_gran - (long long)p.k_full * gran_per_tile * grid;  // < gran_per_tile * grid
+        p.rem_base = (int)(rem / grid);
+        p.rem_extra = (int)(rem % grid);
+        p.rem_row0 = (long long)p.k_full * grid * block_rows;
+    } else {
+        p.k_full = (p.n_tiles + grid - 1) / grid;
+        p.rem_base = p.rem_extra = 0;
+        p.rem_row0 = 0;
+    }
+    p.idesc64 = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, 64, p.n_mma);
     if (dtype == MT_DTYPE_F16)
-        return m_tiles == 2 ? launch_fit<0, 2>(tm_spec, tm_w, p, smem, grid, stream)
-                            : launch_fit<0, 1>(tm_spec, tm_w, p, smem, grid, stream);
-    return m_tiles == 2 ? launch_fit<1, 2>(tm_spec, tm_w, p, smem, grid, stream)
-                        : launch_fit<1, 1>(tm_spec, tm_w, p, smem, grid, stream);
+        return m_tiles == 2 ? launch_fit<0, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)
+                            : launch_fit<0, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream);
+    return m_tiles == 2 ? launch_fit<1, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)
+                        : launch_fit<1, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream);
 }
 
 extern "C" int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,

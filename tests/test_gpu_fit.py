@@ -452,3 +452,30 @@ def test_caller_buffer_rows_of_dead_components_are_zeroed():
     out = torch.full((len(plan.names), 32), 7.0, device="cuda")
     plan.fit(torch.from_numpy(y).cuda(), out=out)
     assert float(out[plan.names.index("Pb_L")].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n_px", [64, 100, 148 * 64 + 37, 148 * 64 * 2 - 17, 148 * 64 * 3 - 5, 148 * 64 * 5 + 130])
+def test_partial_last_tiles_of_every_granule_count(n_px):
+    """K3's tile schedule (csrc/mt_fit.cu): whole 256-pixel tiles round-robin, then the rest of the map in 64-pixel
+    granules, one partial tile per CTA -- one, two or three granules, i.e. a 64-row MMA, a 128-row MMA, or both, with the
+    64-row accumulator in lanes 0..15 of every TMEM quarter.  Every pixel must still be the float64 least-squares fit
+    (exact integer accumulation: 5e-7 of the pixel maximum), wherever in the schedule it falls."""
+    from mapstorch_b200 import opt
+    from oracle import maps_oracle as mo
+
+    p = params12(2048)
+    er = (0, 2047)
+    y, names = synth(p, er, ELEMS10, 2048, seed=3)
+    reps = -(-n_px // y.shape[0])
+    idx = np.random.default_rng(n_px).integers(0, y.shape[0], size=n_px)  # pixels drawn with repetition, in random order
+    yy = y[idx]
+    plan = opt.MapFitPlan(er, ELEMS10, p, use_snip=False)
+    B, _ = mo.basis(p, er, ELEMS10)
+    ref = mo.fit_lstsq(y, B)[idx]
+    for dtype in (torch.float16, torch.float32):
+        x = plan.fit(torch.from_numpy(yy).to("cuda", dtype), nonneg=False).cpu().numpy().T
+        assert x.shape == ref.shape and reps >= 1
+        assert (np.abs(x - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() <= 5e-7
+    # and the non-negative path through the epilogue fix-up on the same partial tiles
+    xn = plan.fit(torch.from_numpy(yy).cuda(), nonneg=True).cpu().numpy().T
+    assert xn.min() >= 0 and (np.abs(xn - np.maximum(ref, 0)) / np.abs(ref).max(axis=1, keepdims=True)).max() <= 1e-3
