@@ -267,6 +267,42 @@ constexpr int kListWarps = 4;
 // per 131 072-pixel shard).  The count lives on the device, so both kernels are launched and one returns at once.
 constexpr int kShortListMax = 6144;
 
+// Row `lane` of the Gauss-Jordan solve of H[a_r, a_c] z = v over the n <= NMAX zero-set components (a = this lane's
+// component, v = its right-hand side): returns z of this row (0 for lanes >= n).  Registers and shuffles only.
+template <int NMAX>
+__device__ __forceinline__ double gauss_jordan_row(const double *Hs, int E, int a, int n, int lane, double v) {
+    double M[NMAX];
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) {
+        M[c] = 0.0;
+        if (c < n) {
+            const int ac = __shfl_sync(0xffffffffu, a, c);
+            M[c] = (lane < n) ? Hs[a * E + ac] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+        if (k < n) {
+            const double pkk = __shfl_sync(0xffffffffu, M[k], k);
+            const double pv = __shfl_sync(0xffffffffu, v, k);
+            const double f = (lane != k && lane < n) ? M[k] / pkk : 0.0;
+#pragma unroll
+            for (int c = k + 1; c < NMAX; ++c) {
+                if (c < n) {
+                    const double pc = __shfl_sync(0xffffffffu, M[c], k);
+                    M[c] -= f * pc;
+                }
+            }
+            v -= f * pv;
+        }
+    }
+    double diag = 1.0;
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c)
+        if (c == lane) diag = M[c];
+    return (lane < n) ? v / diag : 0.0;
+}
+
 __global__ void __launch_bounds__(kListWarps * 32)
 nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ list,
                  const int *__restrict__ count, int E, const double *__restrict__ h_dev, const MtPeers peers) {
@@ -297,36 +333,17 @@ nnls_warp_kernel(float *__restrict__ x, long long ld_x, const int *__restrict__ 
             const int n = __popc(A);
             const int a = (lane < n) ? (int)__fns(A, 0, lane + 1) : 0;  // component of my system row
             double v = __shfl_sync(0xffffffffu, xu, a);
-            double M[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                M[c] = 0.0;
-                if (c < n) {
-                    const int ac = __shfl_sync(0xffffffffu, a, c);
-                    M[c] = (lane < n) ? Hs[a * E + ac] : 0.0;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k < n) {
-                    const double pkk = __shfl_sync(0xffffffffu, M[k], k);
-                    const double pv = __shfl_sync(0xffffffffu, v, k);
-                    const double f = (lane != k && lane < n) ? M[k] / pkk : 0.0;
-#pragma unroll
-                    for (int c = k + 1; c < 32; ++c) {
-                        if (c < n) {
-                            const double pc = __shfl_sync(0xffffffffu, M[c], k);
-                            M[c] -= f * pc;
-                        }
-                    }
-                    v -= f * pv;
-                }
-            }
-            double diag = 1.0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (c == lane) diag = M[c];
-            const double z = (lane < n) ? v / diag : 0.0;
+            // the elimination is unrolled to the smallest of four sizes that holds the zero set: with 32-wide loops a
+            // three-component system (the common case here) issued the predicated-off instructions of all 496 pairs
+            double z;
+            if (n <= 4)
+                z = gauss_jordan_row<4>(Hs, E, a, n, lane, v);
+            else if (n <= 8)
+                z = gauss_jordan_row<8>(Hs, E, a, n, lane, v);
+            else if (n <= 16)
+                z = gauss_jordan_row<16>(Hs, E, a, n, lane, v);
+            else
+                z = gauss_jordan_row<32>(Hs, E, a, n, lane, v);
             const bool active = (A >> lane) & 1u;
             xs = xu;
             for (int r = 0; r < n; ++r) {
