@@ -172,7 +172,15 @@ __device__ __forceinline__ bool fixup_small(float (&x)[32], int E, const float *
     return settled;
 }
 
-template <int KIND, int M_TILES>
+// CL > 1: clusters of CL CTAs share every slab of the pseudo-inverse pack -- CTA r of a cluster loads rows
+// [r, r + 1) * N / CL of it and the TMA multicasts them into the same stage of all CL rings, so the pack crosses the L2
+// once per cluster and k-block instead of once per CTA.  Measured why: the streaming rate follows
+// 7.8 TB/s / (1 + pack slab / spectra slab) -- 6.5 TB/s at N = 48, 6.1 at N = 72, 5.6-5.8 at N = 96 -- i.e. the L2's
+// aggregate delivery rate bounds the kernel, not HBM, and a third of what it delivered at N = 96 was the pack.
+// The CTAs of a cluster walk their tiles in lockstep (stage by stage: a stage is refilled when ALL of them have
+// consumed it -- the MMA warps commit to every CTA's empty barrier); a CTA with one tile less runs a round without
+// spectra so that its partners still get their slabs.
+template <int KIND, int M_TILES, int CL>
 __global__ void __launch_bounds__(kFitThreads, 1)
 fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_constant__ CUtensorMap tm_spec64,
                     const __grid_constant__ CUtensorMap tm_w, const FitParams p) {
@@ -198,17 +206,27 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
     // takes its share as one last, partial tile -- a 128-row MMA per full pair of granules, a 64-row MMA for an odd
     // one -- so that no SM idles through a last wave (c2: 512 half-tiles on 148 SMs ran as 4 rounds for 3.46 of work).
     constexpr int kGranPerTile = 2 * M_TILES;
-    auto tile_at = [&](int k, long long &row0) -> int {
+    auto tile_of = [&](int b, int k, long long &row0) -> int {
         if (k < p.k_full) {
-            const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+            const long long tile = (long long)b + (long long)k * gridDim.x;
             row0 = tile * block_rows;
             return tile < p.n_tiles ? kGranPerTile : 0;
         }
         if (k > p.k_full) return 0;
-        const int b = (int)blockIdx.x;
         row0 = p.rem_row0 + 64ll * ((long long)b * p.rem_base + (b < p.rem_extra ? b : p.rem_extra));
         return p.rem_base + (b < p.rem_extra ? 1 : 0);
     };
+    auto tile_at = [&](int k, long long &row0) -> int { return tile_of((int)blockIdx.x, k, row0); };
+    // rounds of the cluster: the largest tile count among its CTAs
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+    int rounds = 0;
+    for (int j = 0; j < CL; ++j) {
+        int n = 0;
+        long long r0;
+        while (tile_of((int)blockIdx.x - (int)crank + j, n, r0) != 0) ++n;
+        rounds = n > rounds ? n : rounds;
+    }
 
     if (threadIdx.x == 0) {
         prefetch_tensormap(&tm_spec);
@@ -216,7 +234,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         prefetch_tensormap(&tm_w);
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL);  // one commit from the MMA warp of every CTA of the cluster
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -236,16 +254,16 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a partner multicasts into them
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int k = 0;; ++k) {
-                long long row0;
-                const int n_gran = tile_at(k, row0);
-                if (n_gran == 0) break;
+            for (int k = 0; k < rounds; ++k) {
+                long long row0 = 0;
+                const int n_gran = tile_at(k, row0);  // 0: a round for the partners' sake (CL > 1 only)
                 const uint32_t w_bytes = (uint32_t)(p.n_mma * kRowBytes);
                 for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -261,7 +279,13 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                             tma_load_2d(dst + (uint32_t)g * (kSubTileBytes / 2), &tm_spec64, full_bar(stage), kb * p.bke,
                                         (int)row0 + 64 * g, kEvictFirst);
                     }
-                    tma_load_2d(dst + M_TILES * kSubTileBytes, &tm_w, full_bar(stage), kb * p.bke, 0, kEvictLast);
+                    if (CL == 1) {
+                        tma_load_2d(dst + M_TILES * kSubTileBytes, &tm_w, full_bar(stage), kb * p.bke, 0, kEvictLast);
+                    } else {
+                        const int part_rows = p.n_mma / CL;
+                        tma_load_2d_multicast(dst + M_TILES * kSubTileBytes + crank * (uint32_t)(part_rows * kRowBytes), &tm_w,
+                                              full_bar(stage), kb * p.bke, (int)crank * part_rows, kClusterMask, kEvictLast);
+                    }
                     if (++stage == p.n_stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -276,13 +300,14 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int k = 0;; ++k) {
+            for (int k = 0; k < rounds; ++k) {
                 long long row0;
-                const int n_gran = tile_at(k, row0);
-                if (n_gran == 0) break;
+                const int n_gran = tile_at(k, row0);  // 0: nothing to multiply, the stages are only released
                 const int n_sub = (n_gran + 1) >> 1;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
-                tc_fence_after();
+                if (n_gran) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                    tc_fence_after();
+                }
                 for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
                     mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
                     tc_fence_after();
@@ -302,16 +327,22 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                             }
                         }
                     }
-                    tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+                    // frees the smem stage once these MMAs retire -- in every ring of the cluster
+                    if (CL == 1)
+                        tc_commit(empty_bar(stage));
+                    else
+                        tc_commit_multicast(empty_bar(stage), kClusterMask);
                     if (++stage == p.n_stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                if (n_gran) {
+                    tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1u;
+                    }
                 }
             }
         }
@@ -506,6 +537,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no partner may still write into this CTA's stages or barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -610,10 +642,10 @@ int make_tile_map(CUtensorMap *map, const void *base, int dtype, uint64_t cols, 
     return MT_OK;
 }
 
-template <int KIND, int M_TILES>
+template <int KIND, int M_TILES, int CL>
 int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_spec64, const CUtensorMap &tm_w, const FitParams &p,
                size_t smem, int grid, cudaStream_t stream) {
-    auto kern = fit_contract_kernel<KIND, M_TILES>;
+    auto kern = fit_contract_kernel<KIND, M_TILES, CL>;
     static int smem_set[16] = {0};  // per device: opt in to the large dynamic smem carve-out once
     int dev = 0;
     cudaGetDevice(&dev);
@@ -621,9 +653,50 @@ int launch_fit(const CUtensorMap &tm_spec, const CUtensorMap &tm_spec64, const C
         MT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         if (dev < 16) smem_set[dev] = kSmemLimit;
     }
-    kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_spec64, tm_w, p);
+    if (CL == 1) {
+        kern<<<grid, kFitThreads, smem, stream>>>(tm_spec, tm_spec64, tm_w, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kFitThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm_spec, tm_spec64, tm_w, p));
+    }
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
+}
+
+// CTAs of clusters of CL that can be resident at once with this kernel's shared memory (one CTA per SM): the
+// GPCs do not all hold a multiple of CL SMs.  0 if the query fails.
+template <int KIND, int M_TILES, int CL>
+int resident_cluster_ctas(size_t smem) {
+    auto kern = fit_contract_kernel<KIND, M_TILES, CL>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(mt::num_sms() / CL * CL));
+    cfg.blockDim = dim3(kFitThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n * CL;
 }
 
 }  // namespace
@@ -714,15 +787,6 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     p.idesc = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, kTileRows, p.n_mma);
     const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
 
-    CUtensorMap tm_spec, tm_spec64, tm_w;
-    if (int rc = make_tile_map(&tm_spec, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec,
-                               (uint32_t)block_rows))
-        return rc;
-    if (int rc = make_tile_map(&tm_spec64, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec, 64u))
-        return rc;
-    if (int rc = make_tile_map(&tm_w, wpack_dev, dtype, (uint64_t)n_ch_total, (uint64_t)p.n_mma, (uint64_t)ld_w,
-                               (uint32_t)p.n_mma))
-        return rc;
     const int sms = mt::num_sms();
     // Tile schedule (see the kernel): whole tiles round-robin, then the remainder in 64-pixel granules, one partial tile
     // per CTA.  MT_FIT_TAIL=0 restores whole tiles only (the last wave then runs partly empty).
@@ -730,27 +794,70 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
         const char *v = getenv("MT_FIT_TAIL");
         return !(v && atoi(v) == 0);
     }();
+    // Clusters of 2 CTAs share the pack slabs by TMA multicast (MT_FIT_CLUSTER=1 switches it off): only for problems
+    // that give every CTA work, pack halves of whole 8-row swizzle atoms, and where (nearly) all SMs can host a cluster
+    static const int cluster_pref = [] {
+        const char *v = getenv("MT_FIT_CLUSTER");
+        return v ? atoi(v) : 2;
+    }();
     const long long n_gran = (n_px + 63) / 64;
     const int gran_per_tile = 2 * m_tiles;
-    int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    int grid = sms;
+    int cl = 1;
+    if (tail && cluster_pref == 2 && n_gran >= 2ll * gran_per_tile * sms && (p.n_mma / 2) % 8 == 0) {
+        static int cached[2][2][16];  // [dtype][m_tiles - 1][device]: resident cluster CTAs + 1 (0 = not asked yet)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &slot = cached[dtype == MT_DTYPE_F16 ? 0 : 1][m_tiles - 1][dev & 15];
+        if (slot == 0) {
+            const size_t smem_guess = (size_t)kSmemLimit;
+            int n = 0;
+            if (dtype == MT_DTYPE_F16)
+                n = m_tiles == 2 ? resident_cluster_ctas<0, 2, 2>(smem_guess) : resident_cluster_ctas<0, 1, 2>(smem_guess);
+            else
+                n = m_tiles == 2 ? resident_cluster_ctas<1, 2, 2>(smem_guess) : resident_cluster_ctas<1, 1, 2>(smem_guess);
+            slot = n + 1;
+        }
+        const int resident = slot - 1;
+        if (resident >= sms - 4 && resident >= 2) {
+            cl = 2;
+            grid = resident < sms ? resident : (sms / 2) * 2;
+        }
+    }
+    if (const char *cap = getenv("MT_FIT_GRID")) {  // measurement knob: fewer CTAs than SMs
+        const int c = atoi(cap);
+        if (c >= 2 && c < grid) grid = cl == 2 ? (c / 2) * 2 : c;
+    }
     if (tail) {
-        grid = (int)(n_gran < sms ? n_gran : sms);
+        if (cl == 1) grid = (int)(n_gran < grid ? n_gran : grid);
         p.k_full = (int)(n_gran / ((long long)gran_per_tile * grid));
         const long long rem = n_gran - (long long)p.k_full * gran_per_tile * grid;  // < gran_per_tile * grid
         p.rem_base = (int)(rem / grid);
         p.rem_extra = (int)(rem % grid);
         p.rem_row0 = (long long)p.k_full * grid * block_rows;
     } else {
+        grid = p.n_tiles < grid ? p.n_tiles : grid;
         p.k_full = (p.n_tiles + grid - 1) / grid;
         p.rem_base = p.rem_extra = 0;
         p.rem_row0 = 0;
     }
     p.idesc64 = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, 64, p.n_mma);
-    if (dtype == MT_DTYPE_F16)
-        return m_tiles == 2 ? launch_fit<0, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)
-                            : launch_fit<0, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream);
-    return m_tiles == 2 ? launch_fit<1, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)
-                        : launch_fit<1, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream);
+
+    CUtensorMap tm_spec, tm_spec64, tm_w;
+    if (int rc = make_tile_map(&tm_spec, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec,
+                               (uint32_t)block_rows))
+        return rc;
+    if (int rc = make_tile_map(&tm_spec64, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec, 64u))
+        return rc;
+    if (int rc = make_tile_map(&tm_w, wpack_dev, dtype, (uint64_t)n_ch_total, (uint64_t)p.n_mma, (uint64_t)ld_w,
+                               (uint32_t)(p.n_mma / cl)))
+        return rc;
+#define MT_FIT_LAUNCH(K, M)                                                                              \
+    (cl == 2 ? launch_fit<K, M, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)                         \
+             : launch_fit<K, M, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream))
+    if (dtype == MT_DTYPE_F16) return m_tiles == 2 ? MT_FIT_LAUNCH(0, 2) : MT_FIT_LAUNCH(0, 1);
+    return m_tiles == 2 ? MT_FIT_LAUNCH(1, 2) : MT_FIT_LAUNCH(1, 1);
+#undef MT_FIT_LAUNCH
 }
 
 extern "C" int mt_fit_contract_simt(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec,

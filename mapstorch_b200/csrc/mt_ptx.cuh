@@ -55,6 +55,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint
         : "memory");
 }
 
+// the same load delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of every
+// CTA of the cluster whose bit is set in cta_mask: one L2 read instead of one per CTA
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1,
+                                                      uint16_t cta_mask, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t n_cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(n_cols)
@@ -75,6 +95,13 @@ __device__ __forceinline__ void tc_fence_after() {
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// the same arrival on the mbarrier at this offset in every CTA of the mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
                  : "memory");
 }
 

@@ -454,11 +454,15 @@ def test_caller_buffer_rows_of_dead_components_are_zeroed():
     assert float(out[plan.names.index("Pb_L")].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n_px", [64, 100, 148 * 64 + 37, 148 * 64 * 2 - 17, 148 * 64 * 3 - 5, 148 * 64 * 5 + 130])
+@pytest.mark.parametrize("n_px", [64, 100, 148 * 64 + 37, 148 * 64 * 2 - 17, 148 * 64 * 3 - 5, 148 * 64 * 5 + 130,
+                                  148 * 64 * 8 + 64 * 77 + 17, 148 * 64 * 9 + 64 * 3 + 1])
 def test_partial_last_tiles_of_every_granule_count(n_px):
     """K3's tile schedule (csrc/mt_fit.cu): whole 256-pixel tiles round-robin, then the rest of the map in 64-pixel
     granules, one partial tile per CTA -- one, two or three granules, i.e. a 64-row MMA, a 128-row MMA, or both, with the
-    64-row accumulator in lanes 0..15 of every TMEM quarter.  Every pixel must still be the float64 least-squares fit
+    64-row accumulator in lanes 0..15 of every TMEM quarter.  The two largest sizes give every CTA at least two whole
+    tiles, which switches on the clusters of two CTAs that share the pack slabs by TMA multicast and walk their tiles in
+    lockstep -- with partners whose last tiles differ in size, and (the last case) partners of which only one HAS a
+    last tile, so that the other runs a round without spectra.  Every pixel must still be the float64 least-squares fit
     (exact integer accumulation: 5e-7 of the pixel maximum), wherever in the schedule it falls."""
     from mapstorch_b200 import opt
     from oracle import maps_oracle as mo
