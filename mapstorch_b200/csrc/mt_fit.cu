@@ -57,6 +57,7 @@ struct FitParams {
     int k_full, rem_base, rem_extra;
     long long rem_row0;
     uint32_t idesc64;  // instruction descriptor of the 64-row MMA of a partial tile's last sub-tile
+    int debug;         // measurement knobs (MT_FIT_DEBUG bit mask): 1 no stores, 2 no pack loads, 4 no MMAs, 8 no fix-up
     int kb_begin, kb_end;
     int bke;  // elements per k-block (64 for fp16, 32 for fp32)
     int n_mma, e_pad, n_comp, n_planes;
@@ -269,17 +270,19 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t dst = ring + (uint32_t)stage * p.stage_bytes;
                     if (n_gran == kGranPerTile) {
-                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes - ((p.debug & 2) ? w_bytes : 0u));
                         tma_load_2d(dst, &tm_spec, full_bar(stage), kb * p.bke, (int)row0, kEvictFirst);
                     } else {
                         // partial tile: one 64-row box per granule (stacked boxes = the layout of a taller one: the
                         // 128-byte swizzle repeats every 8 rows)
-                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)n_gran * (kSubTileBytes / 2) + w_bytes);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)n_gran * (kSubTileBytes / 2) + ((p.debug & 2) ? 0u : w_bytes));
                         for (int g = 0; g < n_gran; ++g)
                             tma_load_2d(dst + (uint32_t)g * (kSubTileBytes / 2), &tm_spec64, full_bar(stage), kb * p.bke,
                                         (int)row0 + 64 * g, kEvictFirst);
                     }
-                    if (CL == 1) {
+                    if (p.debug & 2) {
+                        // (results are garbage: the MMAs read whatever the stage holds)
+                    } else if (CL == 1) {
                         tma_load_2d(dst + M_TILES * kSubTileBytes, &tm_w, full_bar(stage), kb * p.bke, 0, kEvictLast);
                     } else {
                         const int part_rows = p.n_mma / CL;
@@ -315,7 +318,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                     const uint64_t w_desc = umma_desc_sw128(a_addr + M_TILES * kSubTileBytes);
 #pragma unroll
                     for (int mt = 0; mt < M_TILES; ++mt) {
-                        if (mt < n_sub) {
+                        if (mt < n_sub && !(p.debug & 4)) {
                             const uint64_t a_desc = umma_desc_sw128(a_addr + mt * kSubTileBytes);
                             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + (uint32_t)(mt * p.n_mma);
                             const uint32_t idesc = (mt == n_sub - 1 && (n_gran & 1)) ? p.idesc64 : p.idesc;
@@ -406,8 +409,8 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
 #pragma unroll
                     for (int e = 0; e < 32; ++e) any_neg |= (xv[mt][e] < 0.f);
                     bool negative = any_neg && valid;
-                    if (negative && p.hinv32 != nullptr) negative = !fixup_small(xv[mt], p.n_comp, hs);
-                    if (valid) {
+                    if (negative && p.hinv32 != nullptr && !(p.debug & 8)) negative = !fixup_small(xv[mt], p.n_comp, hs);
+                    if (valid && !(p.debug & 1)) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             if (e < p.n_comp) {
@@ -842,6 +845,13 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
         p.rem_row0 = 0;
     }
     p.idesc64 = umma_idesc(dtype == MT_DTYPE_F16 ? 0 : 2, 64, p.n_mma);
+    {
+        static const int dbg = [] {
+            const char *v = getenv("MT_FIT_DEBUG");
+            return v ? atoi(v) : 0;
+        }();
+        p.debug = dbg;
+    }
 
     CUtensorMap tm_spec, tm_spec64, tm_w;
     if (int rc = make_tile_map(&tm_spec, spec_dev, dtype, (uint64_t)n_ch_total, (uint64_t)n_px, (uint64_t)ld_spec,
