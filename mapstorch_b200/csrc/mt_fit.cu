@@ -23,6 +23,7 @@
 // maximum instead -- measured, see DESIGN.md.
 // Bound: HBM (C*sizeof(in) + E*4 bytes per pixel); tensor-pipe use stays well below peak.
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>
 
@@ -865,8 +866,12 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
 #define MT_FIT_LAUNCH(K, M)                                                                              \
     (cl == 2 ? launch_fit<K, M, 2>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream)                         \
              : launch_fit<K, M, 1>(tm_spec, tm_spec64, tm_w, p, smem, grid, stream))
-    if (dtype == MT_DTYPE_F16) return m_tiles == 2 ? MT_FIT_LAUNCH(0, 2) : MT_FIT_LAUNCH(0, 1);
-    return m_tiles == 2 ? MT_FIT_LAUNCH(1, 2) : MT_FIT_LAUNCH(1, 1);
+    int rc_launch;
+    if (dtype == MT_DTYPE_F16)
+        rc_launch = m_tiles == 2 ? MT_FIT_LAUNCH(0, 2) : MT_FIT_LAUNCH(0, 1);
+    else
+        rc_launch = m_tiles == 2 ? MT_FIT_LAUNCH(1, 2) : MT_FIT_LAUNCH(1, 1);
+    return rc_launch;
 #undef MT_FIT_LAUNCH
 }
 
