@@ -58,6 +58,7 @@ struct FitParams {
     int k_full, rem_base, rem_extra;
     long long rem_row0;
     uint32_t idesc64;  // instruction descriptor of the 64-row MMA of a partial tile's last sub-tile
+    int bulk;          // epilogue stores through shared memory + cp.async.bulk (reg path without peers)
     int debug;         // measurement knobs (MT_FIT_DEBUG bit mask): 1 no stores, 2 no pack loads, 4 no MMAs, 8 no fix-up
     int kb_begin, kb_end;
     int bke;  // elements per k-block (64 for fp16, 32 for fp32)
@@ -250,6 +251,9 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
     }
     for (int e = threadIdx.x; e < p.e_pad; e += kFitThreads) cs[e] = (e < p.n_comp) ? p.colscale[e] : 0.f;
     float *hs = cs + p.e_pad;  // G^-1 for the in-epilogue fix-up (only if p.hinv32)
+    // staging area of the bulk stores: per epilogue warp [32 components][32 pixels] fp32, 128-byte aligned
+    float *stage_all = reinterpret_cast<float *>(
+        (reinterpret_cast<uintptr_t>(hs + (p.hinv32 ? p.n_comp * p.n_comp : 0)) + 127) & ~(uintptr_t)127);
     if (p.hinv32)
         for (int i = threadIdx.x; i < p.n_comp * p.n_comp; i += kFitThreads) hs[i] = p.hinv32[i];
     tc_fence_before();
@@ -411,7 +415,29 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                     for (int e = 0; e < 32; ++e) any_neg |= (xv[mt][e] < 0.f);
                     bool negative = any_neg && valid;
                     if (negative && p.hinv32 != nullptr && !(p.debug & 8)) negative = !fixup_small(xv[mt], p.n_comp, hs);
-                    if (valid && !(p.debug & 1)) {
+                    // Whole groups of 32 pixels leave through shared memory: every lane parks its pixel's values in the
+                    // warp's staging tile and lane e sends component e's 128 bytes with one cp.async.bulk -- the warp does
+                    // not wait for 32 global stores per sub-tile (which cost the epilogue 29 us per tile and kept it
+                    // level with the MMAs) but for nothing.
+                    const bool m64 = (mt == n_sub - 1) && (n_gran & 1);
+                    const bool bulk = p.bulk && !m64 && !(p.debug & 1) && __all_sync(0xffffffffu, valid);
+                    if (bulk) {
+                        float *st = stage_all + (warp - 2) * 1024;
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // my earlier row has been read
+                        __syncwarp();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) st[e * 32 + lane] = xv[mt][e];
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane < p.n_comp) {
+                            float *dst = p.x + (long long)lane * p.ld_x + (px - lane);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst),
+                                         "r"(smem_u32(st + lane * 32))
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    if (valid && !bulk && !(p.debug & 1)) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             if (e < p.n_comp) {
@@ -539,6 +565,7 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
         }
     }
 
+    if (p.bulk && warp >= 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // no partner may still write into this CTA's stages or barriers
@@ -776,8 +803,16 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
     const int block_rows = kTileRows * m_tiles;
     p.n_tiles = (int)((n_px + block_rows - 1) / block_rows);
     p.stage_bytes = (uint32_t)(m_tiles * kSubTileBytes + p.n_mma * kRowBytes);
+    // bulk stores of the epilogue (MT_FIT_BULK_STORE=0 restores scalar stores): register path without peer destinations,
+    // 16-byte aligned component rows
+    static const bool bulk_pref = [] {
+        const char *v = getenv("MT_FIT_BULK_STORE");
+        return !(v && atoi(v) == 0);
+    }();
+    p.bulk = bulk_pref && p.reg_path && p.peers.n_owned == 0 && p.peers.n_peers == 0 && p.peers.multicast == nullptr &&
+             x_layout == MT_X_ELEMENT_MAJOR && (ld_x % 4) == 0 && ((uintptr_t)x_dev & 15) == 0;
     const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64 +
-                         (hinv32_dev ? 4 * (size_t)n_comp * n_comp : 0);
+                         (hinv32_dev ? 4 * (size_t)n_comp * n_comp : 0) + (p.bulk ? 128 + 4 * 4096 : 0);
     p.n_stages = (int)((kSmemLimit - fixed) / p.stage_bytes);
     if (p.n_stages > 12) p.n_stages = 12;
     if (const char *cap = getenv("MT_FIT_MAX_STAGES")) {  // tuning knob (e.g. to leave shared memory to a co-resident kernel)
