@@ -430,11 +430,24 @@ fit_contract_kernel(const __grid_constant__ CUtensorMap tm_spec, const __grid_co
                         fence_proxy_async();
                         __syncwarp();
                         if (lane < p.n_comp) {
-                            float *dst = p.x + (long long)lane * p.ld_x + (px - lane);
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst),
-                                         "r"(smem_u32(st + lane * 32))
-                                         : "memory");
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            // component-owner exchange: the row goes to the GPU that assembles the map of component e
+                            // (row pointer already offset to this rank's pixels; NULL: nobody wants it).  Values of pixels
+                            // that still go to the general solver travel too; that kernel, next in the stream, overwrites
+                            // them with the final ones.
+                            float *dst = p.peers.n_owned > 0 ? p.peers.owner_row[lane]
+                                                             : p.x + (long long)lane * p.ld_x;
+                            if (dst != nullptr) {
+                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst + (px - lane)),
+                                             "r"(smem_u32(st + lane * 32))
+                                             : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        }
+                        // owner mode: the local array carries the pixels the general solver still has to read
+                        if (p.peers.n_owned > 0 && negative) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (e < p.n_comp) p.x[(long long)e * p.ld_x + px] = xv[mt][e];
                         }
                     }
                     if (valid && !bulk && !(p.debug & 1)) {
@@ -809,8 +822,10 @@ extern "C" int mt_fit_contract(const void *spec_dev, int32_t dtype, int64_t n_px
         const char *v = getenv("MT_FIT_BULK_STORE");
         return !(v && atoi(v) == 0);
     }();
-    p.bulk = bulk_pref && p.reg_path && p.peers.n_owned == 0 && p.peers.n_peers == 0 && p.peers.multicast == nullptr &&
+    p.bulk = bulk_pref && p.reg_path && p.peers.n_peers == 0 && p.peers.multicast == nullptr &&
              x_layout == MT_X_ELEMENT_MAJOR && (ld_x % 4) == 0 && ((uintptr_t)x_dev & 15) == 0;
+    for (int e = 0; e < n_comp && e < MT_MAX_OWNED && p.bulk && p.peers.n_owned > 0; ++e)
+        p.bulk = ((uintptr_t)p.peers.owner_row[e] & 15) == 0;  // (NULL rows pass)
     const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * 12 + 4) + 16 + 4 * (size_t)e_pad + 64 +
                          (hinv32_dev ? 4 * (size_t)n_comp * n_comp : 0) + (p.bulk ? 128 + 4 * 4096 : 0);
     p.n_stages = (int)((kSmemLimit - fixed) / p.stage_bytes);
