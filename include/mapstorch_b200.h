@@ -128,6 +128,12 @@ int mt_snip(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, 
             int32_t n_ch, const uint32_t *lohi_dev, int32_t n_pass, int32_t boxcar, float *out_dev,
             int64_t ld_out, int32_t out_mode, void *stream);
 
+/* lohi_dev [n_pass][n_ch] of mt_snip built on the device from six fp32 calibration values with the reference's own
+ * single-precision operation sequence (bkg.py:57-62, 83-91, 104-112): bit-identical to the host tables.  n_pass is the
+ * pass count of bkg.py:104-112, which the host obtains from the largest width alone. */
+int mt_snip_tables_f32(int32_t n_ch, int32_t ch0, float e_offset, float e_slope, float e_quad, float snip_width,
+                       float fwhm_offset, float fwhm_fanoprime, int32_t n_pass, uint32_t *lohi_dev, void *stream);
+
 /* The same kernel driven by a pre-scaled gather table: scaled_dev = (n_pass + 1) rows of ld_scaled words,
  * word = (lo * 16) | (hi * 16) << 16 (shared-memory byte offsets of the 4-pixel records), entries past n_ch and
  * the extra last row are 0 -- the clipping passes then need no index arithmetic and no bounds tests.
@@ -353,6 +359,25 @@ int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec
               const uint32_t *line_window_host, const int32_t *comp_order_host, const float *g0inv_dev,
               float *x_dev, int64_t ld_x,
               float *theta_dev, int64_t ld_theta, float *loss_dev, int32_t *iters_dev, void *stream);
+
+/* Amplitude solve of ONE spectrum at fixed calibration -- the evaluation inside fit_spec(tune_params=True)
+ * (objective of opt.py:329-398; the reference reaches the same amplitudes by Adam on log10 A).  For each of n_prob
+ * problems (the trial points of one Jacobian), over the n_k fitted channels c_k = chan_idx_dev[k] (NULL: c_k = k):
+ *     x = argmin_{x >= 0} sum_k w_k (x . B[:, c_k] - t_k)^2 + 2 shift sum(x),   t = y - bkg (fp32 difference),
+ * with c = l1_lambda * (robust ? sum|t| : sum t^2) / max(n_elements, 1) (opt.py:372-381) and shift = robust ? c : c/2.
+ * basis_dev fp32 [n_prob][n_comp][ld_b] (problem p at p * prob_stride_b; 0 shares one basis), y_dev [>= max c_k + 1],
+ * bkg_dev optional (problem p at p * ld_bkg; ld_bkg = 0 shares one), weights_dev optional fp64 [n_prob][ld_w] indexed by k.
+ * Outputs, all fp64: x_dev [n_prob][n_comp]; res_dev [n_prob][n_k] = model - t; vec_dev [n_prob][n_k + n_comp] =
+ * sqrt(w) * res followed by the penalty entries sqrt((robust ? 2 : 1) * c * x); stats_dev [n_prob][8] = { |vec|^2,
+ * objective (sum res^2 or sum |res|, + c sum x), c, flag (0 ok, 1 singular pivot block: clamped unconstrained solution,
+ * 2 Gram matrix of the live components singular: x = 0), pivot steps, sum res^2, sum |res|, sum x }.
+ * n_comp <= MT_SPEC_MAX_COMP, n_k <= MT_SPEC_MAX_CH.  One launch, one CTA per problem, no host synchronisation. */
+#define MT_SPEC_MAX_COMP 96
+#define MT_SPEC_MAX_CH 8192
+int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_stride_b, int32_t n_comp, const float *y_dev,
+                  const float *bkg_dev, int64_t ld_bkg, const int32_t *chan_idx_dev, int32_t n_k,
+                  const double *weights_dev, int64_t ld_w, double l1_lambda, int32_t robust, int32_t n_elements,
+                  double *x_dev, double *res_dev, double *vec_dev, double *stats_dev, int32_t n_prob, void *stream);
 
 #ifdef __cplusplus
 }

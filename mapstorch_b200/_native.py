@@ -33,6 +33,7 @@ class MtTerm(ctypes.Structure):
 
 
 MT_MAX_THETA, MT_MAX_THETA_REFINE = 8, 4
+MT_SPEC_MAX_COMP, MT_SPEC_MAX_CH = 96, 8192
 MT_LINE_ELEMENT, MT_LINE_ELASTIC, MT_LINE_COMPTON = 0, 1, 2
 
 
@@ -66,7 +67,7 @@ class MtPeerSync(ctypes.Structure):
 THETA_IDS = {"ENERGY_OFFSET": 0, "ENERGY_SLOPE": 1, "FWHM_OFFSET": 2, "FWHM_FANOPRIME": 3, "ENERGY_QUADRATIC": 4,
              "COHERENT_SCT_ENERGY": 5, "COMPTON_ANGLE": 6, "COMPTON_FWHM_CORR": 7}
 
-_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+_vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
 # name -> argument types; every function returns int except mt_last_error
 SIGNATURES = {
@@ -75,6 +76,7 @@ SIGNATURES = {
     "mt_model_terms": [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
     "mt_model_sum": [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp],
     "mt_snip": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
+    "mt_snip_tables_f32": [_i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
     "mt_snip_scaled_pitch": [_i32],
     "mt_snip_scale_tables": [_vp, _i32, _i32, _vp, _i32, _vp],
     "mt_snip_scaled": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp],
@@ -100,6 +102,8 @@ SIGNATURES = {
     "mt_model_jacobian": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
                   _vp, _vp],
+    "mt_spec_solve": [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _vp,
+                      _i32, _vp],
 }
 
 
@@ -141,7 +145,7 @@ def check(status):
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 2, "mt_refine": 1,
                     "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_lad_update": 1, "mt_transpose_cf": 1, "mt_int_spec": 1, "mt_model_jacobian": 1, "mt_snip_residual_f16": 1, "mt_snip_runs": 1, "mt_snip_runs_tables": 2,
-                    "mt_peer_wait": 1}
+                    "mt_peer_wait": 1, "mt_spec_solve": 1, "mt_snip_tables_f32": 1}
 launch_count = 0
 
 
@@ -155,8 +159,11 @@ def stream_ptr(stream=None):
     """cudaStream_t of a torch stream (default: torch's current stream) as a void*."""
     import torch
 
-    s = stream if stream is not None else torch.cuda.current_stream()
-    return ctypes.c_void_p(s.cuda_stream)
+    if stream is None:
+        # the raw handle of the current stream without building a torch.cuda.Stream object (a third of the cost; this
+        # runs three times per trial point of fit_spec(tune_params=True))
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    return ctypes.c_void_p(stream.cuda_stream)
 
 
 def dtype_code(torch_dtype):
@@ -169,10 +176,19 @@ def dtype_code(torch_dtype):
     raise NativeError(MT_ERR_UNSUPPORTED, f"spectral volumes must be float32 or float16 on the device, got {torch_dtype}")
 
 
+_checked_devices = set()
+
+
 def require_device():
-    """Raise unless the current CUDA device is an sm_100 part (no CPU fallback)."""
+    """Raise unless the current CUDA device is an sm_100 part (no CPU fallback).  A device that passed once is not asked
+    again (its compute capability cannot change); the C entry points repeat the check on every call anyway."""
     import torch
 
+    if _checked_devices:
+        dev = torch.cuda.current_device()
+        if dev in _checked_devices:
+            return
     if not torch.cuda.is_available():
         raise NativeError(-4, "no CUDA device is visible; mapstorch_b200 has no CPU path")
     call("mt_device_check")
+    _checked_devices.add(torch.cuda.current_device())

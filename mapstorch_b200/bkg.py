@@ -18,7 +18,18 @@ def snip_tables_device(n_ch, er, e_offset, e_slope, e_quad, snip_width, fwhm_off
     also carries its pre-scaled form (mt_snip_scale_tables) as attribute ``_mt_scaled`` and the tables of the
     contiguous-run kernel as ``_mt_runs``; snip_launch picks them up.  aux=False skips both (three launches and a
     stream synchronisation that only pay off over many spectra): the plain table drives the strided kernel."""
-    tab = tables.snip_tables(n_ch, er[0], e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
+    six = (e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
+    if not aux and n_ch <= 65535 and all(isinstance(v, (torch.Tensor, np.floating)) for v in six):
+        # every operand enters the reference's arithmetic as an fp32 value: the table is built on the device with the same
+        # rounded operations (mt_snip_tables_f32); the host only needs the pass count, i.e. the largest width
+        width = tables.snip_widths(n_ch, er[0], *six)
+        n_pass = tables.snip_pass_count(width.max()) if n_ch else 2
+        vals = [np.float32(v.detach().cpu().to(torch.float32).item()) if isinstance(v, torch.Tensor) else np.float32(v)
+                for v in six]
+        lohi = torch.empty((n_pass, n_ch), dtype=torch.int32, device="cuda")
+        _native.call("mt_snip_tables_f32", int(n_ch), int(er[0]), *vals, n_pass, lohi.data_ptr(), _native.stream_ptr())
+        return lohi, n_pass
+    tab = tables.snip_tables(n_ch, er[0], *six)
     lohi = torch.from_numpy(tab.view(np.int32)).to("cuda")
     if not aux:
         return lohi, tab.shape[0]

@@ -340,6 +340,41 @@ extern "C" int mt_snip_scale_tables(const uint32_t *lohi_dev, int32_t n_pass, in
     return MT_OK;
 }
 
+// The gather table of every clipping pass built on the device from six fp32 calibration values: the operation sequence
+// of bkg.py:83-91 (widths), 104-112 (pass schedule) and 57-62 (clamp, truncate) with explicitly rounded single-precision
+// operations (no contraction into FMAs), i.e. bit-identical to the reference's torch CPU ops and to tables.snip_tables.
+// fit_spec(tune_params=True) rebuilds this table at most of its trial points; on the host it cost 0.15 ms + a copy.
+__global__ void snip_tables_f32_kernel(int n_ch, float ch0, float e_offset, float e_slope, float e_quad, float snip_width,
+                                       float fwhm_offset, float fano, int n_pass, uint32_t *__restrict__ lohi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ch) return;
+    const float idx = (float)i, top = (float)(n_ch - 1);
+    const float g = __fadd_rn(idx, ch0);
+    const float energy = __fadd_rn(__fadd_rn(e_offset, __fmul_rn(e_slope, g)), __fmul_rn(e_quad, __fmul_rn(g, g)));
+    const float t = __fdiv_rn(fwhm_offset, 2.3548f);
+    const float sigma_sq = fmaxf(__fadd_rn(__fmul_rn(t, t), __fmul_rn(__fmul_rn(energy, 2.96f), fano)), 0.f);
+    float w = __fdiv_rn(__fmul_rn(__fmul_rn(snip_width, 2.35f), __fsqrt_rn(sigma_sq)), e_slope);
+    for (int pass = 0; pass < n_pass; ++pass) {
+        if (pass >= 3) w = __fdiv_rn(w, 1.41421356237309504880f);  // passes 0-2 use the full width, then / sqrt(2) each
+        const int lo = __float2int_rz(fminf(fmaxf(__fsub_rn(idx, w), 0.f), top));
+        const int hi = __float2int_rz(fminf(fmaxf(__fadd_rn(idx, w), 0.f), top));
+        lohi[(long long)pass * n_ch + i] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+}
+
+extern "C" int mt_snip_tables_f32(int32_t n_ch, int32_t ch0, float e_offset, float e_slope, float e_quad, float snip_width,
+                                  float fwhm_offset, float fwhm_fanoprime, int32_t n_pass, uint32_t *lohi_dev,
+                                  void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(lohi_dev, "mt_snip_tables_f32: null pointer");
+    MT_REQUIRE(n_ch > 0 && n_ch <= 65535 && n_pass >= 0 && n_pass <= 4096, "mt_snip_tables_f32: bad sizes");
+    if (n_pass == 0) return MT_OK;
+    snip_tables_f32_kernel<<<(n_ch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        n_ch, (float)ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime, n_pass, lohi_dev);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
+
 extern "C" int mt_snip_scaled(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, int32_t ch0,
                               int32_t n_ch, const uint32_t *scaled_dev, int32_t ld_scaled, int32_t n_pass, int32_t boxcar,
                               float *out_dev, int64_t ld_out, int32_t out_mode, void *stream_) {

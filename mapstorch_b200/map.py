@@ -30,12 +30,35 @@ def _to_device(t, device):
     return t if device is None or torch.device(device).type == "cuda" else t.to(device)
 
 
+_EV_CACHE = {}
+
+
+def _energy_axis(params, energy_range):
+    """(energy axis on the host, its device copy), kept for the last few calibrations: the trial points of
+    fit_spec(tune_params=True) move one parameter at a time, most of them not the axis."""
+    key = (int(energy_range[0]), int(energy_range[1]), torch.cuda.current_device()) + tuple(
+        float(tables.scalar32(params[k])) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC"))
+    pair = _EV_CACHE.get(key)
+    if pair is None:
+        if len(_EV_CACHE) >= 16:
+            _EV_CACHE.clear()
+        ev = tables.energy_axis(params, energy_range)
+        pair = _EV_CACHE[key] = (ev, _cuda_f32(ev).reshape(-1))
+    return pair
+
+
 def run_terms(ev, columns, out=None):
     """Evaluate term columns on the GPU: returns a CUDA tensor [n_cols, len(ev)]."""
-    _native.require_device()
-    ev_dev = _cuda_f32(ev).reshape(-1)
     terms, starts = tables.pack_columns(columns)
-    n_cols, n_ch = len(columns), ev_dev.numel()
+    return run_packed(ev, terms, starts, out)
+
+
+def run_packed(ev, terms, starts, out=None):
+    """run_terms on an already packed table (tables.pack_columns / tables.compile_packed)."""
+    _native.require_device()
+    ev_dev = ev if isinstance(ev, torch.Tensor) and ev.is_cuda and ev.dtype == torch.float32 and ev.dim() == 1 \
+        and ev.is_contiguous() else _cuda_f32(ev).reshape(-1)
+    n_cols, n_ch = len(starts) - 1, ev_dev.numel()
     if out is None:
         out = torch.empty((n_cols, n_ch), dtype=torch.float32, device="cuda")
     _native.call("mt_model_terms", ev_dev.data_ptr(), n_ch, terms.ctypes.data_as(ctypes.c_void_p),
@@ -111,10 +134,9 @@ def model_spec(params, energy_range, elements_to_fit=default_fitting_elems, devi
                escape_factor=0.0):
     """Full model spectrum over energy_range (inclusive channel pair), map.py:260-309."""
     _native.require_device()
-    ev = tables.energy_axis(params, energy_range)
+    ev, ev_dev = _energy_axis(params, energy_range)
     names = tables.fitted_components(elements_to_fit, e_consts)
-    cols = tables.compile_terms(params, names, e_consts, elem_info, True, False, log_amps=params)
-    per_col = run_terms(ev, cols)
+    per_col = run_packed(ev_dev, *tables.compile_packed(params, names, e_consts, elem_info, True, False, log_amps=params))
     out = torch.empty(ev.numel(), dtype=torch.float32, device="cuda")
     bins = tables.escape_bins(ev, detector_type) if escape_factor > 0.0 else 0
     _native.call("mt_model_sum", per_col.data_ptr(), per_col.stride(0), per_col.shape[0], ev.numel(), bins,
@@ -130,10 +152,9 @@ def element_basis(params, energy_range, elements_to_fit, e_consts=default_energy
     The model is linear in the amplitudes 10**a (SURVEY.md 0.3), so model_spec == sum_e 10**a_e * B[e];
     with an escape factor each column carries its own shifted copy (the shift-add is linear too)."""
     _native.require_device()
-    ev = tables.energy_axis(params, energy_range)
+    ev, ev_dev = _energy_axis(params, energy_range)
     names = tables.fitted_components(elements_to_fit, e_consts)
-    cols = tables.compile_terms(params, names, e_consts, elem_info, use_step, use_tail, log_amps=None)
-    basis = run_terms(ev, cols)
+    basis = run_packed(ev_dev, *tables.compile_packed(params, names, e_consts, elem_info, use_step, use_tail, log_amps=None))
     if escape_factor > 0.0:
         bins = tables.escape_bins(ev, detector_type)
         if bins > 0:

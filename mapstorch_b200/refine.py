@@ -264,6 +264,20 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     bkg_cache = {}
     LAST_STATS.update(evaluations=0, snip_launches=0, jacobians=0)
 
+    if idx is not None and idx.dtype == torch.bool:
+        idx = idx.nonzero().flatten()
+    idx32 = None if idx is None else idx.to(torch.int32).contiguous()
+    n_k = y.numel() if idx is None else int(idx.numel())
+    no_bkg = torch.zeros_like(y)
+
+    def dense(info):
+        """fp64 basis and target on the fitted channels (the analytic Jacobian and the final polish want them)."""
+        if "bm" not in info:
+            target = (y - info["bkg"]).double()
+            info["bm"] = info["basis"].double() if idx is None else info["basis"].double()[:, idx]
+            info["tm"] = target if idx is None else target[idx]
+        return info["bm"], info["tm"]
+
     def evaluate(theta, w=None):
         LAST_STATS["evaluations"] += 1
         pp = dict(params, **dict(zip(free, (float(t) for t in theta))))
@@ -280,18 +294,27 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                 LAST_STATS["snip_launches"] += 1
                 bkg = bkg_cache[key] = _bkg.snip_bkg(y, er, *(torch.tensor(v) for v in key), device="cuda")
         else:
-            bkg = torch.zeros_like(y)
-        target = (y - bkg).double()
-        bm = basis.double() if idx is None else basis.double()[:, idx]
-        tm = target if idx is None else target[idx]
+            bkg = no_bkg
+        if basis.shape[0] <= _native.MT_SPEC_MAX_COMP and n_k <= _native.MT_SPEC_MAX_CH:
+            # one launch (csrc/mt_spec.cu): Gram matrix, non-negative solve, residual vector, objective; one 64-byte
+            # read-back per trial point
+            x, res, vec, stats = robust.spec_solve(basis, y, bkg if use_snip else None, idx32, w, l1_lambda, robust_loss,
+                                                   len(names))
+            st = stats[0].tolist()
+            if st[3] == 2.0:
+                st[0] = st[1] = float("inf")  # collinear components at this trial point: never accepted as a step
+            return (vec[0] if l1_lambda > 0 else vec[0, :n_k]), dict(
+                x=x[0], names=names, basis=basis, bkg=bkg, params=pp, res=res[0], c=st[2], objective=st[1], value=st[0])
+        info = dict(names=names, basis=basis, bkg=bkg, params=pp)
+        bm, tm = dense(info)
         c = robust.penalty_constant(tm, loss, l1_lambda, len(names))
         x = robust.weighted_nnls(bm, tm, w, c if robust_loss else 0.5 * c)
         res = x @ bm - tm
         vec = res if w is None else torch.sqrt(w) * res
-        if c > 0:
+        if l1_lambda > 0:
             vec = torch.cat([vec, torch.sqrt((2.0 if robust_loss else 1.0) * c * x)])
-        return vec, dict(x=x, names=names, basis=basis, bkg=bkg, params=pp, res=res, bm=bm, tm=tm, c=c,
-                         objective=robust.objective(bm, tm, x, loss, c))
+        info.update(x=x, res=res, c=c, objective=robust.objective(bm, tm, x, loss, c), value=float(vec @ vec))
+        return vec, info
 
     # Parameters that move the model: the tail fractions of default_fitting_params never enter model_spec
     # (use_tail=False, map.py:290,302), their gradient is zero in the reference as well and they keep their values.
@@ -331,8 +354,9 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         x = info["x"]
         _, d = model_jacobian(info["params"], er, info["names"], x.float(), [free[k] for k in active], e_consts, elem_info)
         d = d.double() if idx is None else d.double()[:, idx]
-        bf = info["bm"][x > 0]
-        wv = torch.ones_like(info["tm"]) if w is None else w
+        bm, tm = dense(info)
+        bf = bm[x > 0]
+        wv = torch.ones_like(tm) if w is None else w
         if bf.shape[0]:
             gram = (bf * wv) @ bf.T
             coef = torch.linalg.solve(gram + 1e-12 * torch.diag(torch.diagonal(gram)), (bf * wv) @ d.T)
@@ -353,7 +377,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
 
     def run_lm(theta, w, max_it, trace):
         resid, info = evaluate(theta, w)
-        value = float(resid @ resid)
+        value = info["value"]
         lam = 1e-3
         radius = 1.0
         # Forward differences cost one evaluation per moving parameter.  Between full differencings the Jacobian is
@@ -384,7 +408,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                     step = step * (radius / longest)
                 cand = np.clip(theta + step * scale, lo, hi)
                 r_new, info_new = evaluate(cand, w)
-                value_new = float(r_new @ r_new)
+                value_new = info_new["value"]
                 if value_new < value:
                     rel = (value - value_new) / max(value, 1e-30)
                     if state["fd"] and r_new.shape == resid.shape:
@@ -447,12 +471,16 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                     break
                 eps = max(eps * 0.2, floor)
             # calibration settled: converge the amplitudes of the final model all the way
-            polished = robust.solve_amplitudes(info["bm"], info["tm"], loss, info["c"])
-            value = robust.objective(info["bm"], info["tm"], polished, loss, info["c"])
+            bm, tm = dense(info)
+            polished = robust.solve_amplitudes(bm, tm, loss, info["c"])
+            value = robust.objective(bm, tm, polished, loss, info["c"])
             if value <= info["objective"]:
                 info = dict(info, x=polished, objective=value)
                 trace.append(value)
 
+        if not np.isfinite(info["objective"]):
+            raise RuntimeError("fit_spec: the Gram matrix of the model components is singular (collinear components) at "
+                               f"{ {k: info['params'][k] for k in free} }")
         pp, names, x = info["params"], info["names"], info["x"]
         tensors, _ = create_tensors(names, free, pp, {k: pp[k] for k in pp if k not in free}, tune_params=True, device=device)
         for n, a in zip(names, x.float()):

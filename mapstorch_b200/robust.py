@@ -45,6 +45,44 @@ def weighted_nnls(bm, tm, weights=None, shift=0.0):
     return x
 
 
+def spec_solve(basis, y, bkg=None, chan_idx=None, weights=None, l1_lambda=0.0, robust=False, n_elements=1):
+    """The amplitude solve of one spectrum (or a batch of trial points) in ONE launch of mt_spec_solve
+    (csrc/mt_spec.cu): Gram matrix, non-negative solve, residual vector and objective, no host synchronisation.
+
+    basis fp32 CUDA [E, C] or [N, E, C]; y fp32 CUDA [C]; bkg fp32 CUDA [C] / [N, C] / None; chan_idx int32 CUDA [K] or
+    None (all channels); weights fp64 CUDA [K] / [N, K] or None.  Returns (x [N, E], res [N, K], vec [N, K + E],
+    stats [N, 8]) as fp64 CUDA tensors, see include/mapstorch_b200.h."""
+    b3 = basis if basis.dim() == 3 else basis.unsqueeze(0)
+    if b3.stride(2) != 1 or b3.stride(1) < b3.shape[2]:
+        b3 = b3.contiguous()
+    n_prob, n_comp, n_ch = b3.shape
+    n_k = int(chan_idx.numel()) if chan_idx is not None else n_ch
+    if n_comp > _native.MT_SPEC_MAX_COMP or n_k > _native.MT_SPEC_MAX_CH or n_k < 1:
+        raise _native.NativeError(_native.MT_ERR_UNSUPPORTED, f"mt_spec_solve: {n_comp} components x {n_k} channels")
+    ld_bkg = 0
+    if bkg is not None:
+        bkg = bkg.contiguous()
+        ld_bkg = bkg.stride(0) if bkg.dim() == 2 and bkg.shape[0] > 1 else 0
+    ld_w = 0
+    if weights is not None:
+        weights = weights.contiguous()
+        ld_w = weights.stride(0) if weights.dim() == 2 and weights.shape[0] > 1 else 0
+    out = torch.empty((n_prob, n_comp + n_k + (n_k + n_comp) + 8), dtype=torch.float64, device=b3.device)
+    x, res, vec, stats = torch.split(out, [n_comp, n_k, n_k + n_comp, 8], dim=1)
+    # outputs are rows of one allocation: per-problem pitches differ from the packed layout the entry point expects
+    # only for n_prob > 1, so batches get their own packed tensors
+    if n_prob > 1:
+        x, res, vec, stats = (torch.empty((n_prob, n), dtype=torch.float64, device=b3.device)
+                              for n in (n_comp, n_k, n_k + n_comp, 8))
+    _native.call("mt_spec_solve", b3.data_ptr(), b3.stride(1), b3.stride(0) if n_prob > 1 else 0, n_comp, y.data_ptr(),
+                 bkg.data_ptr() if bkg is not None else None, ld_bkg,
+                 chan_idx.data_ptr() if chan_idx is not None else None, n_k,
+                 weights.data_ptr() if weights is not None else None, ld_w, float(l1_lambda), int(bool(robust)),
+                 int(n_elements), x.data_ptr(), res.data_ptr(), vec.data_ptr(), stats.data_ptr(), n_prob,
+                 _native.stream_ptr())
+    return x, res, vec, stats
+
+
 def penalty_constant(tm, loss, l1_lambda, n_elements):
     """c of the module docstring; tm = y - bkg on the fitted channels."""
     if l1_lambda <= 0:

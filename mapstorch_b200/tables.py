@@ -192,6 +192,125 @@ def compile_terms(params, components, e_consts, elem_info, use_step=True, use_ta
     return columns
 
 
+# ---- vectorised line-table compiler --------------------------------------------------------------------------------
+# fit_spec(tune_params=True) rebuilds the term table at every trial point of its Levenberg-Marquardt loop; the scalar
+# code above costs ~0.4 ms for ten elements (NumPy scalar arithmetic per line).  compile_packed does the same fp32
+# operations on arrays over all lines at once (IEEE single-precision adds, multiplies, divisions and square roots round
+# identically for scalars and arrays) and writes the packed table directly; everything that does not depend on the
+# parameters (line energies, ratios, absorption edges, column membership) is gathered once per component list.
+_LINE_SETS = {}
+
+
+class _LineSet:
+    """Static per-line arrays of the element columns of one component list."""
+
+    def __init__(self, components, e_consts, elem_info):
+        e, e296, mu, ratio, kl, col, edge = [], [], [], [], [], [], []
+        self.columns = []  # per component: ("lines", first, last) or the scatter name
+        for name in components:
+            if name in SCATTER_NAMES:
+                self.columns.append(name)
+                continue
+            first = len(e)
+            for s in e_consts[name]:
+                if s.ratio == 0 or s.energy <= 0:
+                    continue
+                edges = s.binding_edge(elem_info)
+                if edges is None:
+                    continue  # never excited (check_binding_energy is False for every incident energy)
+                e.append(f32(s.energy))
+                e296.append(f32(s.energy * 2.96))
+                mu.append(f32(s.mu_fraction))
+                ratio.append(f32(s.ratio))
+                kl.append(s.ptype[:2] in ("Ka", "Kb") or s.ptype.startswith("L"))
+                col.append(len(self.columns))
+                # the gate compares each edge with the fp32 incident energy: Python floats enter that comparison as fp32
+                pair = [f32(v) for v in edges] + [f32(-np.inf)] * (2 - len(edges))
+                edge.append(pair[:2])
+                if len(edges) > 2:
+                    raise ValueError("more than two absorption edges per line")
+            self.columns.append(("lines", first, len(e)))
+        self.e = np.asarray(e, dtype=np.float32)
+        self.e296 = np.asarray(e296, dtype=np.float32)
+        self.mu = np.asarray(mu, dtype=np.float32)
+        self.ratio = np.asarray(ratio, dtype=np.float32)
+        self.kl = np.asarray(kl, dtype=bool)
+        self.col = np.asarray(col, dtype=np.int64)
+        self.edge = np.asarray(edge, dtype=np.float32).reshape(-1, 2)
+        self.consts = (e_consts, elem_info)  # keeps the keyed objects alive (the cache key holds their ids)
+
+
+def _line_set(components, e_consts, elem_info):
+    key = (tuple(components), id(e_consts), id(elem_info))
+    ls = _LINE_SETS.get(key)
+    if ls is None:
+        if len(_LINE_SETS) > 32:
+            _LINE_SETS.clear()
+        ls = _LINE_SETS[key] = _LineSet(components, e_consts, elem_info)
+    return ls
+
+
+def compile_packed(params, components, e_consts, elem_info, use_step=True, use_tail=False, log_amps=None):
+    """pack_columns(compile_terms(...)) in one vectorised step: (structured term array, int32 col_start[n_cols+1]).
+    Bit-identical to the scalar route (tests/test_tables.py); tail terms take the scalar route."""
+    if use_tail:
+        return pack_columns(compile_terms(params, components, e_consts, elem_info, use_step, use_tail, log_amps))
+    ls = _line_set(components, e_consts, elem_info)
+    gain = scalar32(params["ENERGY_SLOPE"])
+    e0 = scalar32(params["COHERENT_SCT_ENERGY"])
+    n_cols = len(ls.columns)
+    amps = np.ones(n_cols, dtype=np.float32)
+    if log_amps is not None:
+        for k, name in enumerate(components):
+            amps[k] = pow10(log_amps[name])
+    n = ls.e.shape[0]
+    with np.errstate(all="ignore"):
+        a = scalar32(params["FWHM_OFFSET"]) / f32(2.3548)
+        sigma = np.sqrt(a * a + ls.e296 * scalar32(params["FWHM_FANOPRIME"]))
+        f_step = np.abs(ls.mu * (scalar32(params["F_STEP_OFFSET"]) + scalar32(params["F_STEP_LINEAR"]) * ls.e))
+        faktor = ls.ratio * amps[ls.col]
+        faktor = np.where(ls.kl, faktor / (f32(1.0) + f_step), faktor)
+        on = (ls.edge[:, 0] < e0) & (ls.edge[:, 1] < e0)
+        rows = np.zeros((n, 2), dtype=TERM_DTYPE)  # [line, gauss | step]
+        rows["sign"] = 1.0
+        rows["e"] = ls.e[:, None]
+        g, st = rows[:, 0], rows[:, 1]
+        g["kind"] = MT_TERM_GAUSS
+        g["p0"] = sigma
+        g["p1"] = gain / (sigma * _SQRT2PI)
+        g["amp"] = faktor
+        st["kind"] = MT_TERM_STEP
+        st["p0"] = _SQRT2 * sigma
+        st["p1"] = gain / f32(2.0) / ls.e
+        st["amp"] = faktor * f_step
+        keep = np.stack([on, on & (f_step > 0) & bool(use_step)], axis=1)
+    per_col = np.zeros(n_cols, dtype=np.int64)
+    np.add.at(per_col, ls.col, keep.sum(axis=1))
+    line_terms = rows[keep]  # row-major: line order, Gaussian before its step
+    scatter = {}
+    for k, c in enumerate(ls.columns):
+        if c == "COHERENT_SCT_AMPLITUDE":
+            scatter[k] = elastic_terms(params, gain, amps[k])
+        elif c == "COMPTON_AMPLITUDE":
+            scatter[k] = compton_terms(params, gain, amps[k], use_step, use_tail)
+        if k in scatter:
+            per_col[k] = len(scatter[k])
+    starts = np.zeros(n_cols + 1, dtype=np.int32)
+    np.cumsum(per_col, out=starts[1:])
+    total = int(starts[-1])
+    terms = np.zeros(max(total, 1), dtype=TERM_DTYPE)
+    src = 0
+    for k, c in enumerate(ls.columns):  # element columns are contiguous runs of line_terms in column order
+        lo, hi = int(starts[k]), int(starts[k + 1])
+        if k in scatter:
+            for i, t in enumerate(scatter[k]):
+                terms[lo + i] = t
+        else:
+            terms[lo:hi] = line_terms[src: src + hi - lo]
+            src += hi - lo
+    return terms, starts
+
+
 def snip_tables(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
     """Gather indices of every SNIP clipping pass: uint32 [n_pass, n_ch], lo | hi << 16.
 
@@ -203,6 +322,23 @@ def snip_tables(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, f
     fifth of its time -- it runs once per trial point of fit_spec(tune_params=True)."""
     if n_ch > 65535:
         raise ValueError("snip tables hold 16-bit channel indices")
+
+    width = snip_widths(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime)
+    idx = np.arange(n_ch, dtype=np.float32)
+    widths = [width, width]
+    while float(width.max()) >= 0.5:
+        widths.append(width)
+        width = width / f32(M_SQRT2)
+        if len(widths) > 4096:
+            raise ValueError("SNIP width does not shrink (check ENERGY_SLOPE / SNIP_WIDTH)")
+    w = np.stack(widths)
+    lo = np.clip(idx[None, :] - w, f32(0), f32(n_ch - 1)).astype(np.int64)
+    hi = np.clip(idx[None, :] + w, f32(0), f32(n_ch - 1)).astype(np.int64)
+    return np.ascontiguousarray((lo | (hi << 16)).astype(np.uint32))
+
+
+def snip_widths(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):
+    """First-pass clipping half-width per channel (bkg.py:83-91), float32 [n_ch]; see snip_tables."""
 
     def operand(v):
         return f32(v.detach().cpu().to(torch.float32).item()) if isinstance(v, torch.Tensor) else v
@@ -218,17 +354,19 @@ def snip_tables(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, f
     else:
         first = (fwhm_offset / 2.3548) ** 2  # Python floats: double arithmetic, rounded when it meets the tensor
     sigma_sq = np.maximum((first + energy * 2.96 * fwhm_fanoprime).astype(np.float32), f32(0.0))
-    width = ((snip_width * 2.35 * np.sqrt(sigma_sq)).astype(np.float32) / f32(e_slope)).astype(np.float32)
-    widths = [width, width]
-    while float(width.max()) >= 0.5:
-        widths.append(width)
-        width = width / f32(M_SQRT2)
-        if len(widths) > 4096:
+    return ((snip_width * 2.35 * np.sqrt(sigma_sq)).astype(np.float32) / f32(e_slope)).astype(np.float32)
+
+
+def snip_pass_count(width_max):
+    """Number of clipping passes (bkg.py:104-112) from the largest first-pass width alone: every pass divides all widths
+    by the same constant and rounding is monotone, so the largest width stays the largest."""
+    w, n = f32(width_max), 2
+    while float(w) >= 0.5:
+        n += 1
+        w = w / f32(M_SQRT2)
+        if n > 4096:
             raise ValueError("SNIP width does not shrink (check ENERGY_SLOPE / SNIP_WIDTH)")
-    w = np.stack(widths)
-    lo = np.clip(idx[None, :] - w, f32(0), f32(n_ch - 1)).astype(np.int64)
-    hi = np.clip(idx[None, :] + w, f32(0), f32(n_ch - 1)).astype(np.int64)
-    return np.ascontiguousarray((lo | (hi << 16)).astype(np.uint32))
+    return n
 
 
 def snip_tables_torch(n_ch, ch0, e_offset, e_slope, e_quad, snip_width, fwhm_offset, fwhm_fanoprime):

@@ -179,3 +179,28 @@ def test_runs_kernel_overflow_flag_and_unaligned_problems_fall_back(snip_golden)
     _native.call("mt_snip", wide.data_ptr(), _native.MT_DTYPE_F32, 4, wide.stride(0), 3, 2048, lohi2.data_ptr(), n_pass2, 5,
                  ref.data_ptr(), ref.stride(0), 0, _native.stream_ptr())
     assert torch.equal(out2, ref)
+
+
+def test_device_built_gather_tables_are_bit_identical_to_the_host_tables():
+    """mt_snip_tables_f32 (the table builder fit_spec(tune_params=True) uses at every trial point) against
+    tables.snip_tables, itself pinned to the reference's torch ops: 150 random calibrations, crops and sizes."""
+    import torch
+
+    from mapstorch_b200 import bkg, tables
+
+    rng = np.random.default_rng(7)
+    for trial in range(150):
+        n_ch = int(rng.integers(8, 4096)) if trial % 10 else int(rng.choice([1, 2, 5, 16384]))
+        ch0 = int(rng.integers(0, 300))
+        vals = (rng.normal(0, 0.05), rng.uniform(0.003, 0.03), rng.normal(0, 1e-7) if trial % 3 else 0.0,
+                rng.uniform(0.05, 4.0), rng.uniform(0.02, 0.4), rng.uniform(1e-6, 2e-3))
+        six = [torch.tensor(float(v)) for v in vals]
+        want = tables.snip_tables(n_ch, ch0, *six)
+        lohi, n_pass = bkg.snip_tables_device(n_ch, (ch0, ch0 + n_ch - 1), *six, aux=False)
+        assert n_pass == want.shape[0]
+        got = lohi.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), f"trial {trial}: {np.argwhere(got != want)[:4]}"
+    # Python-float operands keep the host route (their arithmetic is partly double precision in the reference)
+    floats = [float(v) for v in vals]
+    lohi, n_pass = bkg.snip_tables_device(n_ch, (ch0, ch0 + n_ch - 1), *floats, aux=False)
+    assert np.array_equal(lohi.cpu().numpy().view(np.uint32), tables.snip_tables(n_ch, ch0, *floats))

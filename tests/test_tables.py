@@ -181,3 +181,35 @@ def test_snip_tables_numpy_builder_equals_the_torch_op_sequence():
         ref = tables.snip_tables_torch(n_ch, ch0, *args)
         got = tables.snip_tables(n_ch, ch0, *args)
         assert got.dtype == ref.dtype and got.shape == ref.shape and np.array_equal(got, ref), (trial, n_ch, ch0, vals)
+
+
+def test_vectorised_term_compiler_is_bit_identical_to_the_scalar_route():
+    """tables.compile_packed (array arithmetic over all lines, used by model_spec / element_basis) against
+    pack_columns(compile_terms(...)) (the reference's scalar op sequence, pinned above against the goldens): 200 random
+    calibrations, random component subsets, incident energies exactly on absorption edges, with and without steps."""
+    from mapstorch_b200 import default as d, tables
+
+    rng = np.random.default_rng(0)
+    ec, ei = d.default_energy_consts, d.default_elem_info
+    for trial in range(200):
+        pp = dict(d.default_param_vals)
+        for k in pp:
+            if isinstance(pp[k], float) and rng.random() < 0.7:
+                pp[k] = float(np.float32(pp[k] * (1 + 0.2 * rng.standard_normal())))
+        pp["COHERENT_SCT_ENERGY"] = float(rng.uniform(1.5, 30.0))
+        if trial % 5 == 0:
+            info = ei[int(rng.integers(10, 60))]
+            pp["COHERENT_SCT_ENERGY"] = float(np.float32(list(info.bindingE.values())[0]))
+        elems = d.default_fitting_elems if trial % 2 == 0 else list(
+            rng.choice(d.default_fitting_elems, size=int(rng.integers(1, 40)), replace=False))
+        comps = tables.fitted_components(elems, ec)
+        log_amps = {c: float(rng.uniform(-2, 3)) for c in comps} if trial % 3 == 0 else None
+        for use_step in (True, False):
+            want_t, want_s = tables.pack_columns(tables.compile_terms(pp, comps, ec, ei, use_step, False, log_amps))
+            got_t, got_s = tables.compile_packed(pp, comps, ec, ei, use_step, False, log_amps)
+            assert np.array_equal(want_s, got_s)
+            assert want_t.tobytes() == got_t.tobytes()
+    # tail terms take the scalar route
+    want_t, want_s = tables.pack_columns(tables.compile_terms(pp, comps, ec, ei, True, True))
+    got_t, got_s = tables.compile_packed(pp, comps, ec, ei, True, True)
+    assert np.array_equal(want_s, got_s) and want_t.tobytes() == got_t.tobytes()
