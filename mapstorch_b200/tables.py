@@ -284,8 +284,8 @@ def compile_packed(params, components, e_consts, elem_info, use_step=True, use_t
         st["p1"] = gain / f32(2.0) / ls.e
         st["amp"] = faktor * f_step
         keep = np.stack([on, on & (f_step > 0) & bool(use_step)], axis=1)
-    per_col = np.zeros(n_cols, dtype=np.int64)
-    np.add.at(per_col, ls.col, keep.sum(axis=1))
+    per_col = np.bincount(ls.col, weights=keep.sum(axis=1), minlength=n_cols).astype(np.int64) if n else \
+        np.zeros(n_cols, dtype=np.int64)
     line_terms = rows[keep]  # row-major: line order, Gaussian before its step
     scatter = {}
     for k, c in enumerate(ls.columns):
@@ -299,6 +299,14 @@ def compile_packed(params, components, e_consts, elem_info, use_step=True, use_t
     np.cumsum(per_col, out=starts[1:])
     total = int(starts[-1])
     terms = np.zeros(max(total, 1), dtype=TERM_DTYPE)
+    first_scatter = min(scatter) if scatter else n_cols
+    if all(k >= first_scatter for k in scatter) and len(scatter) == n_cols - first_scatter:
+        # model_spec's column order: element columns, then the scatter peaks -- the line terms are one contiguous run
+        terms[: line_terms.shape[0]] = line_terms
+        for k, col in scatter.items():
+            for i, t in enumerate(col):
+                terms[int(starts[k]) + i] = t
+        return terms, starts
     src = 0
     for k, c in enumerate(ls.columns):  # element columns are contiguous runs of line_terms in column order
         lo, hi = int(starts[k]), int(starts[k + 1])

@@ -209,6 +209,12 @@ def test_vectorised_term_compiler_is_bit_identical_to_the_scalar_route():
             got_t, got_s = tables.compile_packed(pp, comps, ec, ei, use_step, False, log_amps)
             assert np.array_equal(want_s, got_s)
             assert want_t.tobytes() == got_t.tobytes()
+    # column orders other than model_spec's (scatter peaks first / in between / alone)
+    for comps in (["COMPTON_AMPLITUDE", "Fe", "COHERENT_SCT_AMPLITUDE", "Cu"], ["Fe", "Cu"], ["COHERENT_SCT_AMPLITUDE"],
+                  ["COMPTON_AMPLITUDE", "Zn"]):
+        want_t, want_s = tables.pack_columns(tables.compile_terms(pp, comps, ec, ei, True, False))
+        got_t, got_s = tables.compile_packed(pp, comps, ec, ei, True, False)
+        assert np.array_equal(want_s, got_s) and want_t.tobytes() == got_t.tobytes()
     # tail terms take the scalar route
     want_t, want_s = tables.pack_columns(tables.compile_terms(pp, comps, ec, ei, True, True))
     got_t, got_s = tables.compile_packed(pp, comps, ec, ei, True, True)
