@@ -543,12 +543,22 @@ def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e
     launches0 = _native.launch_count
     ms_total = timed(step, steps, after=finish)
     launches_graph = _native.launch_count - launches0
-    # same steps launched eagerly with CUDA events around the kernels (roofline numerators)
-    plan.timers = []
-    refine_state.pop("events", None)
+    # same steps launched eagerly (launch count, eager step time) ...
     launches0 = _native.launch_count
     ms_eager = timed(lambda: step(gather=False, eager=True), steps)
     launches = _native.launch_count - launches0
+    # ... and once more with CUDA events around the kernels (roofline numerators).  Every probed step is queued behind a
+    # 0.25 ms device-side spin, so its launches are in the stream before the GPU reaches the first event: without it the
+    # interval of a 0.1 ms kernel (c2) contains the host's launch latency and reads 20 % long.
+    plan.timers = []
+    refine_state.pop("events", None)
+    spin_cycles = int(0.25e-3 * 1.9e9)
+
+    def probe():
+        torch.cuda._sleep(spin_cycles)
+        step(gather=False, eager=True)
+
+    timed(probe, steps)
     clocks = sampler.stop()
     timers, plan.timers = plan.timers, None
     ms_fit_only = timed(lambda: step(gather=False), steps) if world > 1 else ms_total

@@ -97,6 +97,10 @@ const char *mt_last_error(void);
 /* MT_OK iff the current CUDA device is a compute-capability-10.x part. */
 int mt_device_check(void);
 
+/* Energy axis of channels ch0 .. ch0 + n_ch - 1 on the device, ev = offset + slope * ch + quad * ch^2 with the rounding
+ * of the reference's separate fp32 ops (map.py:271-281); channel numbers below 2^24 (exact in fp32). */
+int mt_energy_axis(int32_t ch0, int32_t n_ch, float e_offset, float e_slope, float e_quad, float *ev_dev, void *stream);
+
 /* K1 -- replaces the per-line torch op chains of model_elem_spec / elastic_peak /
  * compton_peak (map.py:72-124,152-257).  out_dev[col*ld_out + c] = sum of the column's
  * terms at channel c, fp32, accumulated in term order.  col_start_host has n_cols+1

@@ -73,6 +73,7 @@ _vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c
 SIGNATURES = {
     "mt_abi_version": [],
     "mt_device_check": [],
+    "mt_energy_axis": [_i32, _i32, _f32, _f32, _f32, _vp, _vp],
     "mt_model_terms": [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
     "mt_model_sum": [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp],
     "mt_snip": [_vp, _i32, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
@@ -145,7 +146,7 @@ def check(status):
 KERNELS_PER_CALL = {"mt_model_terms": 1, "mt_model_sum": 1, "mt_snip": 1, "mt_fit_contract": 1,
                     "mt_fit_contract_simt": 1, "mt_nnls_fixup": 1, "mt_nnls_list": 2, "mt_refine": 1,
                     "mt_penalty_shift": 1, "mt_snip_scaled": 1, "mt_snip_scale_tables": 1, "mt_split_hilo": 1, "mt_operand_inexact": 1, "mt_peer_signal": 1, "mt_lad_update": 1, "mt_transpose_cf": 1, "mt_int_spec": 1, "mt_model_jacobian": 1, "mt_snip_residual_f16": 1, "mt_snip_runs": 1, "mt_snip_runs_tables": 2,
-                    "mt_peer_wait": 1, "mt_spec_solve": 1, "mt_snip_tables_f32": 1}
+                    "mt_peer_wait": 1, "mt_spec_solve": 1, "mt_snip_tables_f32": 1, "mt_energy_axis": 1}
 launch_count = 0
 
 

@@ -73,7 +73,26 @@ model_sum_kernel(const float *__restrict__ cols, long long ld, int n_cols, int n
     out[c] = s;
 }
 
+// ev[c] = offset + slope * ch + quad * ch^2 for ch = ch0 + c, with the reference's rounding (map.py:271-281 evaluates
+// it with separate fp32 torch ops: no fused multiply-add anywhere)
+__global__ void energy_axis_kernel(int ch0, int n_ch, float off, float slope, float quad, float *__restrict__ ev) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) return;
+    const float ch = (float)(ch0 + c);
+    ev[c] = __fadd_rn(__fadd_rn(off, __fmul_rn(slope, ch)), __fmul_rn(quad, __fmul_rn(ch, ch)));
+}
+
 }  // namespace
+
+extern "C" int mt_energy_axis(int32_t ch0, int32_t n_ch, float e_offset, float e_slope, float e_quad, float *ev_dev,
+                              void *stream_) {
+    if (int rc = mt::require_sm100()) return rc;
+    MT_REQUIRE(ev_dev && n_ch > 0 && ch0 >= 0 && (long long)ch0 + n_ch <= (1 << 24), "mt_energy_axis: bad arguments");
+    energy_axis_kernel<<<(n_ch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(ch0, n_ch, e_offset, e_slope,
+                                                                                            e_quad, ev_dev);
+    MT_CUDA_TRY(cudaGetLastError());
+    return MT_OK;
+}
 
 extern "C" int mt_model_terms(const float *ev_dev, int32_t n_ch, const MtTerm *terms_host,
                               const int32_t *col_start_host, int32_t n_cols, float *out_dev,

@@ -34,17 +34,19 @@ _EV_CACHE = {}
 
 
 def _energy_axis(params, energy_range):
-    """(energy axis on the host, its device copy), kept for the last few calibrations: the trial points of
-    fit_spec(tune_params=True) move one parameter at a time, most of them not the axis."""
-    key = (int(energy_range[0]), int(energy_range[1]), torch.cuda.current_device()) + tuple(
-        float(tables.scalar32(params[k])) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC"))
-    pair = _EV_CACHE.get(key)
-    if pair is None:
+    """Energy axis on the device (mt_energy_axis: the reference's fp32 operation sequence, bit-identical to
+    tables.energy_axis), kept for the last few calibrations: the trial points of fit_spec(tune_params=True) move one
+    parameter at a time, most of them not the axis.  No host copy, no host-to-device transfer, no synchronisation."""
+    cal = tuple(tables.scalar32(params[k]) for k in ("ENERGY_OFFSET", "ENERGY_SLOPE", "ENERGY_QUADRATIC"))
+    key = (int(energy_range[0]), int(energy_range[1]), torch.cuda.current_device()) + tuple(float(v) for v in cal)
+    ev_dev = _EV_CACHE.get(key)
+    if ev_dev is None:
         if len(_EV_CACHE) >= 16:
             _EV_CACHE.clear()
-        ev = tables.energy_axis(params, energy_range)
-        pair = _EV_CACHE[key] = (ev, _cuda_f32(ev).reshape(-1))
-    return pair
+        n_ch = key[1] - key[0] + 1
+        ev_dev = _EV_CACHE[key] = torch.empty(n_ch, dtype=torch.float32, device="cuda")
+        _native.call("mt_energy_axis", key[0], n_ch, *cal, ev_dev.data_ptr(), _native.stream_ptr())
+    return ev_dev
 
 
 def run_terms(ev, columns, out=None):
@@ -134,12 +136,12 @@ def model_spec(params, energy_range, elements_to_fit=default_fitting_elems, devi
                escape_factor=0.0):
     """Full model spectrum over energy_range (inclusive channel pair), map.py:260-309."""
     _native.require_device()
-    ev, ev_dev = _energy_axis(params, energy_range)
+    ev_dev = _energy_axis(params, energy_range)
     names = tables.fitted_components(elements_to_fit, e_consts)
     per_col = run_packed(ev_dev, *tables.compile_packed(params, names, e_consts, elem_info, True, False, log_amps=params))
-    out = torch.empty(ev.numel(), dtype=torch.float32, device="cuda")
-    bins = tables.escape_bins(ev, detector_type) if escape_factor > 0.0 else 0
-    _native.call("mt_model_sum", per_col.data_ptr(), per_col.stride(0), per_col.shape[0], ev.numel(), bins,
+    out = torch.empty(ev_dev.numel(), dtype=torch.float32, device="cuda")
+    bins = tables.escape_bins(tables.energy_axis(params, energy_range), detector_type) if escape_factor > 0.0 else 0
+    _native.call("mt_model_sum", per_col.data_ptr(), per_col.stride(0), per_col.shape[0], ev_dev.numel(), bins,
                  float(escape_factor), out.data_ptr(), _native.stream_ptr())
     return _to_device(out, device)
 
@@ -152,11 +154,11 @@ def element_basis(params, energy_range, elements_to_fit, e_consts=default_energy
     The model is linear in the amplitudes 10**a (SURVEY.md 0.3), so model_spec == sum_e 10**a_e * B[e];
     with an escape factor each column carries its own shifted copy (the shift-add is linear too)."""
     _native.require_device()
-    ev, ev_dev = _energy_axis(params, energy_range)
+    ev_dev = _energy_axis(params, energy_range)
     names = tables.fitted_components(elements_to_fit, e_consts)
     basis = run_packed(ev_dev, *tables.compile_packed(params, names, e_consts, elem_info, use_step, use_tail, log_amps=None))
     if escape_factor > 0.0:
-        bins = tables.escape_bins(ev, detector_type)
+        bins = tables.escape_bins(tables.energy_axis(params, energy_range), detector_type)
         if bins > 0:
             shifted = torch.zeros_like(basis)
             shifted[:, : basis.shape[1] - bins] = basis[:, bins:] * float(escape_factor)

@@ -278,7 +278,9 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
             info["tm"] = target if idx is None else target[idx]
         return info["bm"], info["tm"]
 
-    def evaluate(theta, w=None):
+    def evaluate(theta, w=None, defer=None):
+        """Residual vector and solution at `theta`.  defer: a list -- the evaluation's device-side statistics are appended to it
+        instead of being read back (no synchronisation; the trial points of a forward-difference Jacobian)."""
         LAST_STATS["evaluations"] += 1
         pp = dict(params, **dict(zip(free, (float(t) for t in theta))))
         basis, names = _map.element_basis(pp, er, elements, e_consts, elem_info, detector_type, escape_factor)
@@ -300,6 +302,9 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
             # read-back per trial point
             x, res, vec, stats = robust.spec_solve(basis, y, bkg if use_snip else None, idx32, w, l1_lambda, robust_loss,
                                                    len(names))
+            if defer is not None:
+                defer.append(stats)
+                return (vec[0] if l1_lambda > 0 else vec[0, :n_k]), None
             st = stats[0].tolist()
             if st[3] == 2.0:
                 st[0] = st[1] = float("inf")  # collinear components at this trial point: never accepted as a step
@@ -337,6 +342,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         # (the tail fractions, see `active`) have an identically zero column: no evaluation is spent on them.
         cols = []
         zero = None
+        pending = []  # device-side statistics of the trial points: nothing is read back until all of them are queued
         for k in range(len(free)):
             if k not in moving:
                 zero = torch.zeros_like(resid) if zero is None else zero
@@ -344,9 +350,14 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
                 continue
             t2 = theta.copy()
             t2[k] += 0.05 * scale[k]
-            r2, _ = evaluate(t2, w)
+            r2, _ = evaluate(t2, w, defer=pending)
             cols.append((r2 - resid) / 0.05)  # derivative w.r.t. the scaled variable theta_k / scale_k
-        return torch.stack(cols, dim=1)
+        jac = torch.stack(cols, dim=1)
+        if pending and bool((torch.cat(pending)[:, 3] == 2.0).any()):
+            # a trial point with collinear components has no usable residual: its column would be garbage
+            raise RuntimeError("fit_spec: the Gram matrix of the model components is singular next to "
+                               f"{dict(zip(free, theta))}")
+        return jac
 
     def jacobian_analytic(theta, w, resid, info):
         # variable projection (Kaufman): d r / d theta_k = P (d model / d theta_k at fixed amplitudes), P the projector

@@ -134,3 +134,23 @@ def test_element_spectra_with_override_file_constants(tmp_path, override_golden,
         kb = int(np.argmin(np.abs(g["spectra_ev"] - 7.058)))
         assert got is not None and abs(mmap.model_elem_spec(pp, "Fe", ev, True, True, e_consts=consts).numpy()[kb]
                                        / base[kb] - 1.2) < 0.02
+
+
+def test_device_energy_axis_is_bit_identical_to_the_host_axis():
+    """mt_energy_axis (what model_spec / element_basis evaluate the lines on) against tables.energy_axis, the reference's
+    torch CPU op sequence (map.py:271-281)."""
+    import torch
+
+    from mapstorch_b200 import map as mmap, tables
+
+    rng = np.random.default_rng(11)
+    for trial in range(100):
+        lo = int(rng.integers(0, 500))
+        hi = lo + int(rng.integers(1, 4096))
+        p = {"ENERGY_OFFSET": float(rng.normal(0, 0.1)), "ENERGY_SLOPE": float(rng.uniform(0.002, 0.04)),
+             "ENERGY_QUADRATIC": float(rng.normal(0, 1e-6)) if trial % 4 else 0.0}
+        if trial % 7 == 0:
+            p = {k: torch.tensor(v) for k, v in p.items()}
+        want = tables.energy_axis(p, (lo, hi))
+        got = mmap._energy_axis(p, (lo, hi)).cpu()
+        assert torch.equal(want, got), trial
