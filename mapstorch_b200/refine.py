@@ -221,6 +221,7 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
 
 
 # ---- fit_spec(tune_params=True): global calibration fit of one spectrum -------------------------
+LM_REFRESH = 5  # accepted steps between full forward differencings (Broyden updates in between)
 LAST_STATS = {"evaluations": 0, "snip_launches": 0, "jacobians": 0}  # work done by the last fit_spec_global call
 
 
@@ -394,7 +395,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         # Forward differences cost one evaluation per moving parameter.  Between full differencings the Jacobian is
         # carried along by Broyden's rank-one secant update (free: it uses the accepted trial point), refreshed every
         # `refresh` accepted steps and whenever a step computed from a carried Jacobian fails.
-        jac, age, refresh = None, 0, 5
+        jac, age, refresh = None, 0, LM_REFRESH
         it = 0
         while it < (max_it if free else 0):
             fresh = jac is None or not state["fd"] or age >= refresh
