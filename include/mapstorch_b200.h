@@ -356,9 +356,11 @@ int mt_model_jacobian(const MtRefineConfig *cfg_host, const MtRefineLine *lines_
  * component-major pass, so the host orders them to balance the summed window lengths; g0inv_dev = inverse
  * Gram matrix of the unit-amplitude basis at the global parameters, fp32 [n_comp][n_comp].
  * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
- * theta_dev [n_theta][ld_theta], loss_dev [n_px], iters_dev [n_px] are optional outputs. */
+ * theta_dev [n_theta][ld_theta], loss_dev [n_px], iters_dev [n_px] are optional outputs.
+ * chan_weight_dev (optional, fp32 [n_ch], 0 or 1): the channels that enter the objective -- `indices` of fit_spec
+ * (opt.py:344-347); g0inv_dev must then be the inverse Gram matrix of the masked basis. */
 int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
-              int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+              int64_t ld_bkg, const float *chan_weight_dev, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
               const uint32_t *chan_lines_host, const int32_t *comp_start_host, const int32_t *comp_lines_host,
               const uint32_t *line_window_host, const int32_t *comp_order_host, const float *g0inv_dev,
               float *x_dev, int64_t ld_x,

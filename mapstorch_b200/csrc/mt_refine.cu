@@ -65,6 +65,7 @@ struct RefParams {
     const float *g0inv;             // [n_comp][n_comp]
     const float *bkg;
     long long ld_bkg;
+    const float *chan_w;            // optional [n_ch]: weight (0 / 1) of each channel in the objective (fit_spec's `indices`)
     const void *spec;
     long long ld_spec;
     float *x;
@@ -312,6 +313,10 @@ refine_kernel(const RefParams p) {
     }
     __syncthreads();
 
+    // largest active set the scratch (residual + derivative rows) can hold: cap^2 + cap (NT + 1) floats
+    int cap = E;
+    while (cap > 0 && cap * cap + cap * (NT + 1) > (1 + NT) * ld) --cap;
+
     int iter = 0;
     for (;; ++iter) {
         // ---- current calibration ------------------------------------------------------------
@@ -357,6 +362,16 @@ refine_kernel(const RefParams p) {
             f32x2 m, d[NT > 0 ? NT : 1];
             eval_pair<NT, GENERAL>(id_k, cal, cg, l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
             f32x2 res = add2(m, pack2(-y0, -y1));
+            if (GENERAL && p.chan_w != nullptr) {
+                // (only in the GENERAL instantiations, which the host selects for masked fits: the lean kernel of the
+                // Gaussian-only benchmark path keeps its register budget)
+                // channels outside `indices` leave the objective: their residual and derivative rows are zero, and with
+                // them every sum the step is built from (loss, D^T r, D^T D here; B^T r, D^T B in the component pass)
+                const f32x2 w2 = pack2(__ldg(p.chan_w + c0), has1 ? __ldg(p.chan_w + c0 + 1) : 0.f);
+                res = mul2(res, w2);
+#pragma unroll
+                for (int k = 0; k < NT; ++k) d[k] = mul2(d[k], w2);
+            }
             if (!has1) {
                 // phantom channel of an odd window: contributes nothing anywhere
                 float lo, hi;
@@ -518,6 +533,72 @@ refine_kernel(const RefParams p) {
             }
         }
         __syncthreads();
+        // ---- active set: components at zero whose gradient keeps them there -----------------------------------------
+        // w_s and t1 were formed with the inverse of the FULL Gram matrix, i.e. they describe a step in which a clamped
+        // amplitude is free to go negative; projecting that step afterwards biases every other component and the
+        // iteration stalls where the least-squares start left it (pixels without one of the fitted elements).  The
+        // Newton step has to be taken on the free set F alone, and the inverse of G_FF follows from H = G^-1 by
+        // eliminating the active rows:  (G_FF)^-1 = H_FF - H_FA (H_AA)^-1 H_AF,  i.e.  V <- V - H[:, A] (H_AA)^-1 V[A]
+        // for the NT + 1 vectors V = (t1, w_s).  A = { e : x_e = 0 and (B^T r)_e > 0 }; the scratch is the residual /
+        // derivative rows, dead until the next evaluation.  Pixels with an empty A (the common case) skip all of it.
+        {
+            __shared__ int s_na;
+            __shared__ unsigned char s_act[kMaxComp], s_in[kMaxComp];
+            constexpr int NV = NT + 1;
+            if (warp == 0) {
+                int base = 0;
+                for (int e0 = 0; e0 < E; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool act = e < E && xs[e] <= 0.f && gx[e] > 0.f;
+                    const unsigned m = __ballot_sync(0xffffffffu, act);
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (e < E) s_in[e] = act && pos < cap;
+                    if (act && pos < cap) s_act[pos] = (unsigned char)e;
+                    base += __popc(m);
+                }
+                if (lane == 0) s_na = min(base, cap);
+            }
+            __syncthreads();
+            const int na = s_na;
+            if (na > 0) {
+                float *M = r_s, *R = r_s + na * na;  // M = H_AA [na][na], R = V[A] [na][NV]
+                for (int i = tid; i < na * na; i += kRefThreads)
+                    M[i] = __ldg(p.g0inv + (long long)s_act[i / na] * E + s_act[i % na]);
+                for (int i = tid; i < na * NV; i += kRefThreads) {
+                    const int e = s_act[i / NV], k = i % NV;
+                    R[i] = k == NT ? w_s[e] : t1[e][k < NT ? k : 0];
+                }
+                // elimination without pivoting (H_AA is symmetric positive definite), thread q owns row q
+                for (int c = 0; c < na; ++c) {
+                    __syncthreads();
+                    if (tid > c && tid < na) {
+                        const float f = M[tid * na + c] / M[c * na + c];
+                        for (int cc = c + 1; cc < na; ++cc) M[tid * na + cc] = fmaf(-f, M[c * na + cc], M[tid * na + cc]);
+                        for (int k = 0; k < NV; ++k) R[tid * NV + k] = fmaf(-f, R[c * NV + k], R[tid * NV + k]);
+                    }
+                }
+                for (int c = na - 1; c >= 0; --c) {
+                    __syncthreads();
+                    if (tid < NV) R[c * NV + tid] = R[c * NV + tid] / M[c * na + c];
+                    __syncthreads();
+                    if (tid < c)
+                        for (int k = 0; k < NV; ++k) R[tid * NV + k] = fmaf(-M[tid * na + c], R[c * NV + k], R[tid * NV + k]);
+                }
+                __syncthreads();
+                for (int i = tid; i < E * NV; i += kRefThreads) {
+                    const int e = i / NV, k = i % NV;
+                    float corr = 0.f;
+                    for (int j = 0; j < na; ++j) corr = fmaf(__ldg(p.g0inv + (long long)e * E + s_act[j]), R[j * NV + k], corr);
+                    if (!isfinite(corr)) corr = 0.f;  // (a non-positive pivot in fp32: leave the entry as it was)
+                    const float v = s_in[e] ? 0.f : (k == NT ? w_s[e] : t1[e][k < NT ? k : 0]) - corr;
+                    if (k == NT)
+                        w_s[e] = v;
+                    else
+                        t1[e][k < NT ? k : 0] = v;
+                }
+                __syncthreads();
+            }
+        }
         // Schur complement of the theta block: the E-long dot products across warp 0, the NT x NT solve on lane 0
         __shared__ float schur[kMaxTheta + kMaxTheta * kMaxTheta];
         if (warp == 0) {
@@ -734,7 +815,7 @@ int cached_tables(const std::vector<char> &packed, const char **out) {
 }  // namespace
 
 extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
-                         int64_t ld_bkg, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+                         int64_t ld_bkg, const float *chan_weight_dev, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
                          const uint32_t *chan_lines_host, const int32_t *comp_start_host,
                          const int32_t *comp_lines_host, const uint32_t *line_window_host,
                          const int32_t *comp_order_host, const float *g0inv_dev,
@@ -854,6 +935,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.g0inv = g0inv_dev;
     p.bkg = bkg_dev;
     p.ld_bkg = ld_bkg;
+    p.chan_w = chan_weight_dev;
     p.spec = spec_dev;
     p.ld_spec = ld_spec;
     p.x = x_dev;
@@ -868,6 +950,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     bool general = false;
     for (int k = 0; k < cfg.n_theta; ++k) general = general || cfg.theta_id[k] >= MT_THETA_COHERENT_SCT_ENERGY;
     for (int l = 0; l < cfg.n_lines; ++l) general = general || lines_host[l].step > 0.f;
+    general = general || chan_weight_dev != nullptr;  // the channel weights live in the GENERAL instantiations
     const size_t smem = sizeof(float) * (size_t)((cfg.n_ch + 1) & ~1) * (1 + cfg.n_theta) +
                         sizeof(float4) * (size_t)cfg.n_lines * (general ? 4 + cfg.n_theta : 2);
     if (smem > 200 * 1024)

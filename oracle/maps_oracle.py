@@ -494,15 +494,19 @@ def gaussian_model_jacobian(params, energy_range, elements_to_fit, amps):
     return model, d_theta, basis, names
 
 
-def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bkg=None):
+def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bkg=None,
+                    indices=None):
     """Variable projection in float64: minimise over the free calibration parameters the NNLS
     residual of the spectrum on the Gaussian basis -- the minimiser the reference's
-    fit_spec(fitting_params=free, tune_params=True) heads for.  Returns (theta, amplitudes, loss)."""
+    fit_spec(fitting_params=free, tune_params=True) heads for.  `indices` restricts the objective to those channels
+    of the window, as fit_spec(indices=...) does (opt.py:344-347).  Returns (theta, amplitudes, loss)."""
     from scipy.optimize import least_squares, nnls
 
     y = np.asarray(spectrum, dtype=np.float64)[energy_range[0]: energy_range[1] + 1]
     if bkg is not None:
         y = y - np.asarray(bkg, dtype=np.float64)
+    if indices is not None:
+        y = y[np.asarray(indices)]
     start = np.array([float(p32(params, k)) for k in free])
     scale = np.where(start != 0, np.abs(start), 1.0)
     n_comp = len(component_names(elements_to_fit))
@@ -511,6 +515,8 @@ def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENER
         pp = dict(params, **dict(zip(free, theta)))
         # the full path of model_spec: Gaussians, step terms, scatter lines following their parameters
         _, _, B = model_jacobian(pp, energy_range, elements_to_fit, np.ones(n_comp), free=())
+        if indices is not None:
+            B = B[np.asarray(indices)]
         x, _ = nnls(B, y, maxiter=50 * n_comp)
         return B, x
 

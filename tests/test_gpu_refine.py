@@ -287,3 +287,75 @@ def test_linear_fit_includes_step_terms():
     # data were generated AT the global parameters: the refined offset stays put and the loss is the Poisson noise
     assert abs(float(maps["ENERGY_OFFSET"][0]) - p["ENERGY_OFFSET"]) < 5e-4
     assert float(maps["loss"][0]) < 1.3 * model.sum()
+
+
+def test_refinement_on_a_channel_subset():
+    """fit_map(indices=..., refine=...): the per-pixel refinement minimises over the selected channels only, like the
+    reference's fit_spec(indices=..., tune_params=True) (opt.py:344-347); oracle = float64 variable projection on the
+    same channels.  The selection drops a third of the window in blocks, including parts of peaks."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(14)
+    names = mo.component_names(ELEMS20)
+    idx = np.nonzero((np.arange(2048) // 48) % 3 != 1)[0]
+    specs = []
+    for i in range(4):
+        shift, widen = rng.uniform(-0.006, 0.006), rng.uniform(0.93, 1.08)
+        pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + shift, FWHM_OFFSET=p["FWHM_OFFSET"] * widen)
+        amps = 10.0 ** rng.uniform(2.0, 3.2, size=len(names))
+        model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+        spec = rng.poisson(model).astype(np.float32)
+        spec[(np.arange(2048) // 48) % 3 == 1] += 500.0  # garbage outside the selection must not matter
+        specs.append(spec)
+    y = np.stack(specs)
+    free = ("ENERGY_OFFSET", "FWHM_OFFSET")
+    maps = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, indices=idx, refine=free, refine_iters=20,
+                       device="cpu")
+    for i in range(4):
+        theta, x, loss = mo.refine_spectrum(y[i], p, er, ELEMS20, free=free, indices=idx)
+        assert abs(float(maps["ENERGY_OFFSET"][i]) - theta[0]) < 1e-5, i
+        assert abs(float(maps["FWHM_OFFSET"][i]) / theta[1] - 1) < 1e-4, i
+        assert float(maps["loss"][i]) <= loss * (1 + 2e-5), i
+        mine = np.array([float(maps[n][i]) for n in names])
+        interior = x > 1e-3 * x.max()
+        assert (np.abs(mine - x)[interior] / x[interior]).max() < 2e-4, i
+
+
+def test_refinement_with_absent_elements_reaches_the_constrained_minimum():
+    """Pixels that lack some of the fitted elements: their amplitudes sit at zero with a gradient that keeps them
+    there, and the Newton step has to be taken on the free components only (active set in mt_refine's step C).
+    Without it the iteration stalls at the least-squares start; oracle = float64 variable projection with NNLS inside."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(21)
+    names = mo.component_names(ELEMS20)
+    specs, n_zero = [], []
+    for i in range(5):
+        shift, widen = rng.uniform(-0.006, 0.006), rng.uniform(0.93, 1.08)
+        pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + shift, FWHM_OFFSET=p["FWHM_OFFSET"] * widen)
+        amps = 10.0 ** rng.uniform(2.0, 3.2, size=len(names))
+        amps[rng.random(len(names)) < 0.35] = 0.0
+        model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+        # (a constant taken off the counts, as after an over-estimated background: absent elements then want negative
+        # amplitudes and the constraint is active -- 5 to 9 of the 22 components per pixel in the oracle's solution)
+        specs.append(rng.poisson(model).astype(np.float32) - 1.5)
+    y = np.stack(specs)
+    free = ("ENERGY_OFFSET", "FWHM_OFFSET")
+    maps = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, refine=free, refine_iters=30, device="cpu")
+    for i in range(5):
+        theta, x, loss = mo.refine_spectrum(y[i], p, er, ELEMS20, free=free)
+        n_zero.append(int((x == 0).sum()))
+        assert float(maps["loss"][i]) <= loss * (1 + 5e-5), (i, float(maps["loss"][i]) / loss - 1)
+        assert abs(float(maps["ENERGY_OFFSET"][i]) - theta[0]) < 2e-5, i
+        assert abs(float(maps["FWHM_OFFSET"][i]) / theta[1] - 1) < 2e-4, i
+        mine = np.array([float(maps[n][i]) for n in names])
+        assert np.abs(mine - x).max() < 5e-4 * x.max(), i
+    assert min(n_zero) >= 3  # the constraint is active in every pixel
