@@ -453,7 +453,8 @@ def accuracy_check(plan, flat, got, params, er, w, device):
     return check
 
 
-def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e_steps, with_cpu_baseline):
+def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e_steps, with_cpu_baseline,
+                 extra_modes=False):
     """Build, check, time one workload; returns the record of its measurements (rank 0's view)."""
     import torch.distributed as dist
     from mapstorch_b200 import _native, opt
@@ -642,6 +643,44 @@ def run_workload(name, args, rank, local_rank, world, device, steps, warmup, e2e
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         peer_check = {"bit_identical": bool(int(flag)), "mode": sharded.gather, "graph": bool(use_graph),
                       "components_checked_on_rank0": len(owned), "against": "NCCL all-gather of the same fit"}
+        # the other two exchange patterns of the same fit (everything on rank 0 / everything everywhere), short runs:
+        # same step, same check; reported beside the headline mode, never instead of it
+        exchange_modes = {}
+        if extra_modes:
+            for mode in ("owner", "root", "all"):
+                if mode == sharded.gather:
+                    exchange_modes[mode] = {"ms_per_step": ms_total / steps, "value": value, "unit": "px/s",
+                                            "bit_identical": peer_check["bit_identical"], "headline": True}
+                    continue
+                other = ShardedMapFit(plan, total_rows, w["width"], gather=mode, buffers=2)
+                ok_all = torch.tensor([1 if other.fused else 0], device=device)
+                dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+                if not int(ok_all):
+                    exchange_modes[mode] = {"unavailable": other.why_not or "not fused on every rank"}
+                    del other
+                    continue
+
+                def other_step():
+                    other.step(flat, graph=use_graph)
+
+                for _ in range(3):
+                    other_step()
+                other.finish()
+                n_short = max(3, min(steps, 10))
+                ms_o = timed(other_step, n_short, after=other.finish) / n_short
+                bo = other.step(flat, graph=use_graph)
+                other.finish()
+                torch.cuda.synchronize()
+                other.peer_maps.check()
+                res_o = other.result(bo)
+                same_o = all(torch.equal(res_o[e], ref_full[e]) for e in other.owned())
+                flag_o = torch.tensor([1 if same_o else 0], device=device)
+                dist.all_reduce(flag_o, op=dist.ReduceOp.MIN)
+                exchange_modes[mode] = {"ms_per_step": ms_o, "value": world * n_px / (ms_o * 1e-3), "unit": "px/s",
+                                        "steps": n_short, "bit_identical": bool(int(flag_o))}
+                del other, res_o
+                torch.cuda.empty_cache()
+            peer_check["exchange_modes"] = exchange_modes
         del ref_full
 
     # ---- end to end through the public API, host buffers ------------------------------------------
@@ -770,7 +809,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     head = run_workload(args.workload, args, rank, local_rank, world, device, args.steps, args.warmup,
-                        0 if args.no_e2e else args.e2e_steps, not args.no_cpu_baseline)
+                        0 if args.no_e2e else args.e2e_steps, not args.no_cpu_baseline,
+                        extra_modes=world > 1 and not args.no_extra and not args.nccl_gather)
     if early_cb is not None:
         head["cpu_baseline"] = early_cb
 
