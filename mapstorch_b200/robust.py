@@ -144,7 +144,7 @@ LAD_KAPPA = 3.0       # first-stage threshold per pixel = LAD_KAPPA x mean |resi
 LAD_CHUNK_PX = 32768  # t, u and the operand planes cost 16 bytes per (pixel, channel)
 
 
-def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPPA, chunk_px=LAD_CHUNK_PX):
+def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPPA, chunk_px=LAD_CHUNK_PX, l1_lambda=0.0):
     """argmin_{x >= 0} sum_c |x . B[:, c] + bkg_c - y_c| for every pixel of spec2d [P, C_full] (CUDA or host; the
     reference's loss="l1" with the calibration fixed, opt.py:232-233, 371-375; restricted to plan's `indices`).
 
@@ -152,7 +152,12 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
     pseudo-inverse + the batched non-negative fix-up, applied to the modified target t + z - u (incrementally: the
     contraction sees the change of the target, the unconstrained solution is accumulated) -- and mt_lad_update
     does the rest in one pass (model, soft threshold, dual update, operand split, L1 objective of the current x).
-    The best iterate per pixel is kept; `schedule` lists (iterations, threshold factor) stages.  Returns (x [E, P] fp32, objective [P]) on the device."""
+    The best iterate per pixel is kept; `schedule` lists (iterations, threshold factor) stages.  Returns (x [E, P] fp32, objective [P]) on the device.
+
+    l1_lambda > 0 adds the reference's amplitude penalty c_p * sum(x) with c_p = l1_lambda * sum|y - bkg| / n_elements per
+    pixel (opt.py:372-381 with the L1 loss).  On x >= 0 the penalty is linear, so it only moves the unconstrained
+    solution of the x-update: with the threshold kappa = 1 / rho the update minimises c sum(x) + |B^T x - v|^2 / (2 kappa),
+    i.e. x = nonneg(xu - c_p kappa_p G^-1 1).  The reported objective includes the penalty."""
     import ctypes  # noqa: F401
 
     from mapstorch_b200 import bkg as _bkg
@@ -173,6 +178,10 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
     qs = torch.zeros((chunk, pitch), dtype=torch.float32, device="cuda")
     q = torch.zeros((chunk, 2 * pitch), dtype=torch.float32, device="cuda")[:, : 2 * n_ch]
     stream = _native.stream_ptr()
+    penalised = float(l1_lambda) > 0
+    if penalised and not nonneg:
+        raise ValueError("the l1_lambda penalty needs the non-negative solve")
+    hinv1 = torch.from_numpy(plan.hinv.sum(axis=1).astype("float32")).cuda() if penalised else None  # (G^-1 1), live components
 
     def update(tn, xn, un, kap, qsn, qn, obj, mode):
         ptr = lambda a: a.data_ptr() if a is not None else None  # noqa: E731
@@ -211,6 +220,19 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
         obj = torch.empty(n, dtype=torch.float32, device="cuda")
         update(tn, x, None, None, None, None, obj, 0)
         kap = (float(kappa) / n_active) * obj
+        pen = (float(l1_lambda) / max(n_all, 1)) * tn[:, :n_ch].abs().sum(dim=1) if penalised else None  # c_p
+
+        def solve(kap_now):
+            if pen is None:
+                return nonneg_copy(xu)
+            return nonneg_copy(xu - hinv1[:, None] * (pen * kap_now)[None, :])
+
+        def total(x_now):  # the kernel's L1 objective of x_now (in obj) plus the penalty
+            if pen is not None:
+                obj.add_(pen * x_now.sum(dim=0))
+            return obj
+
+        total(x)
         best_obj, best_x = obj.clone(), x.clone()
         for n_stage, factor in schedule:
             if factor != 1.0:
@@ -218,13 +240,15 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
                 kap = kap * factor
             for _ in range(int(n_stage)):
                 update(tn, x, un, kap, qsn, qn, obj, 1)  # obj = objective of the x that enters
+                total(x)
                 better = obj < best_obj
                 best_obj = torch.where(better, obj, best_obj)
                 best_x = torch.where(better[None, :], x, best_x)
                 plan.fit_operand_hilo(qn, dxu, nonneg=False)
                 xu += dxu
-                x = nonneg_copy(xu)
+                x = solve(kap)
         update(tn, x, None, None, None, None, obj, 0)
+        total(x)
         better = obj < best_obj
         best_obj = torch.where(better, obj, best_obj)
         best_x = torch.where(better[None, :], x, best_x)

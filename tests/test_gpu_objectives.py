@@ -159,8 +159,8 @@ def test_fit_map_penalty_per_pixel(dtype, use_snip, with_idx):
         assert np.abs(got[px][~interior] - exact[~interior]).max(initial=0.0) <= 1e-4 * top, px
         effect = max(effect, float(np.abs(plain - exact).max() / top))
     assert effect > 1e-3  # the penalty did move the answer (100x the tolerance checked above)
-    with pytest.raises(NotImplementedError):  # the L1 maps take no amplitude penalty (the single-spectrum fit does)
-        opt.fit_map(vol, er, fitted, p, use_snip=use_snip, loss="l1", l1_lambda=lam)
+    with pytest.raises(NotImplementedError):  # the L1 maps are not refined per pixel
+        opt.fit_map(vol, er, fitted, p, use_snip=use_snip, loss="l1", refine=("ENERGY_OFFSET",))
 
 
 def test_global_fit_with_l1_loss_recovers_the_calibration():
@@ -247,3 +247,46 @@ def test_l1_maps_reach_the_lad_optimum_per_pixel(use_snip, masked):
     # measured on B200: 1.9e-6 (plain), 5.2e-6 (SNIP residuals), ~1e-5 (peak-window masks); median ~2e-7
     assert worst <= 2e-5
     assert np.mean(gain) > 1.0005
+
+
+def test_l1_maps_with_amplitude_penalty_reach_the_lp_optimum():
+    """fit_map(loss="l1", l1_lambda=...): sum|B^T x - t| + c_p sum(x), c_p = l1_lambda * sum|t| / n_elements per pixel
+    (opt.py:372-381 with the L1 loss), against the exact linear programme (oracle.fit_lad with that c) on every eighth
+    of 128 pixels with outliers; the penalty is strong enough to move the answer."""
+    from mapstorch_b200 import opt
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    elems = ["K", "Ca", "Ti", "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn"]
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(19)
+    B, names = mo.basis(p, er, elems)
+    B64 = B.astype(np.float64)
+    n_px, lam = 128, 2e-3  # between "nothing moves" (1e-4) and "everything is switched off" (1e-2) on these pixels
+    amps = 10.0 ** rng.uniform(0.5, 3.0, size=(n_px, B.shape[1]))
+    y = rng.poisson(amps @ B64.T + 1.0).astype(np.float32)
+    for i in range(n_px):
+        y[i, rng.integers(0, 2048, 4)] += rng.uniform(50, 400, 4).astype(np.float32)
+    vol = torch.from_numpy(y).reshape(8, 16, -1)
+    maps = opt.fit_map(vol, er, elems, init_param_vals=p, use_snip=False, loss="l1", l1_lambda=lam)
+    plain = opt.fit_map(vol, er, elems, init_param_vals=p, use_snip=False, loss="l1")
+    got = torch.stack([maps[n] for n in names], dim=-1).reshape(n_px, -1).cpu().numpy().astype(np.float64)
+    unpen = torch.stack([plain[n] for n in names], dim=-1).reshape(n_px, -1).cpu().numpy().astype(np.float64)
+    loss = maps["loss"].reshape(-1).cpu().numpy()
+    assert (got >= 0).all()
+    worst, moved, n_off = 0.0, 0.0, 0
+    for i in range(0, n_px, 8):
+        t = y[i].astype(np.float64)
+        c = lam * np.abs(t).sum() / len(names)
+        exact, best = mo.fit_lad(t, B64.T, None, c)
+        n_off += int((exact <= 1e-9 * exact.max()).sum())
+        assert exact.max() > 0
+        mine = np.abs(B64 @ got[i] - t).sum() + c * got[i].sum()
+        assert abs(mine - loss[i]) <= 2e-4 * best, i
+        worst = max(worst, (mine - best) / best)
+        other = np.abs(B64 @ unpen[i] - t).sum() + c * unpen[i].sum()
+        moved = max(moved, (other - mine) / mine)
+    print(f"penalised L1 maps: worst relative gap to the LP optimum {worst:.2e}; the unpenalised answer is up to {moved:.2%} worse")
+    assert worst <= 5e-5
+    assert moved > 1e-4 and n_off >= 8  # the penalty switched components off without emptying the pixels
