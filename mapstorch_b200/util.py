@@ -20,18 +20,23 @@ def get_channel_from_energy(energy, ev):
     return int(hits[0]) if hits.size else len(ev) - 1
 
 
+def _compton_energy(e0, angle_deg):
+    """Energy of the Compton peak for incident energy e0 (keV) scattered by angle_deg (same float64 expression as
+    util.py:74-78, so the window edges derived from it are bit-identical)."""
+    return e0 / (1 + (e0 / 511) * (1 - math.cos(angle_deg * 2 * M_PI / 360.0)))
+
+
 def get_peak_centers(elements, coherent_sct_energy, compton_angle, e_consts=default_energy_consts):
+    """{peak name: centre energy}: the two scatter peaks under their component names, element lines as "<El>_<slot>"
+    for every slot with a positive energy, in the order of `elements` (util.py:67-84)."""
     centers = {}
-    for e in elements:
-        if e == "COMPTON_AMPLITUDE":
-            centers[e] = coherent_sct_energy / (
-                1 + (coherent_sct_energy / 511) * (1 - math.cos(compton_angle * 2 * M_PI / 360.0)))
-        elif e == "COHERENT_SCT_AMPLITUDE":
-            centers[e] = coherent_sct_energy
-        elif e in default_fitting_elems:
-            for i, line in enumerate(e_consts[e]):
-                if line.energy > 0:
-                    centers[e + "_" + str(i)] = line.energy
+    for name in elements:
+        if name == "COHERENT_SCT_AMPLITUDE":
+            centers[name] = coherent_sct_energy
+        elif name == "COMPTON_AMPLITUDE":
+            centers[name] = _compton_energy(coherent_sct_energy, compton_angle)
+        elif name in default_fitting_elems:
+            centers.update({f"{name}_{slot}": line.energy for slot, line in enumerate(e_consts[name]) if line.energy > 0})
     return centers
 
 
@@ -89,25 +94,29 @@ def _scatter_peak_indices(values, window=3, min_distance=10, top_k=20, threshold
     return (max(left, key=lambda i: sm[i]) if left else None), elastic
 
 
-def estimate_and_update_params(int_spec, energy_range, coherent_sct_energy, param_reference=None):
-    """Updates for COHERENT_SCT_ENERGY / ENERGY_SLOPE / COMPTON_ANGLE inferred from the scatter peaks."""
-    if coherent_sct_energy is None or coherent_sct_energy <= 0:
-        return {}
-    arr = np.asarray(int_spec, dtype=float).ravel()
-    if arr.size == 0:
-        return {}
-    start = max(0, min(int(energy_range[0]), arr.size - 1))
-    stop = min(arr.size, max(start + 1, int(energy_range[1]) + 1))
-    roi = arr[start:stop]
-    if roi.size < 3:
-        return {}
-    compton_rel, elastic_rel = _scatter_peak_indices(roi)
-    elastic_idx = start + elastic_rel if elastic_rel is not None else max(1, int((arr.size - 1) // 1.9))
-    compton_idx = start + compton_rel if compton_rel is not None else max(1, int((arr.size - 1) // 2))
-    slope = coherent_sct_energy / elastic_idx
-    compton_energy = slope * compton_idx
+def _scatter_angle(e_compton, e_elastic):
+    """Scattering angle (degrees) that puts the Compton peak of e_elastic at e_compton; None outside acos's domain."""
     try:
-        angle = math.acos(1 - 511 * (1 / compton_energy - 1 / coherent_sct_energy)) * 180 / math.pi
+        return math.acos(1 - 511 * (1 / e_compton - 1 / e_elastic)) * 180 / math.pi
     except (ValueError, ZeroDivisionError):
-        angle = default_param_vals["COMPTON_ANGLE"]
-    return {"COHERENT_SCT_ENERGY": coherent_sct_energy, "ENERGY_SLOPE": slope, "COMPTON_ANGLE": angle}
+        return None
+
+
+def estimate_and_update_params(int_spec, energy_range, coherent_sct_energy, param_reference=None):
+    """Updates for COHERENT_SCT_ENERGY / ENERGY_SLOPE / COMPTON_ANGLE inferred from the scatter peaks (util.py:189-229):
+    the elastic peak fixes the gain (its channel carries the incident energy), the Compton peak's channel then gives the
+    scattering angle.  Peaks that cannot be found fall back to fixed fractions of the spectrum length."""
+    spectrum = np.asarray(int_spec, dtype=float).ravel()
+    if coherent_sct_energy is None or coherent_sct_energy <= 0 or spectrum.size == 0:
+        return {}
+    first = max(0, min(int(energy_range[0]), spectrum.size - 1))
+    last = min(spectrum.size, max(first + 1, int(energy_range[1]) + 1))
+    if last - first < 3:
+        return {}
+    found = _scatter_peak_indices(spectrum[first:last])  # (compton, elastic), relative to the window
+    fallback = (max(1, int((spectrum.size - 1) // 2)), max(1, int((spectrum.size - 1) // 1.9)))
+    compton_ch, elastic_ch = (first + rel if rel is not None else default for rel, default in zip(found, fallback))
+    slope = coherent_sct_energy / elastic_ch
+    angle = _scatter_angle(slope * compton_ch, coherent_sct_energy)
+    return {"COHERENT_SCT_ENERGY": coherent_sct_energy, "ENERGY_SLOPE": slope,
+            "COMPTON_ANGLE": default_param_vals["COMPTON_ANGLE"] if angle is None else angle}
