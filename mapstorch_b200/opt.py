@@ -745,8 +745,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     ("root").  The exchange is fused into the fit kernels (peer stores over NVLink), see dist.ShardedMapFit."""
     if loss not in ("mse", "l1"):
         raise ValueError("Loss function not supported")
-    if loss == "l1" and (refine or group is not None or energy_dim != 2):
-        raise NotImplementedError('fit_map(loss="l1") is the per-pixel L1 fit (no refine / group / energy_dim)')
+    if loss == "l1" and (refine or group is not None or int_spec):
+        raise NotImplementedError('fit_map(loss="l1") is the per-pixel L1 fit (no refine / group / int_spec)')
     _native.require_device()
     if group is not None:
         # multi-GPU form: spec_vol is this rank's block of rows; maps of the whole grid come back (dist.py)
@@ -841,7 +841,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         # sum of absolute residuals per pixel (opt.py:232-233): ADMM around the same contraction, robust.fit_map_lad
         from mapstorch_b200 import robust
 
-        x, objective = robust.fit_map_lad(plan, flat, nonneg=nonneg, l1_lambda=l1_lambda)
+        x, objective = robust.fit_map_lad(plan, flat, nonneg=nonneg, l1_lambda=l1_lambda, loader=loader,
+                                          n_px=lead[0] * lead[1] if loader is not None else None)
         if as_log10:
             x = torch.log10(x)
         on_dev = torch.device(device).type == "cuda"

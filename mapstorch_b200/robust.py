@@ -144,7 +144,8 @@ LAD_KAPPA = 3.0       # first-stage threshold per pixel = LAD_KAPPA x mean |resi
 LAD_CHUNK_PX = 32768  # t, u and the operand planes cost 16 bytes per (pixel, channel)
 
 
-def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPPA, chunk_px=LAD_CHUNK_PX, l1_lambda=0.0):
+def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPPA, chunk_px=LAD_CHUNK_PX, l1_lambda=0.0,
+                loader=None, n_px=None):
     """argmin_{x >= 0} sum_c |x . B[:, c] + bkg_c - y_c| for every pixel of spec2d [P, C_full] (CUDA or host; the
     reference's loss="l1" with the calibration fixed, opt.py:232-233, 371-375; restricted to plan's `indices`).
 
@@ -157,12 +158,15 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
     l1_lambda > 0 adds the reference's amplitude penalty c_p * sum(x) with c_p = l1_lambda * sum|y - bkg| / n_elements per
     pixel (opt.py:372-381 with the L1 loss).  On x >= 0 the penalty is linear, so it only moves the unconstrained
     solution of the x-update: with the threshold kappa = 1 / rho the update minimises c sum(x) + |B^T x - v|^2 / (2 kappa),
-    i.e. x = nonneg(xu - c_p kappa_p G^-1 1).  The reported objective includes the penalty."""
+    i.e. x = nonneg(xu - c_p kappa_p G^-1 1).  The reported objective includes the penalty.
+
+    loader (with n_px): a slab source of opt.fit_map -- loader(p0, n, dst) fills dst [n, C_full] on the device with pixels
+    p0 .. p0 + n (whole rows) -- instead of spec2d: lazily read files and channel-first volumes, chunk by chunk."""
     import ctypes  # noqa: F401
 
     from mapstorch_b200 import bkg as _bkg
 
-    n_px, n_all = spec2d.shape[0], len(plan.names)
+    n_px, n_all = (int(n_px) if loader is not None else spec2d.shape[0]), len(plan.names)
     n_ch, er0 = plan.n_ch, plan.er[0]
     live = torch.as_tensor(plan.live, device="cuda")
     basis = plan.basis[live].contiguous()
@@ -172,6 +176,11 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
     out = torch.zeros((n_all, n_px), dtype=torch.float32, device="cuda")
     objective = torch.zeros(n_px, dtype=torch.float32, device="cuda")
     chunk = max(1, min(int(chunk_px), n_px))
+    slab = None
+    if loader is not None:
+        # chunks of whole loader slabs (which are whole rows of the map)
+        chunk = min(max(1, int(chunk_px) // loader.chunk_px) * loader.chunk_px, -(-n_px // loader.chunk_px) * loader.chunk_px)
+        slab = torch.empty((chunk, loader.n_ch), dtype=loader.dtype, device="cuda")
     pitch = -(-n_ch // 4) * 4
     t = torch.zeros((chunk, pitch), dtype=torch.float32, device="cuda")
     u = torch.zeros((chunk, pitch), dtype=torch.float32, device="cuda")
@@ -199,9 +208,15 @@ def fit_map_lad(plan, spec2d, nonneg=True, schedule=LAD_SCHEDULE, kappa=LAD_KAPP
 
     for p0 in range(0, n_px, chunk):
         n = min(chunk, n_px - p0)
-        part = spec2d[p0: p0 + n]
-        if part.device.type != "cuda":
-            part = part.cuda(non_blocking=True)
+        if loader is not None:
+            for q0 in range(0, n, loader.chunk_px):
+                m = min(loader.chunk_px, n - q0)
+                loader(p0 + q0, m, slab[q0: q0 + m])
+            part = slab[:n]
+        else:
+            part = spec2d[p0: p0 + n]
+            if part.device.type != "cuda":
+                part = part.cuda(non_blocking=True)
         tn, un, qsn, qn = t[:n], u[:n], qs[:n], q[:n]
         # target t = y - bkg on the fitted window
         if plan.use_snip:
