@@ -432,8 +432,27 @@ def fit_map_sharded(spec_shard, energy_range, elements_to_fit=None, group=None, 
                  "use_snip", "e_consts", "elem_info", "detector_type", "escape_factor")}
     l1_lambda = float(fit_map_kw.pop("l1_lambda", 0.0))
     nonneg = bool(fit_map_kw.pop("nonneg", True))
+    loss = fit_map_kw.pop("loss", "mse")
+    refine = fit_map_kw.pop("refine", None)
+    refine_kw = {k: fit_map_kw.pop(k) for k in list(fit_map_kw) if k in ("refine_iters", "refine_bounds")}
     if fit_map_kw:
         raise TypeError(f"fit_map_sharded does not take {sorted(fit_map_kw)}")
+    if refine or loss != "mse":
+        # Per-pixel refinement and the L1 objective produce more than amplitudes (calibration maps, loss, iteration
+        # counts) and run their own kernels after the contraction: every rank fits its block with the single-GPU call
+        # and the maps are assembled by one NCCL all-gather (what the fused exchange is checked against); entry i of
+        # the result lives on rank i % world with gather="owner", everything on rank 0 with "root".
+        local = opt.fit_map(spec_shard, energy_range, elements, l1_lambda=l1_lambda, nonneg=nonneg, loss=loss,
+                            refine=refine, device="cuda", **supported, **refine_kw)
+        keys = list(local)
+        stacked = torch.stack([local[k].reshape(-1).to(torch.float32) for k in keys])
+        full = gather_maps(stacked, n_rows, width, group=group)
+        rank = dist.get_rank(group)
+        out = {}
+        for i, k in enumerate(keys):
+            if gather == "all" or (gather == "root" and rank == 0) or (gather == "owner" and i % world == rank):
+                out[k] = full[i].reshape(n_rows, width).to(local[k].dtype)
+        return out
     if plan is None:
         params = dict(supported.get("init_param_vals", opt.default_param_vals))
         params.update(supported.get("fixed_param_vals", {}))

@@ -745,13 +745,13 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
     ("root").  The exchange is fused into the fit kernels (peer stores over NVLink), see dist.ShardedMapFit."""
     if loss not in ("mse", "l1"):
         raise ValueError("Loss function not supported")
-    if loss == "l1" and (refine or group is not None or int_spec):
-        raise NotImplementedError('fit_map(loss="l1") is the per-pixel L1 fit (no refine / group / int_spec)')
+    if loss == "l1" and (refine or int_spec):
+        raise NotImplementedError('fit_map(loss="l1") is the per-pixel L1 fit (no refine / int_spec)')
     _native.require_device()
     if group is not None:
         # multi-GPU form: spec_vol is this rank's block of rows; maps of the whole grid come back (dist.py)
-        if refine or as_log10 or plan is not None or return_plan or engine != "tensor":
-            raise NotImplementedError("fit_map(group=...) supports the plain map fit (no refine / as_log10 / plan / engine)")
+        if as_log10 or plan is not None or return_plan or engine != "tensor" or energy_dim != 2 or int_spec:
+            raise NotImplementedError("fit_map(group=...): no as_log10 / plan / return_plan / engine / energy_dim / int_spec")
         from mapstorch_b200.dist import fit_map_sharded
 
         if not isinstance(spec_vol, torch.Tensor):
@@ -759,7 +759,8 @@ def fit_map(spec_vol, energy_range, elements_to_fit=default_fitting_elems, init_
         maps = fit_map_sharded(spec_vol, energy_range, elements_to_fit, group=group, gather=gather,
                                init_param_vals=init_param_vals, fixed_param_vals=fixed_param_vals, indices=indices,
                                use_snip=use_snip, e_consts=e_consts, elem_info=elem_info, detector_type=detector_type,
-                               escape_factor=escape_factor, nonneg=nonneg, l1_lambda=l1_lambda)
+                               escape_factor=escape_factor, nonneg=nonneg, l1_lambda=l1_lambda, loss=loss, refine=refine,
+                               refine_iters=refine_iters, refine_bounds=refine_bounds)
         return maps if torch.device(device).type == "cuda" else {k: v.cpu() for k, v in maps.items()}
     if energy_dim not in (0, 1, 2):
         raise ValueError("energy_dim must be 0, 1, or 2")

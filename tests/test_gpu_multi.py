@@ -109,6 +109,22 @@ def _worker(rank, world, port):
             part = opt.fit_map(v[a0:a1], (0, 2047), ELEMS10, init_param_vals=p10, use_snip=False, group=dist.group.WORLD)
             for name in full:
                 assert torch.equal(part[name], full[name]), name
+        # per-pixel refinement and the L1 objective in sharded form: the rank's block through the single-GPU call, maps
+        # (incl. calibration maps, loss, iterations) by NCCL; every gather mode
+        v = _volume(plan10, 6, 40, seed=3).cuda()
+        a0, a1 = mdist.shard_rows(6, rank, world)
+        for kw in (dict(refine=("ENERGY_OFFSET", "FWHM_OFFSET"), refine_iters=8), dict(loss="l1"),
+                   dict(loss="l1", l1_lambda=1e-3)):
+            full = opt.fit_map(v, (0, 2047), ELEMS10, init_param_vals=p10, use_snip=False, **kw)
+            for gather in ("all", "owner", "root"):
+                part = opt.fit_map(v[a0:a1], (0, 2047), ELEMS10, init_param_vals=p10, use_snip=False,
+                                   group=dist.group.WORLD, gather=gather, **kw)
+                keys = list(full)
+                want = keys if gather == "all" else ([k for i, k in enumerate(keys) if i % world == rank]
+                                                     if gather == "owner" else (keys if rank == 0 else []))
+                assert list(part) == want, (kw, gather)
+                for name, m in part.items():
+                    assert m.dtype == full[name].dtype and torch.equal(m, full[name]), (kw, gather, name)
         torch.cuda.synchronize()
         dist.barrier()
     finally:
