@@ -358,9 +358,13 @@ int mt_model_jacobian(const MtRefineConfig *cfg_host, const MtRefineLine *lines_
  * x_dev [n_comp][ld_x] holds the starting amplitudes (from mt_fit_contract) and receives the result;
  * theta_dev [n_theta][ld_theta], loss_dev [n_px], iters_dev [n_px] are optional outputs.
  * chan_weight_dev (optional, fp32 [n_ch], 0 or 1): the channels that enter the objective -- `indices` of fit_spec
- * (opt.py:344-347); g0inv_dev must then be the inverse Gram matrix of the masked basis. */
+ * (opt.py:344-347); g0inv_dev must then be the inverse Gram matrix of the masked basis.
+ * escape_bins > 0 with escape_factor > 0: every component carries its detector escape peak, b'(c) = b(c) + escape_factor *
+ * b(c + escape_bins) for c + escape_bins < n_ch (escape_peak, map.py:127-150; the bin shift is the one of the global
+ * calibration); g0inv_dev then belongs to that augmented basis. */
 int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
-              int64_t ld_bkg, const float *chan_weight_dev, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+              int64_t ld_bkg, const float *chan_weight_dev, int32_t escape_bins, float escape_factor,
+              const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
               const uint32_t *chan_lines_host, const int32_t *comp_start_host, const int32_t *comp_lines_host,
               const uint32_t *line_window_host, const int32_t *comp_order_host, const float *g0inv_dev,
               float *x_dev, int64_t ld_x,

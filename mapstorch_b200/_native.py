@@ -101,8 +101,8 @@ SIGNATURES = {
     "mt_int_spec": [_vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "mt_lad_update": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp],
     "mt_model_jacobian": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
-    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
-                  _vp, _vp],
+    "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
+                  _vp, _vp, _vp],
     "mt_spec_solve": [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _vp,
                       _i32, _vp],
 }

@@ -66,6 +66,8 @@ struct RefParams {
     const float *bkg;
     long long ld_bkg;
     const float *chan_w;            // optional [n_ch]: weight (0 / 1) of each channel in the objective (fit_spec's `indices`)
+    int escape_bins;                // > 0: every column carries its escape peak, b'(c) = b(c) + escape_factor * b(c + bins)
+    float escape_factor;            //      (map.py:127-150); GENERAL instantiations only
     const void *spec;
     long long ld_spec;
     float *x;
@@ -361,6 +363,24 @@ refine_kernel(const RefParams p) {
             const int l_end = l_begin + (int)(info >> 22);
             f32x2 m, d[NT > 0 ? NT : 1];
             eval_pair<NT, GENERAL>(id_k, cal, cg, l_begin, l_end, L, lc0, lc1, lc2, lck, m, d);
+            if (GENERAL && p.escape_bins > 0) {
+                // escape peaks: the residual needs the model of channel c + bins as well; store the raw model and
+                // derivative rows here, the shift passes below form the residual and the sums
+                if (!has1) {
+                    float lo, hi;
+                    unpack2(m, lo, hi);
+                    m = pack2(lo, 0.f);
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) {
+                        unpack2(d[k], lo, hi);
+                        d[k] = pack2(lo, 0.f);
+                    }
+                }
+                *reinterpret_cast<f32x2 *>(r_s + c0) = m;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) *reinterpret_cast<f32x2 *>(d_s + k * ld + c0) = d[k];
+                continue;
+            }
             f32x2 res = add2(m, pack2(-y0, -y1));
             if (GENERAL && p.chan_w != nullptr) {
                 // (only in the GENERAL instantiations, which the host selects for masked fits: the lean kernel of the
@@ -391,6 +411,70 @@ refine_kernel(const RefParams p) {
                 acc[1 + k] = fma2(d[k], res, acc[1 + k]);
 #pragma unroll
                 for (int k2 = 0; k2 < NT; ++k2) acc[1 + NT + k * NT + k2] = fma2(d[k], d[k2], acc[1 + NT + k * NT + k2]);
+            }
+        }
+        if (GENERAL && p.escape_bins > 0) {
+            // ---- escape peaks (map.py:127-150): model'(c) = model(c) + f * model(c + bins) for c + bins < n_ch ------
+            // In place, 128 channels at a time in ASCENDING order: a thread reads its channel and the shifted one, the
+            // CTA synchronises, the thread writes -- the shifted source lies in the same block (hence the barrier) or in a
+            // later one that is still untouched.  Residual, channel weights and the sums of the step are formed here.
+            const int bins = p.escape_bins;
+            const float f = p.escape_factor;
+            __syncthreads();
+            for (int base = 0; base < n_ch; base += kRefThreads) {
+                const int c = base + tid;
+                const bool in = c < n_ch;
+                float mv = 0.f, dv[NT > 0 ? NT : 1];
+#pragma unroll
+                for (int k = 0; k < NT; ++k) dv[k] = 0.f;
+                if (in) {
+                    const bool sh = c + bins < n_ch;
+                    mv = r_s[c] + (sh ? f * r_s[c + bins] : 0.f);
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) dv[k] = d_s[k * ld + c] + (sh ? f * d_s[k * ld + c + bins] : 0.f);
+                    const float y = ld_spec<T>(row + c) - (brow ? __ldg(brow + c) : 0.f);
+                    const float w = p.chan_w != nullptr ? __ldg(p.chan_w + c) : 1.f;
+                    mv = (mv - y) * w;
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) dv[k] *= w;
+                }
+                __syncthreads();
+                if (in) {
+                    r_s[c] = mv;
+                    const f32x2 r2 = pack2(mv, 0.f);
+                    acc[0] = fma2(r2, r2, acc[0]);
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) {
+                        d_s[k * ld + c] = dv[k];
+                        const f32x2 dk = pack2(dv[k], 0.f);
+                        acc[1 + k] = fma2(dk, r2, acc[1 + k]);
+#pragma unroll
+                        for (int k2 = 0; k2 < NT; ++k2)
+                            acc[1 + NT + k * NT + k2] = fma2(dk, pack2(dv[k2], 0.f), acc[1 + NT + k * NT + k2]);
+                    }
+                }
+            }
+            // The component pass multiplies the rows with the UNSHIFTED line shapes b(c); sum_c b'(c) r(c) equals
+            // sum_c b(c) (r(c) + f * r(c - bins)), so the rows are folded once more, in DESCENDING order (the source
+            // c - bins lies in the same block or in a lower one, processed later).
+            __syncthreads();
+            for (int base = ((n_ch - 1) / kRefThreads) * kRefThreads; base >= 0; base -= kRefThreads) {
+                const int c = base + tid;
+                const bool in = c < n_ch && c >= bins;
+                float rv = 0.f, dv[NT > 0 ? NT : 1];
+#pragma unroll
+                for (int k = 0; k < NT; ++k) dv[k] = 0.f;
+                if (in) {
+                    rv = r_s[c] + f * r_s[c - bins];
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) dv[k] = d_s[k * ld + c] + f * d_s[k * ld + c - bins];
+                }
+                __syncthreads();
+                if (in) {
+                    r_s[c] = rv;
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) d_s[k * ld + c] = dv[k];
+                }
             }
         }
 #pragma unroll
@@ -815,7 +899,8 @@ int cached_tables(const std::vector<char> &packed, const char **out) {
 }  // namespace
 
 extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec, const float *bkg_dev,
-                         int64_t ld_bkg, const float *chan_weight_dev, const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
+                         int64_t ld_bkg, const float *chan_weight_dev, int32_t escape_bins, float escape_factor,
+                         const MtRefineConfig *cfg_host, const MtRefineLine *lines_host,
                          const uint32_t *chan_lines_host, const int32_t *comp_start_host,
                          const int32_t *comp_lines_host, const uint32_t *line_window_host,
                          const int32_t *comp_order_host, const float *g0inv_dev,
@@ -833,6 +918,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     MT_REQUIRE(cfg.n_theta >= 0 && cfg.n_theta <= kMaxTheta, "mt_refine: n_theta=%d (at most %d per pixel)", cfg.n_theta,
                kMaxTheta);
     MT_REQUIRE(n_px >= 0 && ld_x >= n_px && (!bkg_dev || ld_bkg >= cfg.n_ch), "mt_refine: sizes");
+    MT_REQUIRE(escape_bins >= 0 && escape_bins < cfg.n_ch && escape_factor >= 0.f, "mt_refine: escape peak (bins %d, factor %g)",
+               escape_bins, (double)escape_factor);
     MT_REQUIRE(!theta_dev || cfg.n_theta == 0 || ld_theta >= n_px, "mt_refine: ld_theta=%lld < n_px", (long long)ld_theta);
     for (int l = 0; l < cfg.n_lines; ++l)
         MT_REQUIRE(lines_host[l].comp >= 0 && lines_host[l].comp < cfg.n_comp && lines_host[l].kind >= MT_LINE_ELEMENT &&
@@ -936,6 +1023,8 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     p.bkg = bkg_dev;
     p.ld_bkg = ld_bkg;
     p.chan_w = chan_weight_dev;
+    p.escape_bins = escape_bins > 0 && escape_factor > 0.f ? escape_bins : 0;
+    p.escape_factor = escape_factor;
     p.spec = spec_dev;
     p.ld_spec = ld_spec;
     p.x = x_dev;
@@ -951,6 +1040,7 @@ extern "C" int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int6
     for (int k = 0; k < cfg.n_theta; ++k) general = general || cfg.theta_id[k] >= MT_THETA_COHERENT_SCT_ENERGY;
     for (int l = 0; l < cfg.n_lines; ++l) general = general || lines_host[l].step > 0.f;
     general = general || chan_weight_dev != nullptr;  // the channel weights live in the GENERAL instantiations
+    general = general || escape_bins > 0;              // ... and so do the escape-peak passes
     const size_t smem = sizeof(float) * (size_t)((cfg.n_ch + 1) & ~1) * (1 + cfg.n_theta) +
                         sizeof(float4) * (size_t)cfg.n_lines * (general ? 4 + cfg.n_theta : 2);
     if (smem > 200 * 1024)

@@ -181,12 +181,15 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
     Returns (theta [len(free), P], loss [P], iterations [P]) on the device."""
     if plan.n_live != len(plan.names):
         raise NotImplementedError("refinement with components that have no open line")
-    # A channel mask (fit_spec's `indices`) enters the kernel as 0 / 1 weights of the residual and derivative rows; the
-    # plan's G^-1 (the fixed amplitude curvature) was built from the masked basis, as the kernel expects.  Escape peaks
-    # are not modelled by mt_refine: the plan's G^-1 then belongs to the escape-augmented basis and the refinement would
-    # silently answer a different problem than the linear fit and the reference's fit_spec(escape_factor=...)
-    if getattr(plan, "escape_factor", 0.0) > 0:
-        raise NotImplementedError("per-pixel refinement with escape peaks (escape_factor > 0)")
+    # A channel mask (fit_spec's `indices`) enters the kernel as 0 / 1 weights of the residual and derivative rows, escape
+    # peaks (escape_factor > 0) as the shifted, scaled copy every column carries (map.py:127-150; the bin shift of the
+    # plan's calibration); the plan's G^-1 (the fixed amplitude curvature) was built from that same masked / augmented basis
+    escape_factor = float(getattr(plan, "escape_factor", 0.0))
+    escape_bins = 0
+    if escape_factor > 0:
+        from mapstorch_b200 import tables
+
+        escape_bins = int(tables.escape_bins(tables.energy_axis(plan.params, plan.er), getattr(plan, "detector_type", "Si")))
     free = list(free)
     unknown = [f for f in free if f not in _native.THETA_IDS]
     if unknown or len(free) > _native.MT_MAX_THETA_REFINE:
@@ -211,7 +214,8 @@ def refine_map(plan, spec2d, x, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bounds=No
         bkg = bkg.float().contiguous()
     _native.call("mt_refine", spec2d.data_ptr(), _native.dtype_code(spec2d.dtype), n_px, spec2d.stride(0),
                  bkg.data_ptr() if bkg is not None else None, bkg.stride(0) if bkg is not None else 0,
-                 plan.chan_mask.data_ptr() if plan.chan_mask is not None else None, ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p), chan_lines.ctypes.data_as(ctypes.c_void_p),
+                 plan.chan_mask.data_ptr() if plan.chan_mask is not None else None, escape_bins, escape_factor,
+                 ctypes.byref(cfg), ctypes.cast(lines, ctypes.c_void_p), chan_lines.ctypes.data_as(ctypes.c_void_p),
                  comp_start.ctypes.data_as(ctypes.c_void_p), comp_lines.ctypes.data_as(ctypes.c_void_p),
                  window.ctypes.data_as(ctypes.c_void_p), comp_order.ctypes.data_as(ctypes.c_void_p),
                  plan._g0inv32.data_ptr(), x.data_ptr(), x.stride(0),

@@ -495,11 +495,12 @@ def gaussian_model_jacobian(params, energy_range, elements_to_fit, amps):
 
 
 def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENERGY_OFFSET", "FWHM_OFFSET"), bkg=None,
-                    indices=None):
+                    indices=None, escape=None):
     """Variable projection in float64: minimise over the free calibration parameters the NNLS
     residual of the spectrum on the Gaussian basis -- the minimiser the reference's
     fit_spec(fitting_params=free, tune_params=True) heads for.  `indices` restricts the objective to those channels
-    of the window, as fit_spec(indices=...) does (opt.py:344-347).  Returns (theta, amplitudes, loss)."""
+    of the window, as fit_spec(indices=...) does (opt.py:344-347); `escape` = (escape_factor, bins) adds every column's
+    detector escape peak, b'(c) = b(c) + factor * b(c + bins) (escape_peak, map.py:127-150).  Returns (theta, amplitudes, loss)."""
     from scipy.optimize import least_squares, nnls
 
     y = np.asarray(spectrum, dtype=np.float64)[energy_range[0]: energy_range[1] + 1]
@@ -515,6 +516,10 @@ def refine_spectrum(spectrum, params, energy_range, elements_to_fit, free=("ENER
         pp = dict(params, **dict(zip(free, theta)))
         # the full path of model_spec: Gaussians, step terms, scatter lines following their parameters
         _, _, B = model_jacobian(pp, energy_range, elements_to_fit, np.ones(n_comp), free=())
+        if escape is not None and escape[1] > 0:
+            shifted = np.zeros_like(B)
+            shifted[: B.shape[0] - escape[1]] = B[escape[1]:] * escape[0]
+            B = B + shifted
         if indices is not None:
             B = B[np.asarray(indices)]
         x, _ = nnls(B, y, maxiter=50 * n_comp)

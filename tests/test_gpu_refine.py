@@ -359,3 +359,42 @@ def test_refinement_with_absent_elements_reaches_the_constrained_minimum():
         mine = np.array([float(maps[n][i]) for n in names])
         assert np.abs(mine - x).max() < 5e-4 * x.max(), i
     assert min(n_zero) >= 3  # the constraint is active in every pixel
+
+
+def test_refinement_with_escape_peaks():
+    """fit_map(escape_factor=..., refine=...): every component carries its detector escape peak (map.py:127-150) inside
+    the per-pixel refinement as well -- model'(c) = model(c) + f * model(c + bins) -- against the float64 variable
+    projection on the same augmented basis; and the escape peaks matter (fitting without them is visibly worse)."""
+    from mapstorch_b200 import opt, tables
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    factor = 0.04
+    rng = np.random.default_rng(33)
+    names = mo.component_names(ELEMS20)
+    bins = tables.escape_bins(tables.energy_axis(p, er), "Si")
+    assert 100 < bins < 400
+    specs = []
+    for i in range(4):
+        shift, widen = rng.uniform(-0.006, 0.006), rng.uniform(0.93, 1.08)
+        pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + shift, FWHM_OFFSET=p["FWHM_OFFSET"] * widen)
+        amps = 10.0 ** rng.uniform(2.0, 3.2, size=len(names))
+        model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+        model = model + mo.escape_peak(model, mo.energy_axis(pp, er), factor, "Si")
+        specs.append(rng.poisson(model).astype(np.float32))
+    y = np.stack(specs)
+    free = ("ENERGY_OFFSET", "FWHM_OFFSET")
+    maps = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, escape_factor=factor, refine=free,
+                       refine_iters=20, device="cpu")
+    plain = opt.fit_map(y, er, ELEMS20, init_param_vals=p, use_snip=False, refine=free, refine_iters=20, device="cpu")
+    for i in range(4):
+        theta, x, loss = mo.refine_spectrum(y[i], p, er, ELEMS20, free=free, escape=(factor, bins))
+        assert abs(float(maps["ENERGY_OFFSET"][i]) - theta[0]) < 1e-5, i
+        assert abs(float(maps["FWHM_OFFSET"][i]) / theta[1] - 1) < 1e-4, i
+        assert float(maps["loss"][i]) <= loss * (1 + 2e-5), i
+        mine = np.array([float(maps[n][i]) for n in names])
+        interior = x > 1e-3 * x.max()
+        assert (np.abs(mine - x)[interior] / x[interior]).max() < 2e-4, i
+        assert float(plain["loss"][i]) > 1.02 * float(maps["loss"][i]), i
