@@ -398,3 +398,46 @@ def test_refinement_with_escape_peaks():
         interior = x > 1e-3 * x.max()
         assert (np.abs(mine - x)[interior] / x[interior]).max() < 2e-4, i
         assert float(plain["loss"][i]) > 1.02 * float(maps["loss"][i]), i
+
+
+def test_fit_spec_tuned_on_a_channel_subset_and_with_escape_peaks():
+    """fit_spec(tune_params=True, indices=...) and (..., escape_factor=...): the global calibration fit through the
+    one-launch evaluation (mt_spec_solve with a channel list / the escape-augmented basis) against the float64 variable
+    projection on the same channels / basis; garbage outside the selected channels must not matter."""
+    from mapstorch_b200 import opt, tables
+    from mapstorch_b200.default import default_param_vals
+    from oracle import maps_oracle as mo
+
+    p = dict(default_param_vals, COHERENT_SCT_ENERGY=12.0)
+    er = (0, 2047)
+    rng = np.random.default_rng(41)
+    names = mo.component_names(ELEMS20)
+    free = ["ENERGY_OFFSET", "FWHM_OFFSET"]
+    pp = dict(p, ENERGY_OFFSET=p["ENERGY_OFFSET"] + 0.004, FWHM_OFFSET=p["FWHM_OFFSET"] * 1.05)
+    amps = 10.0 ** rng.uniform(3.0, 4.2, size=len(names))
+    model, _, _, _ = mo.gaussian_model_jacobian(pp, er, ELEMS20, amps)
+    # (1) channel subset
+    idx = np.nonzero((np.arange(2048) // 48) % 3 != 1)[0]
+    spec = rng.poisson(model).astype(np.float32)
+    spec[(np.arange(2048) // 48) % 3 == 1] += 5000.0
+    tensors, spec_fit, bkg, trace = opt.fit_spec(spec, er, ELEMS20, fitting_params=free, init_param_vals=p, tune_params=True,
+                                                 use_snip=False, indices=idx, n_iter=40)
+    theta, x, loss = mo.refine_spectrum(spec, p, er, ELEMS20, free=tuple(free), indices=idx)
+    # (the basis is evaluated in fp32: the objective agrees with the float64 oracle's to ~1e-5 relative)
+    assert trace[-1] <= loss * (1 + 3e-5) and trace[-1] < 0.5 * trace[0]
+    assert abs(float(tensors["ENERGY_OFFSET"].detach()) - theta[0]) < 2e-5
+    assert abs(float(tensors["FWHM_OFFSET"].detach()) / theta[1] - 1) < 2e-4
+    mine = np.array([10.0 ** float(tensors[n].detach()) for n in names])
+    interior = x > 1e-3 * x.max()
+    # (components whose peaks are partly cut away by the selection follow the calibration steeply: 5e-4 measured)
+    assert (np.abs(mine - x)[interior] / x[interior]).max() < 1e-3
+    # (2) escape peaks
+    factor = 0.04
+    bins = tables.escape_bins(tables.energy_axis(p, er), "Si")
+    spec = rng.poisson(model + mo.escape_peak(model, mo.energy_axis(pp, er), factor, "Si")).astype(np.float32)
+    tensors, spec_fit, bkg, trace = opt.fit_spec(spec, er, ELEMS20, fitting_params=free, init_param_vals=p, tune_params=True,
+                                                 use_snip=False, escape_factor=factor, n_iter=40)
+    theta, x, loss = mo.refine_spectrum(spec, p, er, ELEMS20, free=tuple(free), escape=(factor, bins))
+    assert trace[-1] <= loss * (1 + 3e-5)
+    assert abs(float(tensors["ENERGY_OFFSET"].detach()) - theta[0]) < 2e-5
+    assert abs(float(tensors["FWHM_OFFSET"].detach()) / theta[1] - 1) < 2e-4
