@@ -13,6 +13,8 @@
 //   B  block principal pivoting (the rule of mt_nnls.cu) on the normal equations, every pivot step a CTA-wide
 //      right-looking Cholesky of G_FF in shared memory + two triangular solves + the duals of the zero set;
 //   C  residual vector, its weighted form (what Levenberg-Marquardt differences), the objective and the penalty entries.
+#include <algorithm>
+
 #include "mt_common.cuh"
 
 namespace {
@@ -33,6 +35,8 @@ struct SpecArgs {
     double l1_lambda;
     int robust, n_elements;
     double *x, *res, *vec, *stats;
+    double *partial;  // [n_prob][slices][E * E + E] Gram / right-hand-side partial sums (slices > 1)
+    int *arrived;     // [n_prob] CTAs of the problem that have delivered their partial sums
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -55,7 +59,7 @@ __device__ double block_sum(double v, double *scratch) {
 __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs a) {
     extern __shared__ double smem[];
     const int E = a.n_comp, K = a.n_k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int prob = blockIdx.x;
+    const int prob = blockIdx.y, n_slice = gridDim.x, slice = blockIdx.x;
     double *G = smem;                 // [E][E] Gram matrix (weighted), symmetric by construction
     double *W = G + E * E;            // [E][E] Cholesky workspace of the free block
     double *rhs = W + E * E;          // [E]
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
     float *tm = reinterpret_cast<float *>(red + kSpecThreads / 32);  // [K] target y - bkg (an fp32 difference, as the host code forms it)
     int *idx = reinterpret_cast<int *>(tm + ((K + 1) & ~1));         // [E] members of the free set
     unsigned char *free_ = reinterpret_cast<unsigned char *>(idx + E);  // [E] 1 free, 0 zero set, 2 dead (empty column)
-    __shared__ int s_n, s_last_bad;
+    __shared__ int s_n, s_last_bad, s_is_last;
 
     const float *B = a.basis + (long long)prob * a.prob_stride_b;
     const float *bkg = a.bkg ? a.bkg + (long long)prob * a.ld_bkg : nullptr;
@@ -96,6 +100,11 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
     {
         const int nb = (E + 1 + 3) / 4;  // 4-row blocks over the E + 1 rows
         const int n_blocks = nb * (nb + 1) / 2;
+        // wide problems are cut into channel slices, one CTA each (grid.x): the partial sums go to global memory and the
+        // last CTA to arrive adds them up in slice order (deterministic) and carries on alone
+        const int per = ((K + n_slice - 1) / n_slice + 31) & ~31;
+        const int k_lo = min(K, slice * per), k_hi = min(K, k_lo + per);
+        double *mine = n_slice > 1 ? a.partial + ((long long)prob * n_slice + slice) * (E * E + E) : nullptr;
         for (int blk = warp; blk < n_blocks; blk += kSpecThreads / 32) {
             int bi = 0, rem = blk;  // upper triangle, row-major: (bi, bj >= bi)
             while (rem >= nb - bi) {
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
-            for (int k = lane; k < K; k += 32) {
+            for (int k = k_lo + lane; k < k_hi; k += 32) {
                 const int c = a.chan_idx ? a.chan_idx[k] : k;
                 const double w = wts ? wts[k] : 1.0;
                 const double t = (double)tm[k];
@@ -131,7 +140,9 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
                     const double sum = warp_sum(acc[p][q]);
                     const int r = r0 + p, s = s0 + q;
                     if (lane == 0 && r < E && s >= r) {  // upper triangle only: both halves get the same number
-                        if (s < E) {
+                        if (mine != nullptr) {
+                            if (s <= E) mine[s < E ? r * E + s : E * E + r] = sum;
+                        } else if (s < E) {
                             G[r * E + s] = sum;
                             G[s * E + r] = sum;
                         } else if (s == E) {
@@ -142,6 +153,29 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
         }
     }
     __syncthreads();
+    if (n_slice > 1) {
+        if (tid == 0) {
+            __threadfence();
+            s_is_last = atomicAdd(a.arrived + prob, 1) == n_slice - 1;
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        const double *part = a.partial + (long long)prob * n_slice * (E * E + E);
+        for (int i = tid; i < E * E + E; i += kSpecThreads) {
+            const int r = i < E * E ? i / E : i - E * E, c = i < E * E ? i - r * E : E;
+            if (c < r) continue;  // the slices wrote the upper triangle only
+            double sum = 0.0;
+            for (int q = 0; q < n_slice; ++q) sum += __ldcg(part + (long long)q * (E * E + E) + i);
+            if (c < E) {
+                G[r * E + c] = sum;
+                G[c * E + r] = sum;
+            } else {
+                rhs[r] = sum - shift;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- phase B: block principal pivoting.  Dead components (empty columns) never enter.
     double gmax = 0.0;
@@ -301,7 +335,7 @@ extern "C" int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_
     MT_REQUIRE(basis_dev && y_dev && x_dev && res_dev && vec_dev && stats_dev, "mt_spec_solve: null pointer");
     MT_REQUIRE(n_comp >= 1 && n_comp <= kSpecMaxComp, "mt_spec_solve: n_comp %d outside [1, %d]", n_comp, kSpecMaxComp);
     MT_REQUIRE(n_k >= 1 && n_k <= kSpecMaxCh, "mt_spec_solve: %d fitted channels outside [1, %d]", n_k, kSpecMaxCh);
-    MT_REQUIRE(n_prob >= 1 && n_prob <= 65535, "mt_spec_solve: n_prob %d", n_prob);
+    MT_REQUIRE(n_prob >= 1 && n_prob <= 65535, "mt_spec_solve: n_prob %d", n_prob);  // grid.y
     MT_REQUIRE(ld_b >= 1 && ld_bkg >= 0 && ld_w >= 0, "mt_spec_solve: negative pitch");
     SpecArgs a;
     a.basis = basis_dev;
@@ -332,7 +366,22 @@ extern "C" int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_
         MT_CUDA_TRY(cudaFuncSetAttribute(spec_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) smem_set[dev] = (int)smem;
     }
-    spec_solve_kernel<<<(unsigned)n_prob, kSpecThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    // channel slices per problem: one per ~20 k (4 x 4 block, channel) products of the Gram phase, at most 32
+    const long long nb = (n_comp + 1 + 3) / 4, work = nb * (nb + 1) / 2 * (long long)n_k;
+    int n_slice = (int)std::min<long long>(32, std::max<long long>(1, work / 20000));
+    n_slice = std::min(n_slice, std::max(1, n_k / 64));
+    mt::StreamScratch scratch;
+    a.partial = nullptr;
+    a.arrived = nullptr;
+    if (n_slice > 1) {
+        const size_t part_bytes = sizeof(double) * (size_t)n_prob * n_slice * (E * E + E);
+        const size_t count_bytes = (sizeof(int) * (size_t)n_prob + 15) & ~(size_t)15;
+        MT_CUDA_TRY(scratch.alloc(part_bytes + count_bytes, static_cast<cudaStream_t>(stream)));
+        a.partial = reinterpret_cast<double *>(scratch.ptr);
+        a.arrived = reinterpret_cast<int *>(scratch.ptr + part_bytes);
+        MT_CUDA_TRY(cudaMemsetAsync(a.arrived, 0, count_bytes, static_cast<cudaStream_t>(stream)));
+    }
+    spec_solve_kernel<<<dim3((unsigned)n_slice, (unsigned)n_prob), kSpecThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     MT_CUDA_TRY(cudaGetLastError());
     return MT_OK;
 }
