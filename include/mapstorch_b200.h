@@ -381,13 +381,16 @@ int mt_refine(const void *spec_dev, int32_t dtype, int64_t n_px, int64_t ld_spec
  * sqrt(w) * res followed by the penalty entries sqrt((robust ? 2 : 1) * c * x); stats_dev [n_prob][8] = { |vec|^2,
  * objective (sum res^2 or sum |res|, + c sum x), c, flag (0 ok, 1 singular pivot block: clamped unconstrained solution,
  * 2 Gram matrix of the live components singular: x = 0), pivot steps, sum res^2, sum |res|, sum x }.
- * n_comp <= MT_SPEC_MAX_COMP, n_k <= MT_SPEC_MAX_CH.  One launch, one CTA per problem, no host synchronisation. */
+ * free_set_dev (optional, [n_prob][n_comp] bytes, in / out): the partition the pivoting starts from (1 free, 0 held at zero,
+ * any other value: no hint) and, on return, the final one (2 = component without signal) -- the warm start between
+ * neighbouring trial points.  n_comp <= MT_SPEC_MAX_COMP, n_k <= MT_SPEC_MAX_CH.  One launch, no host synchronisation. */
 #define MT_SPEC_MAX_COMP 96
 #define MT_SPEC_MAX_CH 8192
 int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_stride_b, int32_t n_comp, const float *y_dev,
                   const float *bkg_dev, int64_t ld_bkg, const int32_t *chan_idx_dev, int32_t n_k,
                   const double *weights_dev, int64_t ld_w, double l1_lambda, int32_t robust, int32_t n_elements,
-                  double *x_dev, double *res_dev, double *vec_dev, double *stats_dev, int32_t n_prob, void *stream);
+                  double *x_dev, double *res_dev, double *vec_dev, double *stats_dev, uint8_t *free_set_dev, int32_t n_prob,
+                  void *stream);
 
 #ifdef __cplusplus
 }

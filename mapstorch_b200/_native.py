@@ -104,7 +104,7 @@ SIGNATURES = {
     "mt_refine": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                   _vp, _vp, _vp],
     "mt_spec_solve": [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _vp,
-                      _i32, _vp],
+                      _vp, _i32, _vp],
 }
 
 

@@ -37,6 +37,7 @@ struct SpecArgs {
     double *x, *res, *vec, *stats;
     double *partial;  // [n_prob][slices][E * E + E] Gram / right-hand-side partial sums (slices > 1)
     int *arrived;     // [n_prob] CTAs of the problem that have delivered their partial sums
+    unsigned char *free_set;  // optional [n_prob][E], in: starting partition (1 free, 0 zero, other: no hint), out: final one
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -180,8 +181,14 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
     // ---- phase B: block principal pivoting.  Dead components (empty columns) never enter.
     double gmax = 0.0;
     for (int e = 0; e < E; ++e) gmax = fmax(gmax, G[e * E + e]);
+    // Starting partition: everything free, or the partition the caller hands in -- the final one of a neighbouring trial
+    // point of the Levenberg-Marquardt loop, which is nearly always already right (a 93-component problem took 33 pivot
+    // steps from scratch, ~0.1 ms each).
+    unsigned char *hint = a.free_set ? a.free_set + (long long)prob * E : nullptr;
+    const bool my_zero = tid < E && hint != nullptr && hint[tid] == 0;
+    bool warm = __syncthreads_or(my_zero) != 0;
     if (tid < E) {
-        free_[tid] = G[tid * E + tid] > 0.0 ? 1 : 2;
+        free_[tid] = G[tid * E + tid] > 0.0 ? (my_zero ? 0 : 1) : 2;
         xs[tid] = 0.0;
         xu[tid] = 0.0;
     }
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
     double tol_x = 0.0, tol_y = 0.0;
     const int max_iter = 8 * E + 16;
     for (int iter = 0; iter < max_iter; ++iter) {
-        iters = iter + 1;
+        ++iters;
         if (tid == 0) {
             int n = 0;
             for (int e = 0; e < E; ++e)
@@ -219,12 +226,23 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
             __syncthreads();
             for (int i = j + tid; i < n; i += kSpecThreads) W[i * n + j] = (i == j) ? d : W[i * n + j] / d;
             __syncthreads();
-            const int m = n - j - 1;
-            for (int t = tid; t < m * m; t += kSpecThreads) {
-                const int i = j + 1 + t / m, k = j + 1 + t % m;
-                if (k <= i) W[i * n + k] = fma(-W[i * n + j], W[k * n + j], W[i * n + k]);
+            // trailing update of the lower triangle: a warp per row, lanes along the row
+            for (int i = j + 1 + warp; i < n; i += kSpecThreads / 32) {
+                const double lij = W[i * n + j];
+                for (int k = j + 1 + lane; k <= i; k += 32) W[i * n + k] = fma(-lij, W[k * n + j], W[i * n + k]);
             }
             __syncthreads();
+        }
+        if (!ok && warm) {
+            // the handed-in partition does not fit this problem: start over from the full live set
+            __syncthreads();
+            if (tid < E && free_[tid] != 2) free_[tid] = 1;
+            warm = false;
+            ninf = E + 1;
+            backup = 3;
+            iter = -1;
+            __syncthreads();
+            continue;
         }
         if (!ok) {
             // numerically singular subset (strongly overlapping components).  On the first step nothing has been solved
@@ -260,8 +278,9 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
         }
         __syncthreads();
         if (iter == 0) {
-            double xmax = 0.0;
-            for (int e = 0; e < E; ++e) xmax = fmax(xmax, fabs(xs[e]));
+            double xmax = 0.0;  // scale of the amplitudes (free entries: with a handed-in partition the others hold duals)
+            for (int e = 0; e < E; ++e)
+                if (free_[e] == 1) xmax = fmax(xmax, fabs(xs[e]));
             tol_x = 1e-12 * xmax;
             tol_y = 1e-12 * xmax * gmax;
             if (tid < E) xu[tid] = xs[tid];
@@ -284,6 +303,7 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
         if (bad && (flip_all || tid == s_last_bad)) free_[tid] = free_[tid] == 1 ? 0 : 1;
         __syncthreads();
     }
+    if (tid < E && hint != nullptr) hint[tid] = free_[tid];
     if (tid < E) {
         const double out = (free_[tid] == 1 && flag != 2) ? fmax(xs[tid], 0.0) : 0.0;
         xs[tid] = out;
@@ -329,8 +349,8 @@ __global__ void __launch_bounds__(kSpecThreads) spec_solve_kernel(const SpecArgs
 extern "C" int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_stride_b, int32_t n_comp, const float *y_dev,
                              const float *bkg_dev, int64_t ld_bkg, const int32_t *chan_idx_dev, int32_t n_k,
                              const double *weights_dev, int64_t ld_w, double l1_lambda, int32_t robust, int32_t n_elements,
-                             double *x_dev, double *res_dev, double *vec_dev, double *stats_dev, int32_t n_prob,
-                             void *stream) {
+                             double *x_dev, double *res_dev, double *vec_dev, double *stats_dev, uint8_t *free_set_dev,
+                             int32_t n_prob, void *stream) {
     if (int rc = mt::require_sm100()) return rc;
     MT_REQUIRE(basis_dev && y_dev && x_dev && res_dev && vec_dev && stats_dev, "mt_spec_solve: null pointer");
     MT_REQUIRE(n_comp >= 1 && n_comp <= kSpecMaxComp, "mt_spec_solve: n_comp %d outside [1, %d]", n_comp, kSpecMaxComp);
@@ -356,6 +376,7 @@ extern "C" int mt_spec_solve(const float *basis_dev, int64_t ld_b, int64_t prob_
     a.res = res_dev;
     a.vec = vec_dev;
     a.stats = stats_dev;
+    a.free_set = free_set_dev;
     const size_t E = (size_t)n_comp;
     const size_t smem = sizeof(double) * (2 * E * E + 5 * E + kSpecThreads / 32) + sizeof(float) * (((size_t)n_k + 1) & ~(size_t)1) +
                         sizeof(int) * E + ((E + 7) & ~(size_t)7);

@@ -273,6 +273,7 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
     idx32 = None if idx is None else idx.to(torch.int32).contiguous()
     n_k = y.numel() if idx is None else int(idx.numel())
     no_bkg = torch.zeros_like(y)
+    warm = {}
 
     def dense(info):
         """fp64 basis and target on the fitted channels (the analytic Jacobian and the final polish want them)."""
@@ -304,8 +305,10 @@ def fit_spec_global(int_spec, energy_range, elements_to_fit, fitting_params, ini
         if basis.shape[0] <= _native.MT_SPEC_MAX_COMP and n_k <= _native.MT_SPEC_MAX_CH:
             # one launch (csrc/mt_spec.cu): Gram matrix, non-negative solve, residual vector, objective; one 64-byte
             # read-back per trial point
+            if warm.get("n") != basis.shape[0]:  # the active set of the last trial point starts the next solve
+                warm["n"], warm["set"] = basis.shape[0], torch.full((1, basis.shape[0]), 255, dtype=torch.uint8, device="cuda")
             x, res, vec, stats = robust.spec_solve(basis, y, bkg if use_snip else None, idx32, w, l1_lambda, robust_loss,
-                                                   len(names))
+                                                   len(names), free_set=warm["set"])
             if defer is not None:
                 defer.append(stats)
                 return (vec[0] if l1_lambda > 0 else vec[0, :n_k]), None

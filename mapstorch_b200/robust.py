@@ -45,12 +45,13 @@ def weighted_nnls(bm, tm, weights=None, shift=0.0):
     return x
 
 
-def spec_solve(basis, y, bkg=None, chan_idx=None, weights=None, l1_lambda=0.0, robust=False, n_elements=1):
+def spec_solve(basis, y, bkg=None, chan_idx=None, weights=None, l1_lambda=0.0, robust=False, n_elements=1, free_set=None):
     """The amplitude solve of one spectrum (or a batch of trial points) in ONE launch of mt_spec_solve
     (csrc/mt_spec.cu): Gram matrix, non-negative solve, residual vector and objective, no host synchronisation.
 
     basis fp32 CUDA [E, C] or [N, E, C]; y fp32 CUDA [C]; bkg fp32 CUDA [C] / [N, C] / None; chan_idx int32 CUDA [K] or
-    None (all channels); weights fp64 CUDA [K] / [N, K] or None.  Returns (x [N, E], res [N, K], vec [N, K + E],
+    None (all channels); weights fp64 CUDA [K] / [N, K] or None; free_set uint8 CUDA [N, E] or None: starting partition of
+    the pivoting, overwritten with the final one (warm start between neighbouring trial points).  Returns (x [N, E], res [N, K], vec [N, K + E],
     stats [N, 8]) as fp64 CUDA tensors, see include/mapstorch_b200.h."""
     b3 = basis if basis.dim() == 3 else basis.unsqueeze(0)
     if b3.stride(2) != 1 or b3.stride(1) < b3.shape[2]:
@@ -78,8 +79,8 @@ def spec_solve(basis, y, bkg=None, chan_idx=None, weights=None, l1_lambda=0.0, r
                  bkg.data_ptr() if bkg is not None else None, ld_bkg,
                  chan_idx.data_ptr() if chan_idx is not None else None, n_k,
                  weights.data_ptr() if weights is not None else None, ld_w, float(l1_lambda), int(bool(robust)),
-                 int(n_elements), x.data_ptr(), res.data_ptr(), vec.data_ptr(), stats.data_ptr(), n_prob,
-                 _native.stream_ptr())
+                 int(n_elements), x.data_ptr(), res.data_ptr(), vec.data_ptr(), stats.data_ptr(),
+                 free_set.data_ptr() if free_set is not None else None, n_prob, _native.stream_ptr())
     return x, res, vec, stats
 
 

@@ -154,3 +154,31 @@ def test_singular_gram_matrix_is_reported_not_returned():
 
     with pytest.raises(_native.NativeError):
         run(np.zeros((97, 64), np.float32), np.zeros(64, np.float32))
+
+
+def test_warm_started_pivoting_gives_the_same_answer_in_fewer_steps():
+    """free_set (in / out): the partition a neighbouring trial point ended with starts the next solve.  Whatever is
+    handed in -- the right partition, an empty one, another problem's, garbage -- the solution is the same to the bit
+    (the final partition, hence the final factorisation, is the same) and the right one needs a single pivot step."""
+    from mapstorch_b200 import robust as rb
+
+    basis, y, bkg = make_problem(40, 2048, seed=12)
+    b, yy, bb = (torch.as_tensor(a, device="cuda") for a in (basis, y, bkg))
+    cold_set = torch.full((1, 40), 255, dtype=torch.uint8, device="cuda")
+    x0, r0, v0, s0 = rb.spec_solve(b, yy, bb, free_set=cold_set)
+    ref = rb.spec_solve(b, yy, bb)
+    assert torch.equal(x0, ref[0]) and int(s0[0, 4]) == int(ref[3][0, 4]) and int(s0[0, 4]) >= 2
+    assert set(cold_set.unique().tolist()) <= {0, 1, 2} and int((cold_set == 0).sum()) >= 1
+    assert torch.equal((cold_set[0] == 1), x0[0] > 0) or int(((cold_set[0] == 1) != (x0[0] > 0)).sum()) <= 1
+    warm_set = cold_set.clone()
+    x1, _, _, s1 = rb.spec_solve(b, yy, bb, free_set=warm_set)
+    assert torch.equal(x1, x0) and int(s1[0, 4]) == 1 and torch.equal(warm_set, cold_set)
+    other = make_problem(40, 2048, seed=13)
+    wrong = torch.full((1, 40), 255, dtype=torch.uint8, device="cuda")
+    rb.spec_solve(torch.as_tensor(other[0], device="cuda"), torch.as_tensor(other[1], device="cuda"), None, free_set=wrong)
+    for start in (torch.zeros((1, 40), dtype=torch.uint8, device="cuda"), wrong,
+                  torch.randint(0, 2, (1, 40), dtype=torch.uint8, device="cuda")):
+        xs, _, _, ss = rb.spec_solve(b, yy, bb, free_set=start)
+        assert float(ss[0, 3]) == 0.0
+        np.testing.assert_allclose(xs.cpu().numpy(), x0.cpu().numpy(), rtol=0, atol=1e-9 * float(x0.max()))
+        assert torch.equal(start, cold_set)
