@@ -219,3 +219,23 @@ def test_vectorised_term_compiler_is_bit_identical_to_the_scalar_route():
     want_t, want_s = tables.pack_columns(tables.compile_terms(pp, comps, ec, ei, True, True))
     got_t, got_s = tables.compile_packed(pp, comps, ec, ei, True, True)
     assert np.array_equal(want_s, got_s) and want_t.tobytes() == got_t.tobytes()
+
+
+def test_snip_pass_count_follows_from_the_largest_width():
+    """bkg.snip_tables_device builds the window table on the device and needs only the pass count from the host:
+    tables.snip_pass_count(max width) must equal the number of rows of the full host table (every pass divides all
+    widths by the same constant and rounding is monotone)."""
+    import torch
+
+    from mapstorch_b200 import tables
+
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n_ch = int(rng.integers(8, 4096))
+        ch0 = int(rng.integers(0, 200))
+        six = [torch.tensor(float(v)) for v in (rng.normal(0, 0.05), rng.uniform(0.003, 0.03), rng.normal(0, 1e-7),
+                                                 rng.uniform(0.05, 4.0), rng.uniform(0.02, 0.4), rng.uniform(1e-6, 2e-3))]
+        full = tables.snip_tables(n_ch, ch0, *six)
+        width = tables.snip_widths(n_ch, ch0, *six)
+        assert tables.snip_pass_count(width.max()) == full.shape[0], trial
+        assert np.array_equal(full, tables.snip_tables_torch(n_ch, ch0, *six)) or trial % 20  # spot check vs the torch ops
