@@ -604,6 +604,7 @@ refine_kernel(const RefParams p) {
         }
 
         // ---- C: damped Gauss-Newton step through the Schur complement on theta ----------------
+        bool clamped_here = false;  // does this thread see a component held at zero by its gradient?
         for (int i = tid; i < E * (NT + 1); i += kRefThreads) {
             const int e = i / (NT + 1), k = i % (NT + 1);
             const float *gi = p.g0inv + (long long)e * E;
@@ -611,12 +612,14 @@ refine_kernel(const RefParams p) {
             if (k == NT) {
                 for (int j = 0; j < E; ++j) s += __ldg(gi + j) * gx[j];
                 w_s[e] = s;
+                clamped_here = clamped_here || (xs[e] <= 0.f && gx[e] > 0.f);
             } else {
                 for (int j = 0; j < E; ++j) s += __ldg(gi + j) * hthx[k][j];
                 t1[e][k] = s;
             }
         }
-        __syncthreads();
+        // (the barrier this loop needs anyway also tells every thread whether any component is clamped)
+        const bool any_clamped = __syncthreads_or(clamped_here) != 0;
         // ---- active set: components at zero whose gradient keeps them there -----------------------------------------
         // w_s and t1 were formed with the inverse of the FULL Gram matrix, i.e. they describe a step in which a clamped
         // amplitude is free to go negative; projecting that step afterwards biases every other component and the
@@ -625,7 +628,7 @@ refine_kernel(const RefParams p) {
         // eliminating the active rows:  (G_FF)^-1 = H_FF - H_FA (H_AA)^-1 H_AF,  i.e.  V <- V - H[:, A] (H_AA)^-1 V[A]
         // for the NT + 1 vectors V = (t1, w_s).  A = { e : x_e = 0 and (B^T r)_e > 0 }; the scratch is the residual /
         // derivative rows, dead until the next evaluation.  Pixels with an empty A (the common case) skip all of it.
-        {
+        if (any_clamped) {
             __shared__ int s_na;
             __shared__ unsigned char s_act[kMaxComp], s_in[kMaxComp];
             constexpr int NV = NT + 1;
